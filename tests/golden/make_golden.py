@@ -1,0 +1,125 @@
+"""Generate tests/golden/*.npz by EXECUTING the unmodified reference (/root/reference).
+
+Run here (the build container) only:  python tests/golden/make_golden.py
+The GPU box has no reference tree; it consumes the committed .npz files.
+Recipe: SURVEY.md Appendix B via oracle/ref_harness.py.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+
+from oracle import ref_harness as rh  # noqa: E402
+from poccala_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+UNITS = ["a", "b", "c"]
+MIX = 4
+
+
+def estep_golden():
+    truth, init, _, _ = synth.make_corpus(1, 30, 3, 3, MIX, cfg_seed=1)
+    mean, var, alpha = init
+    label_ids = [np.array([0]), np.array([1, 2]), np.array([0, 1, 0]), np.array([2, 2, 1, 0])]
+    lens = [24, 17, 40, 33]
+    utts = [synth.make_utterance(l, t, truth, 4242 + i) for i, (l, t) in enumerate(zip(label_ids, lens))]
+    H = rh.Harness(UNITS, MIX)
+    params = {u: [(mean[i, r], var[i, r], alpha[i, r]) for r in range(3)] for i, u in enumerate(UNITS)}
+    out = dict(mean=mean, var=var, alpha=alpha, n_utt=len(utts))
+    for k, (lab, X) in enumerate(zip(label_ids, utts)):
+        label = [UNITS[i] for i in lab]
+        r = H.estep_in_memory(label, X, params)
+        out[f"u{k}_label"] = lab
+        out[f"u{k}_X"] = X
+        for key in ("A", "B", "alpha", "beta", "ksai", "gamma", "pi_next"):
+            out[f"u{k}_{key}"] = np.array(r[key])
+        for p, h in enumerate(r["hmm_list"]):
+            out[f"u{k}_p{p}_ksai_acc"] = np.array(h.ksai_acc)
+            out[f"u{k}_p{p}_gamma_acc"] = np.array(h.gamma_acc)
+            for gi, g in enumerate(h.profunction[1:-1]):
+                out[f"u{k}_p{p}_g{gi}_acc"] = np.array(g.acc)
+                out[f"u{k}_p{p}_g{gi}_alpha_acc"] = np.array(g.alpha_acc)
+                out[f"u{k}_p{p}_g{gi}_mean_acc"] = np.array(g.mean_acc)
+                out[f"u{k}_p{p}_g{gi}_cov_acc"] = np.array(g._GMM__covariance_acc)
+        sc, path = H.viterbi(r["states"], r["A"], r["B"], r["pi0"])
+        out[f"u{k}_vit_score"] = sc
+        out[f"u{k}_vit_path"] = path
+        _, lab_path = H.viterbi_labels(r["states"], r["A"], r["B"], r["pi0"])
+        out[f"u{k}_vit_units"] = np.array([UNITS.index(x) for x in lab_path])
+    # one full file-based EM iteration through the reference's own code path (two rounds)
+    H2 = rh.Harness(UNITS, MIX)
+    new = H2.file_based_iteration(params, [([UNITS[i] for i in l], X) for l, X in zip(label_ids, utts)], 1e-6)
+    out["it1_transmat"] = np.stack([new[u]["transmat"] for u in UNITS])
+    out["it1_mean"] = np.stack([np.stack([g["mean"] for g in new[u]["gmms"]]) for u in UNITS])
+    out["it1_var"] = np.stack([np.stack([g["var"] for g in new[u]["gmms"]]) for u in UNITS])
+    out["it1_alpha"] = np.stack([np.stack([g["alpha"] for g in new[u]["gmms"]]) for u in UNITS])
+    np.savez_compressed(os.path.join(OUT, "estep_small.npz"), **out)
+    print("estep_small.npz written")
+
+
+def viterbi_ties_golden():
+    """Integer-valued emissions force exact ties; the reference picks the lower state index."""
+    H = rh.Harness(UNITS, MIX)
+    rng = np.random.default_rng(99)
+    out = {}
+    for k, (L, T) in enumerate([(1, 6), (2, 12), (4, 25), (3, 1)]):
+        N = 3 * L + 2
+        A = np.zeros((N, N))
+        A[0, 1] = 1.0
+        for j in range(1, N - 1):
+            A[j, j] = 0.5
+            A[j, j + 1] = 0.5
+        B = rng.integers(-3, 1, size=(N, T)).astype(np.float64)
+        B[0] = 0.0
+        B[-1] = -np.inf
+        pi = np.ones(N) / N
+        states = {i: "a" for i in range(N)}
+        sc, path = H.viterbi(states, A, B, pi)
+        out[f"v{k}_A"] = A
+        out[f"v{k}_B"] = B
+        out[f"v{k}_score"] = sc
+        out[f"v{k}_path"] = path
+    out["n"] = 4
+    np.savez_compressed(os.path.join(OUT, "viterbi_ties.npz"), **out)
+    print("viterbi_ties.npz written")
+
+
+def kmeans_golden():
+    H = rh.Harness(UNITS, MIX)
+    out = {}
+    cases = [(60, 2, 5, 3), (150, 4, 39, 11), (200, 5, 39, 12345), (40, 1, 39, 7)]
+    for k, (n, K, D, seed) in enumerate(cases):
+        rng = np.random.default_rng(seed)
+        centers = rng.normal(0, 3, size=(max(K, 2), D))
+        data = centers[rng.integers(0, max(K, 2), size=n)] + rng.normal(size=(n, D))
+        mean, cov, alpha, clustered = H.kmeans(list(data), K, seed)
+        members = []
+        for cl in clustered:
+            idx = []
+            for p in cl:
+                hit = np.where((data == p).all(axis=1))[0]
+                idx.append(int(hit[0]))
+            members.append(idx)
+        out[f"k{k}_data"] = data
+        out[f"k{k}_K"] = K
+        out[f"k{k}_seed"] = seed
+        out[f"k{k}_mean"] = mean
+        out[f"k{k}_var"] = np.stack([np.diag(c) for c in cov])
+        out[f"k{k}_alpha"] = np.array(alpha)
+        out[f"k{k}_sizes"] = np.array([len(m) for m in members])
+        out[f"k{k}_members"] = np.concatenate([np.array(m, dtype=np.int64) for m in members])
+    out["n"] = len(cases)
+    np.savez_compressed(os.path.join(OUT, "kmeans_small.npz"), **out)
+    print("kmeans_small.npz written")
+
+
+if __name__ == "__main__":
+    assert rh.available(), "needs /root/reference"
+    estep_golden()
+    viterbi_ties_golden()
+    kmeans_golden()
