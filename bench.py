@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: EM frames/sec (GMM score + forward-backward + accumulate [+ allreduce] +
+M-step) on BASELINE.json configs[1] per GPU: Mandarin initial/final unit set (57 units), 3-state
+HMMs, 16-mix GMMs, 1k synthetic utterances x 300 frames x 10 units, one embedded Baum-Welch
+iteration per step.  Weak scaling: every rank owns its own 1k utterances; the only exchange step
+is the NCCL allreduce of the accumulators.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same iteration
+through the host-buffer C-ABI entry point (pc_em_iteration_host) with pinned host inputs.
+`--impl reference` times the CPU port of the reference (oracle/ref_port.py, the reference's own
+cost structure: /root/reference does not exist on the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_UNITS, N_INITIALS, MIX, N_UTT, T, L, DIM = 57, 22, 16, 1000, 300, 10, 39
+WORKLOAD = "cfg2: IF units(57) x 3 states x 16-mix, 1000 utt x 300 frames x 10 units per GPU, 1 EM iteration/step"
+METRIC = "EM frames/sec (GMM score+fwd-bwd+accum)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+_CPU = {}
+
+
+def _cpu_init(seed):
+    from oracle import ref_port as rp
+    from poccala_b200 import synth
+
+    truth = synth.make_truth(N_UNITS, MIX, 1000 * seed + 7)
+    init = synth.perturb(*truth, seed=1000 * seed + 11)
+    names = [str(i) for i in range(N_UNITS)]
+    units = {}
+    for i, u in enumerate(names):
+        d = rp.new_unit(5, MIX, DIM)
+        for r, g in enumerate(d["gmms"]):
+            g["mean"], g["var"], g["alpha"] = init[0][i, r].copy(), init[1][i, r].copy(), init[2][i, r].copy()
+        units[u] = d
+    _CPU.update(rp=rp, synth=synth, truth=truth, units=units, names=names,
+                labels=synth.random_labels(N_UTT, L, N_UNITS, 1000 * seed + 17, N_INITIALS), seed=seed)
+
+
+def _cpu_task(i):
+    rp, synth = _CPU["rp"], _CPU["synth"]
+    lab = _CPU["labels"][i % N_UTT]
+    X = synth.make_utterance(lab, T, _CPU["truth"], 1000 * _CPU["seed"] + 100 + i)
+    t0 = time.perf_counter()
+    r = rp.estep_utterance(_CPU["units"], [_CPU["names"][k] for k in lab], X)
+    return time.perf_counter() - t0, float(r["logp"])
+
+
+def cpu_arm(n_utt_sample, cores, seed=2, steps=1):
+    """E-step of the reference's CPU path on `n_utt_sample` utterances of the bench workload per
+    step, one utterance per task on `cores` processes (AcousticModel.py:861-870).
+    Returns (frames/s over all steps, [wall seconds per step])."""
+    ctx = mp.get_context("spawn")
+    walls = []
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(seed,)) as pool:
+        pool.map(_cpu_task, range(cores))  # warm-up: imports, page-in (1 utterance per core)
+        for k in range(steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_task, range(k * n_utt_sample, (k + 1) * n_utt_sample), chunksize=1)
+            walls.append(time.perf_counter() - t0)
+    return steps * n_utt_sample * T / sum(walls), walls
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = cores  # one utterance per core and step: a few seconds of wall per step at cfg2 shape
+    steps = max(1, min(args.steps, 8))
+    value, walls = cpu_arm(per_step, cores, steps=steps)
+    sample = ("%d utterances x %d frames per step (%d steps; 1 warm-up utterance per process), one utterance "
+              "per process" % (per_step, T, steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from poccala_b200 import synth
+    from poccala_b200.engine import Corpus, Engine, EStep, Model, em_iteration_host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = dist.group.WORLD
+    eng = Engine(local)
+    dev = eng.device
+    # every rank starts from the SAME model (replicated parameters) and owns its own utterances
+    truth, init0, labels, x = synth.torch_corpus(N_UTT, T, L, N_UNITS, MIX, 2, dev, N_INITIALS, data_seed=2 + rank)
+    corpus = Corpus(eng, labels, np.full(N_UTT, T, dtype=np.int32), N_UNITS)
+    tm0 = synth.default_transmat(N_UNITS)
+    model = Model(eng, init0[0], init0[1], init0[2], tm0)
+    es = EStep(eng, corpus, model)
+    es.load_frames(x)
+    frames = corpus.total_frames
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def reset_model():
+        model.mean.copy_(torch.as_tensor(init0[0]).to(dev))
+        model.var.copy_(torch.as_tensor(init0[1]).to(dev))
+        model.alpha.copy_(torch.as_tensor(init0[2]).to(dev))
+        model.transmat.copy_(torch.as_tensor(tm0).to(dev))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(ev=None):
+        if ev is None:
+            es.em_iteration(c_covariance=1e-6, group=group)
+            return
+        ev[0].record(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
+        es.accumulate(); ev[3].record()
+        es.reduce_transitions(group)
+        if group is not None:
+            dist.all_reduce(es.acc, group=group)
+            dist.all_reduce(es.tsum, group=group)
+        es.mstep(c_covariance=1e-6)
+        ev[4].record()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    reset_model()
+    sync_all()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    l0 = eng.launches
+    with ClockSampler(local) as clocks:
+        sync_all()
+        w0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.zero_()  # L2 flush between timed steps (outside the per-step events)
+            step(evs[k])
+        sync_all()
+        wall = time.perf_counter() - w0
+    launches = eng.launches - l0
+    step_ms = [e[0].elapsed_time(e[4]) for e in evs]
+    k1 = [e[0].elapsed_time(e[1]) for e in evs]
+    k2 = [e[1].elapsed_time(e[2]) for e in evs]
+    k3 = [e[2].elapsed_time(e[3]) for e in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX, group=group)
+    total_ms = float(total_ms.item())
+    value = world * frames * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host frames, H2D + D2H inside)
+    host_x = torch.empty((frames, DIM), dtype=torch.float32).pin_memory()
+    host_x.copy_(x.cpu())
+    hp = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init0] + [tm0.copy()]
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        p = [a.copy() for a in hp]
+        em_iteration_host(eng, corpus, host_x.numpy(), *p, c_covariance=1e-6)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        p = [a.copy() for a in hp]
+        em_iteration_host(eng, corpus, host_x.numpy(), *p, c_covariance=1e-6)
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if group is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX, group=group)
+    e2e_val = world * frames * e2e_steps / float(e2e_s.item())
+    G = N_UNITS * 3 * MIX
+    h2d = frames * DIM * 4 + (2 * G * DIM + G + N_UNITS * 25) * 8
+    d2h = (2 * G * DIM + G + N_UNITS * 25) * 8 + 8
+
+    if rank != 0:
+        if group is not None:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    # dominant kernel and its roofline: K1/K3 are contractions, 158 flops per
+    # (frame, Gaussian) pair; K2 moves 8 B per (emitting state, frame)
+    pairs = frames * 3 * L * MIX
+    kern = {"K1_score": (statistics.mean(k1), "tensor", 158.0 * pairs),
+            "K2_forward_backward": (statistics.mean(k2), "hbm", 8.0 * frames * 3 * L),
+            "K3_accumulate": (statistics.mean(k3), "tensor", 2 * 158.0 * pairs)}
+    dom = max(kern, key=lambda k: kern[k][0])
+    ms, bound, work = kern[dom]
+    if bound == "tensor":
+        ach, peak, unit = work / (ms * 1e-3) / 1e12, float(pk["bf16_tflops_sustained"]), "TFLOP/s"
+    else:
+        ach, peak, unit = work / (ms * 1e-3) / 1e9, float(pk["hbm_gbs"]), "GB/s"
+    roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "traffic": None, "peak_source": pk_src + (" (bf16 sustained)" if bound == "tensor" else ""),
+                "ms_per_launch": ms,
+                "all_ms": {k: v[0] for k, v in kern.items()}}
+    cores = os.cpu_count() or 1
+    n_sample = 2 * cores
+    cpu_v, cpu_walls = cpu_arm(n_sample, cores)
+    cpu_wall = sum(cpu_walls)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "l2": "256 MiB memset between timed steps (outside the per-step events)",
+                   "wall_s_timed_region": wall, "parallelism": "dp%d" % world},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "api": "pc_em_iteration_host"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d utterances x %d frames of the same workload (E-step), %.1f s" % (n_sample, T, cpu_wall)},
+    }
+    print(json.dumps(line), flush=True)
+    if group is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/*
+ * poccala_b200.h — C ABI of the B200-native GMM-HMM E-step engine.
+ *
+ * This is the drop-in boundary for Poccala's embedded Baum-Welch hot path.  The reference
+ * (pure Python/numpy, /root/reference) has no FFI layer of its own: its boundary is the Python
+ * class surface (StatisticalModel/LHMM.py, StatisticalModel/Clustering.py,
+ * AcousticModel/AcousticModel.py).  poccala_b200/ mirrors those classes and binds the entry
+ * points below with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ * Every entry point cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types only; all `dev` pointers are CUDA device pointers owned by the caller;
+ *     `host` pointers are ordinary host memory.  The library never frees caller memory.
+ *   - every call returns 0 (PC_OK) or a negative PC_ERR_* code; pc_last_error() gives the message
+ *     for the calling thread.  No C++ exception crosses the boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer calls
+ *     are asynchronous on that stream and perform no hidden host synchronisation unless stated.
+ *   - a pc_handle is bound to one CUDA device and is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device pc_create fails with PC_ERR_CUDA.
+ *
+ * Data layout in HBM
+ *   X      float [n_frames_total][PC_XS]   standardised frames; cols [0,D) data, col 39 = 1.0
+ *   W      float [n_gauss][PC_KA]          packed Gaussians: mu/var | -1/(2 var) | k_hi | k_lo
+ *   b,lgam float per utterance [3*L][Tpad] emitting-state rows, time contiguous (Tpad = T up to 4)
+ *   acc    double[n_gauss][PC_KA]          sum gamma*x | sum gamma*x^2 | sum gamma | sum gamma
+ *   Gaussian index g = (unit*3 + state)*mix + m.
+ */
+#ifndef POCCALA_B200_H
+#define POCCALA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_ABI_VERSION 1
+
+#define PC_OK 0
+#define PC_ERR_INVALID (-1)     /* bad argument (shape, NULL pointer, dimension mismatch) */
+#define PC_ERR_CUDA (-2)        /* CUDA runtime error or no usable device */
+#define PC_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels cover */
+#define PC_ERR_NOMEM (-4)
+
+#define PC_DIM_MAX 39 /* feature dimension limit (39-dim MFCC, init.py:27-43) */
+#define PC_XS 40      /* floats per frame row of X */
+#define PC_KA 80      /* augmented contraction length [x, x^2, 1, 1] */
+#define PC_EMIT 3     /* emitting states per unit HMM (state_num 5, AcousticModel.py:39) */
+#define PC_STATES 5
+#define PC_TRANS_SLOTS 9 /* per unit: 3 x (self, next, gamma) log-domain transition accumulators */
+
+typedef struct pc_handle_s *pc_handle;
+typedef struct pc_corpus_s *pc_corpus;
+
+int pc_abi_version(void);
+const char *pc_last_error(void);
+
+/* One handle per device.  Fails (PC_ERR_CUDA) when the device is absent or not sm_100. */
+int pc_create(int device, pc_handle *out);
+int pc_destroy(pc_handle h);
+/* Select the kernel generation: 0 = CUDA-core kernels, 1 = tcgen05/TMA kernels (default when the
+ * shape is covered).  Used by the tests to cross-check both on the same inputs. */
+int pc_set_option(pc_handle h, const char *key, int64_t value);
+int64_t pc_get_option(pc_handle h, const char *key);
+
+/* ---- corpus descriptors -------------------------------------------------------------------
+ * Replaces the per-utterance Python lists that AcousticModel.embedded_training walks
+ * (AcousticModel.py:842-870: one task per (label, data)).  Host arrays in, device descriptor
+ * tables (owned by the corpus object) out.  labels are unit indices in [0, n_units). */
+int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *host_n_frames,
+                     const int32_t *host_n_labels, const int32_t *host_labels, int32_t n_units,
+                     pc_corpus *out);
+int pc_corpus_destroy(pc_corpus c);
+int64_t pc_corpus_total_frames(pc_corpus c);
+int64_t pc_corpus_emission_floats(pc_corpus c); /* length of the b / lgam buffers */
+int64_t pc_corpus_total_pairs(pc_corpus c);     /* number of (utterance, label position) pairs */
+int64_t pc_corpus_total_states(pc_corpus c);    /* sum over utterances of 3L+2 */
+/* host_out[n_utt+1]: first frame / first float in b / first pair / first composite state. */
+int pc_corpus_offsets(pc_corpus c, int64_t *host_frame_off, int64_t *host_emis_off,
+                      int64_t *host_pair_off, int64_t *host_state_off);
+
+/* ---- model packing -------------------------------------------------------------------------
+ * util.gaussian_function (util.py:20-36, log branch incl. the -1/2*sum(var) normaliser, Q1) and
+ * the log(alpha) term of Clustering.GMM.point (Clustering.py:753-757), folded into one row per
+ * Gaussian so that score = <[x, x^2, 1, 1], W_g>.  mean/var/alpha: dev double [n_gauss][dim] /
+ * [n_gauss]; shift/inv_scale: dev double [dim] or NULL (identity). */
+int pc_pack_gmm(pc_handle h, const double *dev_mean, const double *dev_var,
+                const double *dev_alpha, const double *dev_shift, const double *dev_inv_scale,
+                int32_t n_gauss, int32_t dim, float *dev_W, void *stream);
+
+/* Frames [n][dim] (double or float, device) -> X [n][PC_XS] standardised float rows. */
+int pc_prepare_frames_f64(pc_handle h, const double *dev_x, int64_t n, int32_t dim,
+                          const double *dev_shift, const double *dev_inv_scale, float *dev_X,
+                          void *stream);
+int pc_prepare_frames_f32(pc_handle h, const float *dev_x, int64_t n, int32_t dim,
+                          const double *dev_shift, const double *dev_inv_scale, float *dev_X,
+                          void *stream);
+
+/* ---- K1: GMM scoring -----------------------------------------------------------------------
+ * LHMM.cal_observation_pro -> GMM.point -> util.gaussian_function + util.log_sum_exp
+ * (LHMM.py:163-187, Clustering.py:740-767, util.py:20-36,54-77) for every (utterance, label
+ * position, emitting state, frame).  Writes b (emission log-likelihoods). */
+int pc_gmm_score(pc_handle h, pc_corpus c, const float *dev_X, const float *dev_W, int32_t mix,
+                 float *dev_b, void *stream);
+
+/* Dense scoring sweep (BASELINE config 3): n frames against n_states GMMs of `mix` components,
+ * out[n][n_states] = log-sum-exp over each state's components. */
+int pc_gmm_score_dense(pc_handle h, const float *dev_X, int64_t n, const float *dev_W,
+                       int32_t n_states, int32_t mix, float *dev_out, void *stream);
+
+/* ---- K2: forward-backward ------------------------------------------------------------------
+ * LHMM.baulm_welch loop on the sentence HMM assembled by AcousticModel.embedded
+ * (AcousticModel.py:957-1014; LHMM.py:335-366 forward/backward, :426-471 ksai/gamma/pi,
+ * :412-422 likelihood, :526-544 pi-iteration with the 0.64 threshold, :486-500 per-frame
+ * normalised log gamma).  log_self/log_next: dev double [n_units][5] = log of the unit HMM's
+ * transmat diagonal / super-diagonal (host-computed np.log).  Outputs: lgam (same layout as b),
+ * utt_logp double [n_utt], utt_iters int32 [n_utt] (Baum-Welch iterations the reference would
+ * run), pair_trans float [n_pairs][9]: log expected (self, next, occupancy) counts over t<T-1 per
+ * emitting state, RELATIVE to utt_logp (reference value = utt_logp + pair_trans, Q6). */
+int pc_forward_backward(pc_handle h, pc_corpus c, const float *dev_b, const double *dev_log_self,
+                        const double *dev_log_next, float *dev_lgam, double *dev_utt_logp,
+                        int32_t *dev_utt_iters, float *dev_pair_trans, void *stream);
+
+/* ---- K3: Baum-Welch accumulation -----------------------------------------------------------
+ * LHMM.update_acc -> Clustering.GMM.update_acc (LHMM.py:473-507, Clustering.py:653-680) in the
+ * linear-equivalent form of SURVEY A.4: acc[g] += sum_t gamma_t(j,m) * [x, x^2, 1, 1].
+ * dev_acc is accumulated into (caller zeroes it at the start of an EM iteration). */
+int pc_accumulate(pc_handle h, pc_corpus c, const float *dev_X, const float *dev_W, int32_t mix,
+                  const float *dev_b, const float *dev_lgam, double *dev_acc, void *stream);
+
+/* ---- K6 local part: log-domain transition accumulators -------------------------------------
+ * LHMM.add_acc / init_acc (LHMM.py:149-161,256-290): log-sum-exp over every (utterance, position)
+ * of a unit.  Two steps so that a cross-rank allreduce(max) / allreduce(sum) can sit between them:
+ *   pc_transitions_max : dev_max[n_units][9] = max(dev_max, utt_logp + pair_trans)
+ *   pc_transitions_sum : dev_sum[n_units][9] += exp(utt_logp + pair_trans - dev_max)
+ * accumulator = dev_max + log(dev_sum). */
+int pc_transitions_max(pc_handle h, pc_corpus c, const double *dev_utt_logp,
+                       const float *dev_pair_trans, double *dev_max, void *stream);
+int pc_transitions_sum(pc_handle h, pc_corpus c, const double *dev_utt_logp,
+                       const float *dev_pair_trans, const double *dev_max, double *dev_sum,
+                       void *stream);
+
+/* ---- M-step --------------------------------------------------------------------------------
+ * LHMM.update_param + Clustering.GMM.update_param (LHMM.py:509-524, Clustering.py:682-693):
+ * alpha = occ/socc, mean = sx/occ, var = max(E[(x-mu_old)^2], c_covariance) (Q8), transmat rows
+ * 1..3 = exp(ksai_acc - gamma_acc).  Parameters are updated IN PLACE (dev double).  fix_code bit 4
+ * locks transmat, bit 2 locks the GMMs (LHMM.py:140-145).  Units with zero occupancy keep their
+ * parameters. */
+int pc_update_params(pc_handle h, int32_t n_units, int32_t mix, int32_t dim, const double *dev_acc,
+                     const double *dev_trans_max, const double *dev_trans_sum,
+                     const double *dev_shift, const double *dev_inv_scale, double c_covariance,
+                     int32_t fix_code, double *dev_mean, double *dev_var, double *dev_alpha,
+                     double *dev_transmat /* [n_units][5][5] */, void *stream);
+
+/* ---- K4: Viterbi forced alignment ----------------------------------------------------------
+ * LHMM.viterbi (LHMM.py:546-609) on the banded sentence HMM: fp64 max-plus recurrence, ties to
+ * the lower state index, end state = first argmax over all states.  Emissions: the float buffer
+ * written by pc_gmm_score (dev_b) or a double buffer of the same layout (dev_b64); exactly one
+ * is non-NULL.  logpi: dev double [n_utt] (uniform value per utterance, np.log(1/N)) or
+ * dev_state_logpi [total_states] (general); exactly one is non-NULL.  Outputs: path int32
+ * [n_frames_total] composite state index per frame, optional unit label per frame
+ * (AcousticModel.py:1016-1027 convert=True), score double [n_utt]. */
+int pc_viterbi(pc_handle h, pc_corpus c, const float *dev_b, const double *dev_b64,
+               const double *dev_log_self, const double *dev_log_next, const double *dev_utt_logpi,
+               const double *dev_state_logpi, int32_t *dev_path, int32_t *dev_unit_path,
+               double *dev_score, void *stream);
+
+/* ---- K5: k-means initialisation ------------------------------------------------------------
+ * ClusterInitialization.kmeans(algorithm=1) greedy passes (Clustering.py:894-940) with the
+ * dimension-0 metric of cal_distance (:796-801, Q2).  One call runs the passes to convergence
+ * for `n_problems` independent problems (one per HMM state).  See DESIGN.md §K5. */
+int pc_kmeans_run(pc_handle h, int32_t n_problems, const int64_t *dev_point_off,
+                  const double *dev_x0, int32_t k, const int32_t *dev_seed_points,
+                  int32_t *dev_owner, int32_t *dev_member_list, int32_t *dev_member_count,
+                  int32_t *dev_passes, int64_t max_passes, void *stream);
+
+/* ---- host-buffer entry point (end-to-end) --------------------------------------------------
+ * One full EM iteration the way AcousticModel.embedded_training runs it (AcousticModel.py:842-882)
+ * with HOST inputs and outputs: frames [total_frames][dim] float (pinned or pageable), parameters
+ * double, updated in place on return.  Copies host->device, runs K1,K2,K3,K6,M-step, copies the
+ * new parameters and sum log-likelihood back, and synchronises the stream. */
+int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int32_t dim,
+                         int32_t n_units, int32_t mix, double *host_mean, double *host_var,
+                         double *host_alpha, double *host_transmat, double c_covariance,
+                         int32_t fix_code, double *host_sum_logp, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POCCALA_B200_H */

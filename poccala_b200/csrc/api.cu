@@ -1,0 +1,502 @@
+// C ABI (include/poccala_b200.h): handle, corpus descriptors, argument checking, dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+const char *pc_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return g_err;
+}
+
+extern "C" {
+
+int pc_abi_version(void) { return PC_ABI_VERSION; }
+const char *pc_last_error(void) { return g_err; }
+
+int pc_create(int device, pc_handle *out) {
+    PC_REQUIRE(out != nullptr, "pc_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        pc_set_error("pc_create: no CUDA device (%s); this engine has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return PC_ERR_CUDA;
+    }
+    PC_REQUIRE(device >= 0 && device < n, "pc_create: device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    PC_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        pc_set_error("pc_create: device %d is sm_%d%d; the kernels are built for sm_100a only",
+                     device, prop.major, prop.minor);
+        return PC_ERR_CUDA;
+    }
+    PC_CUDA_TRY(cudaSetDevice(device));
+    pc_handle h = new pc_handle_s();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->use_tc = 1;
+    *out = h;
+    return PC_OK;
+}
+
+int pc_destroy(pc_handle h) {
+    if (!h) return PC_OK;
+    cudaSetDevice(h->device);
+    if (h->ws) cudaFree(h->ws);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+    return PC_OK;
+}
+
+int pc_set_option(pc_handle h, const char *key, int64_t value) {
+    PC_REQUIRE(h && key, "pc_set_option: NULL argument");
+    if (!strcmp(key, "tensor_core")) { h->use_tc = (int)value; return PC_OK; }
+    if (!strcmp(key, "fb_variant")) { h->fb_variant = (int)value; return PC_OK; }
+    if (!strcmp(key, "launches")) { h->launches = value; return PC_OK; }
+    pc_set_error("pc_set_option: unknown key '%s'", key);
+    return PC_ERR_INVALID;
+}
+
+int64_t pc_get_option(pc_handle h, const char *key) {
+    if (!h || !key) return -1;
+    if (!strcmp(key, "tensor_core")) return h->use_tc;
+    if (!strcmp(key, "fb_variant")) return h->fb_variant;
+    if (!strcmp(key, "launches")) return h->launches;
+    if (!strcmp(key, "sm_count")) return h->sm_count;
+    return -1;
+}
+
+// --------------------------------------------------------------------------------- corpus
+int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const int32_t *n_labels,
+                     const int32_t *labels, int32_t n_units, pc_corpus *out) {
+    PC_REQUIRE(h && out, "pc_corpus_create: NULL handle/out");
+    PC_REQUIRE(n_utt >= 0 && n_units > 0, "pc_corpus_create: n_utt=%d n_units=%d", n_utt, n_units);
+    PC_REQUIRE(n_utt == 0 || (n_frames && n_labels && labels), "pc_corpus_create: NULL host array");
+    *out = nullptr;
+    std::vector<int64_t> frame_off(n_utt + 1, 0), emis_off(n_utt + 1, 0), pair_off(n_utt + 1, 0),
+        state_off(n_utt + 1, 0);
+    int max_frames = 0, max_labels = 0;
+    for (int u = 0; u < n_utt; ++u) {
+        PC_REQUIRE(n_frames[u] >= 1, "pc_corpus_create: utterance %d has %d frames", u, n_frames[u]);
+        PC_REQUIRE(n_labels[u] >= 1, "pc_corpus_create: utterance %d has %d labels", u, n_labels[u]);
+        frame_off[u + 1] = frame_off[u] + n_frames[u];
+        pair_off[u + 1] = pair_off[u] + n_labels[u];
+        emis_off[u + 1] = emis_off[u] + (int64_t)PC_EMIT * n_labels[u] * pc_tpad(n_frames[u]);
+        state_off[u + 1] = state_off[u] + PC_EMIT * n_labels[u] + 2;
+        max_frames = std::max(max_frames, n_frames[u]);
+        max_labels = std::max(max_labels, n_labels[u]);
+    }
+    const int64_t n_pairs = pair_off[n_utt];
+    std::vector<int32_t> pair_utt(n_pairs);
+    for (int u = 0; u < n_utt; ++u)
+        for (int64_t p = pair_off[u]; p < pair_off[u + 1]; ++p) {
+            PC_REQUIRE(labels[p] >= 0 && labels[p] < n_units,
+                       "pc_corpus_create: label %d of utterance %d is outside [0,%d)", labels[p], u,
+                       n_units);
+            pair_utt[p] = u;
+        }
+    // forward-backward order: heaviest utterances first
+    std::vector<int32_t> fb_order(n_utt);
+    std::iota(fb_order.begin(), fb_order.end(), 0);
+    std::stable_sort(fb_order.begin(), fb_order.end(), [&](int a, int b) {
+        int64_t wa = (int64_t)n_frames[a] * (PC_EMIT * n_labels[a] + 1);
+        int64_t wb = (int64_t)n_frames[b] * (PC_EMIT * n_labels[b] + 1);
+        return wa > wb;
+    });
+    // unit-major decomposition: counting sort of the pairs by unit (stable)
+    std::vector<int64_t> unit_pair_off(n_units + 1, 0);
+    for (int64_t p = 0; p < n_pairs; ++p) unit_pair_off[labels[p] + 1]++;
+    for (int k = 0; k < n_units; ++k) unit_pair_off[k + 1] += unit_pair_off[k];
+    std::vector<int64_t> sorted_pair(n_pairs);
+    {
+        std::vector<int64_t> cur(unit_pair_off.begin(), unit_pair_off.end() - 1);
+        for (int64_t p = 0; p < n_pairs; ++p) sorted_pair[cur[labels[p]]++] = p;
+    }
+    std::vector<int64_t> tile_pair;
+    std::vector<int32_t> tile_t0;
+    std::vector<int64_t> unit_tile_off(n_units + 1, 0);
+    for (int k = 0; k < n_units; ++k) {
+        for (int64_t i = unit_pair_off[k]; i < unit_pair_off[k + 1]; ++i) {
+            const int64_t p = sorted_pair[i];
+            const int T = n_frames[pair_utt[p]];
+            for (int t0 = 0; t0 < T; t0 += PC_TILE_ROWS) {
+                tile_pair.push_back(p);
+                tile_t0.push_back(t0);
+            }
+        }
+        unit_tile_off[k + 1] = (int64_t)tile_pair.size();
+    }
+    const int64_t n_tiles = (int64_t)tile_pair.size();
+    // work items: runs of <= chunk tiles inside one unit; aim at >= 8 items per SM
+    int64_t chunk = n_tiles / ((int64_t)h->sm_count * 8);
+    chunk = std::max<int64_t>(4, std::min<int64_t>(64, chunk));
+    std::vector<int64_t> item_tile_lo;
+    std::vector<int32_t> item_unit;
+    for (int k = 0; k < n_units; ++k)
+        for (int64_t lo = unit_tile_off[k]; lo < unit_tile_off[k + 1]; lo += chunk) {
+            item_tile_lo.push_back(lo);
+            item_unit.push_back(k);
+        }
+    item_tile_lo.push_back(n_tiles);
+    const int64_t n_items = (int64_t)item_unit.size();
+    PC_REQUIRE(n_items < 2147483647LL, "pc_corpus_create: too many work items");
+
+    // one device block for every table
+    struct Seg { const void *src; size_t bytes; size_t off; };
+    std::vector<Seg> segs;
+    size_t total = 0;
+    auto add = [&](const void *src, size_t bytes) {
+        size_t off = total;
+        segs.push_back({src, bytes, off});
+        total += (bytes + 255) & ~(size_t)255;
+        return off;
+    };
+    size_t o_frame = add(frame_off.data(), frame_off.size() * 8);
+    size_t o_emis = add(emis_off.data(), emis_off.size() * 8);
+    size_t o_pair = add(pair_off.data(), pair_off.size() * 8);
+    size_t o_state = add(state_off.data(), state_off.size() * 8);
+    size_t o_labels = add(labels, (size_t)n_pairs * 4);
+    size_t o_putt = add(pair_utt.data(), (size_t)n_pairs * 4);
+    size_t o_fb = add(fb_order.data(), (size_t)n_utt * 4);
+    size_t o_sorted = add(sorted_pair.data(), (size_t)n_pairs * 8);
+    size_t o_upo = add(unit_pair_off.data(), unit_pair_off.size() * 8);
+    size_t o_tpair = add(tile_pair.data(), (size_t)n_tiles * 8);
+    size_t o_tt0 = add(tile_t0.data(), (size_t)n_tiles * 4);
+    size_t o_ilo = add(item_tile_lo.data(), item_tile_lo.size() * 8);
+    size_t o_iunit = add(item_unit.data(), (size_t)n_items * 4);
+    size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 4);
+    PC_CUDA_TRY(cudaSetDevice(h->device));
+    char *dev = nullptr;
+    PC_CUDA_TRY(cudaMalloc((void **)&dev, std::max<size_t>(total, 256)));
+    for (const Seg &s : segs)
+        if (s.src && s.bytes) {
+            cudaError_t e = cudaMemcpy(dev + s.off, s.src, s.bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                cudaFree(dev);
+                pc_set_error("pc_corpus_create: upload failed: %s", cudaGetErrorString(e));
+                return PC_ERR_CUDA;
+            }
+        }
+    pc_corpus c = new pc_corpus_s();
+    memset(c, 0, sizeof(*c));
+    c->h = h;
+    c->dev_block = dev;
+    c->total_frames = frame_off[n_utt];
+    c->emis_floats = emis_off[n_utt];
+    c->total_states = state_off[n_utt];
+    c->items_per_chunk = (int32_t)chunk;
+    CorpusView &v = c->v;
+    v.n_utt = n_utt;
+    v.n_units = n_units;
+    v.n_pairs = n_pairs;
+    v.n_tiles = n_tiles;
+    v.n_items = (int32_t)n_items;
+    v.max_frames = max_frames;
+    v.max_labels = max_labels;
+    v.frame_off = (const int64_t *)(dev + o_frame);
+    v.emis_off = (const int64_t *)(dev + o_emis);
+    v.pair_off = (const int64_t *)(dev + o_pair);
+    v.state_off = (const int64_t *)(dev + o_state);
+    v.labels = (const int32_t *)(dev + o_labels);
+    v.pair_utt = (const int32_t *)(dev + o_putt);
+    v.fb_order = (const int32_t *)(dev + o_fb);
+    v.sorted_pair = (const int64_t *)(dev + o_sorted);
+    v.unit_pair_off = (const int64_t *)(dev + o_upo);
+    v.tile_pair = (const int64_t *)(dev + o_tpair);
+    v.tile_t0 = (const int32_t *)(dev + o_tt0);
+    v.item_tile_lo = (const int64_t *)(dev + o_ilo);
+    v.item_unit = (const int32_t *)(dev + o_iunit);
+    v.scratch0 = (float *)(dev + o_scratch);
+    c->host_frame_off = new int64_t[4 * (size_t)(n_utt + 1)];
+    c->host_emis_off = c->host_frame_off + (n_utt + 1);
+    c->host_pair_off = c->host_emis_off + (n_utt + 1);
+    c->host_state_off = c->host_pair_off + (n_utt + 1);
+    memcpy(c->host_frame_off, frame_off.data(), (size_t)(n_utt + 1) * 8);
+    memcpy(c->host_emis_off, emis_off.data(), (size_t)(n_utt + 1) * 8);
+    memcpy(c->host_pair_off, pair_off.data(), (size_t)(n_utt + 1) * 8);
+    memcpy(c->host_state_off, state_off.data(), (size_t)(n_utt + 1) * 8);
+    *out = c;
+    return PC_OK;
+}
+
+int pc_corpus_destroy(pc_corpus c) {
+    if (!c) return PC_OK;
+    cudaSetDevice(c->h->device);
+    if (c->dev_block) cudaFree(c->dev_block);
+    delete[] c->host_frame_off;
+    delete c;
+    return PC_OK;
+}
+
+int64_t pc_corpus_total_frames(pc_corpus c) { return c ? c->total_frames : -1; }
+int64_t pc_corpus_emission_floats(pc_corpus c) { return c ? c->emis_floats : -1; }
+int64_t pc_corpus_total_pairs(pc_corpus c) { return c ? c->v.n_pairs : -1; }
+int64_t pc_corpus_total_states(pc_corpus c) { return c ? c->total_states : -1; }
+
+int pc_corpus_offsets(pc_corpus c, int64_t *frame_off, int64_t *emis_off, int64_t *pair_off,
+                      int64_t *state_off) {
+    PC_REQUIRE(c, "pc_corpus_offsets: NULL corpus");
+    size_t n = (size_t)(c->v.n_utt + 1) * 8;
+    if (frame_off) memcpy(frame_off, c->host_frame_off, n);
+    if (emis_off) memcpy(emis_off, c->host_emis_off, n);
+    if (pair_off) memcpy(pair_off, c->host_pair_off, n);
+    if (state_off) memcpy(state_off, c->host_state_off, n);
+    return PC_OK;
+}
+
+// --------------------------------------------------------------------------------- kernels
+#define PC_ENTER(h)                                           \
+    PC_REQUIRE((h) != nullptr, "%s: NULL handle", __func__);  \
+    PC_CUDA_TRY(cudaSetDevice((h)->device))
+
+static int check_dim_mix(const char *fn, int dim, int mix) {
+    if (dim < 1 || dim > PC_DIM_MAX) {
+        pc_set_error("%s: dimension %d outside [1,%d] (DataDimensionError in the reference, "
+                     "Clustering.py:749-751)", fn, dim, PC_DIM_MAX);
+        return PC_ERR_INVALID;
+    }
+    if (mix < 1) {
+        pc_set_error("%s: mix=%d", fn, mix);
+        return PC_ERR_INVALID;
+    }
+    return PC_OK;
+}
+
+int pc_pack_gmm(pc_handle h, const double *mean, const double *var, const double *alpha,
+                const double *shift, const double *inv_scale, int32_t n_gauss, int32_t dim,
+                float *W, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n_gauss >= 0, "pc_pack_gmm: n_gauss=%d", n_gauss);
+    PC_REQUIRE(n_gauss == 0 || (mean && var && alpha && W), "pc_pack_gmm: NULL pointer");
+    int rc = check_dim_mix("pc_pack_gmm", dim, 1);
+    if (rc) return rc;
+    return launch_pack_gmm(h, mean, var, alpha, shift, inv_scale, n_gauss, dim, W,
+                           (cudaStream_t)stream);
+}
+
+int pc_prepare_frames_f64(pc_handle h, const double *x, int64_t n, int32_t dim,
+                          const double *shift, const double *inv_scale, float *X, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n >= 0 && (n == 0 || (x && X)), "pc_prepare_frames_f64: bad arguments");
+    int rc = check_dim_mix("pc_prepare_frames_f64", dim, 1);
+    if (rc) return rc;
+    return launch_prepare_frames(h, x, 1, n, dim, shift, inv_scale, X, (cudaStream_t)stream);
+}
+
+int pc_prepare_frames_f32(pc_handle h, const float *x, int64_t n, int32_t dim, const double *shift,
+                          const double *inv_scale, float *X, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n >= 0 && (n == 0 || (x && X)), "pc_prepare_frames_f32: bad arguments");
+    int rc = check_dim_mix("pc_prepare_frames_f32", dim, 1);
+    if (rc) return rc;
+    return launch_prepare_frames(h, x, 0, n, dim, shift, inv_scale, X, (cudaStream_t)stream);
+}
+
+int pc_gmm_score(pc_handle h, pc_corpus c, const float *X, const float *W, int32_t mix, float *b,
+                 void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && X && W && b, "pc_gmm_score: NULL argument");
+    int rc = check_dim_mix("pc_gmm_score", 1, mix);
+    if (rc) return rc;
+    return launch_score_simt(h, c->v, X, W, mix, b, (cudaStream_t)stream);
+}
+
+int pc_gmm_score_dense(pc_handle h, const float *X, int64_t n, const float *W, int32_t n_states,
+                       int32_t mix, float *out, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n >= 0 && n_states >= 0, "pc_gmm_score_dense: negative size");
+    PC_REQUIRE((n == 0 || n_states == 0) || (X && W && out), "pc_gmm_score_dense: NULL argument");
+    int rc = check_dim_mix("pc_gmm_score_dense", 1, mix);
+    if (rc) return rc;
+    return launch_score_dense_simt(h, X, n, W, n_states, mix, out, (cudaStream_t)stream);
+}
+
+int pc_forward_backward(pc_handle h, pc_corpus c, const float *b, const double *log_self,
+                        const double *log_next, float *lgam, double *utt_logp, int32_t *utt_iters,
+                        float *pair_trans, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && b && log_self && log_next && lgam && utt_logp && utt_iters && pair_trans,
+               "pc_forward_backward: NULL argument");
+    return launch_forward_backward(h, c->v, b, log_self, log_next, lgam, c->v.scratch0, utt_logp,
+                                   utt_iters, pair_trans, (cudaStream_t)stream);
+}
+
+int pc_accumulate(pc_handle h, pc_corpus c, const float *X, const float *W, int32_t mix,
+                  const float *b, const float *lgam, double *acc, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && X && W && b && lgam && acc, "pc_accumulate: NULL argument");
+    int rc = check_dim_mix("pc_accumulate", 1, mix);
+    if (rc) return rc;
+    return launch_accumulate_simt(h, c->v, X, W, mix, b, lgam, acc, (cudaStream_t)stream);
+}
+
+int pc_transitions_max(pc_handle h, pc_corpus c, const double *utt_logp, const float *pair_trans,
+                       double *tmax, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && utt_logp && pair_trans && tmax, "pc_transitions_max: NULL argument");
+    return launch_transitions_max(h, c->v, utt_logp, pair_trans, tmax, (cudaStream_t)stream);
+}
+
+int pc_transitions_sum(pc_handle h, pc_corpus c, const double *utt_logp, const float *pair_trans,
+                       const double *tmax, double *tsum, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && utt_logp && pair_trans && tmax && tsum, "pc_transitions_sum: NULL argument");
+    return launch_transitions_sum(h, c->v, utt_logp, pair_trans, tmax, tsum, (cudaStream_t)stream);
+}
+
+int pc_update_params(pc_handle h, int32_t n_units, int32_t mix, int32_t dim, const double *acc,
+                     const double *tmax, const double *tsum, const double *shift,
+                     const double *inv_scale, double c_cov, int32_t fix_code, double *mean,
+                     double *var, double *alpha, double *transmat, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n_units >= 0, "pc_update_params: n_units=%d", n_units);
+    PC_REQUIRE(acc && tmax && tsum && mean && var && alpha && transmat,
+               "pc_update_params: NULL argument");
+    int rc = check_dim_mix("pc_update_params", dim, mix);
+    if (rc) return rc;
+    return launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, shift, inv_scale, c_cov,
+                                fix_code, mean, var, alpha, transmat, (cudaStream_t)stream);
+}
+
+int pc_viterbi(pc_handle h, pc_corpus c, const float *b, const double *b64, const double *log_self,
+               const double *log_next, const double *utt_logpi, const double *state_logpi,
+               int32_t *path, int32_t *unit_path, double *score, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && log_self && log_next && path && score, "pc_viterbi: NULL argument");
+    PC_REQUIRE((b != nullptr) != (b64 != nullptr), "pc_viterbi: exactly one of b / b64 must be set");
+    PC_REQUIRE((utt_logpi != nullptr) != (state_logpi != nullptr),
+               "pc_viterbi: exactly one of utt_logpi / state_logpi must be set");
+    return launch_viterbi(h, c->v, b, b64, log_self, log_next, utt_logpi, state_logpi, path,
+                          unit_path, score, (cudaStream_t)stream);
+}
+
+int pc_kmeans_run(pc_handle h, int32_t, const int64_t *, const double *, int32_t, const int32_t *,
+                  int32_t *, int32_t *, int32_t *, int32_t *, int64_t, void *) {
+    PC_ENTER(h);
+    pc_set_error("pc_kmeans_run: not built yet");
+    return PC_ERR_UNSUPPORTED;
+}
+
+// --------------------------------------------------------------------------------- host e2e
+static int ensure_ws(pc_handle h, size_t bytes) {
+    if (h->ws_bytes >= bytes) return PC_OK;
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    PC_CUDA_TRY(cudaMalloc(&h->ws, bytes));
+    h->ws_bytes = bytes;
+    return PC_OK;
+}
+
+__global__ void fill_double_kernel(double *p, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void log_bands_kernel(const double *transmat, int n_units, double *log_self,
+                                 double *log_next) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;  // (unit, state)
+    if (i >= n_units * PC_STATES) return;
+    int unit = i / PC_STATES, s = i - unit * PC_STATES;
+    const double *row = transmat + ((size_t)unit * PC_STATES + s) * PC_STATES;
+    log_self[i] = log(row[s]);
+    log_next[i] = (s + 1 < PC_STATES) ? log(row[s + 1]) : -INFINITY;
+}
+
+__global__ void sum_double_kernel(const double *p, int n, double *out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += p[i];
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) *out = s;
+}
+
+int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int32_t dim,
+                         int32_t n_units, int32_t mix, double *host_mean, double *host_var,
+                         double *host_alpha, double *host_transmat, double c_cov, int32_t fix_code,
+                         double *host_sum_logp, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && host_frames && host_mean && host_var && host_alpha && host_transmat,
+               "pc_em_iteration_host: NULL argument");
+    PC_REQUIRE(n_units == c->v.n_units, "pc_em_iteration_host: n_units %d != corpus %d", n_units,
+               c->v.n_units);
+    int rc = check_dim_mix("pc_em_iteration_host", dim, mix);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t F = c->total_frames;
+    const int64_t G = (int64_t)n_units * PC_EMIT * mix;
+    // workspace carve-up (256-byte aligned)
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    size_t o_raw = carve((size_t)F * dim * 4), o_X = carve((size_t)F * PC_XS * 4);
+    size_t o_b = carve((size_t)c->emis_floats * 4), o_lg = carve((size_t)c->emis_floats * 4);
+    size_t o_W = carve((size_t)G * PC_KA * 4), o_acc = carve((size_t)G * PC_KA * 8);
+    size_t o_mean = carve((size_t)G * dim * 8), o_var = carve((size_t)G * dim * 8);
+    size_t o_alpha = carve((size_t)G * 8), o_tm = carve((size_t)n_units * 25 * 8);
+    size_t o_ls = carve((size_t)n_units * 5 * 8), o_ln = carve((size_t)n_units * 5 * 8);
+    size_t o_logp = carve((size_t)c->v.n_utt * 8), o_it = carve((size_t)c->v.n_utt * 4);
+    size_t o_pt = carve((size_t)c->v.n_pairs * PC_TRANS_SLOTS * 4);
+    size_t o_tmax = carve((size_t)n_units * PC_TRANS_SLOTS * 8);
+    size_t o_tsum = carve((size_t)n_units * PC_TRANS_SLOTS * 8), o_sum = carve(8);
+    rc = ensure_ws(h, off);
+    if (rc) return rc;
+    char *ws = (char *)h->ws;
+    float *raw = (float *)(ws + o_raw), *X = (float *)(ws + o_X), *b = (float *)(ws + o_b);
+    float *lg = (float *)(ws + o_lg), *W = (float *)(ws + o_W), *pt = (float *)(ws + o_pt);
+    double *acc = (double *)(ws + o_acc), *mean = (double *)(ws + o_mean);
+    double *var = (double *)(ws + o_var), *alpha = (double *)(ws + o_alpha);
+    double *tm = (double *)(ws + o_tm), *ls = (double *)(ws + o_ls), *ln = (double *)(ws + o_ln);
+    double *logp = (double *)(ws + o_logp), *tmax = (double *)(ws + o_tmax);
+    double *tsum = (double *)(ws + o_tsum), *sum = (double *)(ws + o_sum);
+    int32_t *iters = (int32_t *)(ws + o_it);
+
+    PC_CUDA_TRY(cudaMemcpyAsync(raw, host_frames, (size_t)F * dim * 4, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(mean, host_mean, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(var, host_var, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(alpha, host_alpha, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(tm, host_transmat, (size_t)n_units * 25 * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)G * PC_KA * 8, st));
+    PC_CUDA_TRY(cudaMemsetAsync(tsum, 0, (size_t)n_units * PC_TRANS_SLOTS * 8, st));
+    {
+        int n = n_units * PC_TRANS_SLOTS;
+        fill_double_kernel<<<(n + 255) / 256, 256, 0, st>>>(tmax, n, -INFINITY);
+        log_bands_kernel<<<(n_units * PC_STATES + 127) / 128, 128, 0, st>>>(tm, n_units, ls, ln);
+        PC_LAUNCH_CHECK();
+        h->launches += 2;
+    }
+    if ((rc = launch_prepare_frames(h, raw, 0, F, dim, nullptr, nullptr, X, st))) return rc;
+    if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, W, st))) return rc;
+    if ((rc = launch_score_simt(h, c->v, X, W, mix, b, st))) return rc;
+    if ((rc = launch_forward_backward(h, c->v, b, ls, ln, lg, c->v.scratch0, logp, iters, pt, st))) return rc;
+    if (!(fix_code & 2))
+        if ((rc = launch_accumulate_simt(h, c->v, X, W, mix, b, lg, acc, st))) return rc;
+    if ((rc = launch_transitions_max(h, c->v, logp, pt, tmax, st))) return rc;
+    if ((rc = launch_transitions_sum(h, c->v, logp, pt, tmax, tsum, st))) return rc;
+    if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, nullptr, nullptr, c_cov,
+                                   fix_code, mean, var, alpha, tm, st))) return rc;
+    sum_double_kernel<<<1, 32, 0, st>>>(logp, c->v.n_utt, sum);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    PC_CUDA_TRY(cudaMemcpyAsync(host_mean, mean, (size_t)G * dim * 8, cudaMemcpyDeviceToHost, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(host_var, var, (size_t)G * dim * 8, cudaMemcpyDeviceToHost, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(host_alpha, alpha, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(host_transmat, tm, (size_t)n_units * 25 * 8, cudaMemcpyDeviceToHost, st));
+    double s = 0.0;
+    PC_CUDA_TRY(cudaMemcpyAsync(&s, sum, 8, cudaMemcpyDeviceToHost, st));
+    PC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (host_sum_logp) *host_sum_logp = s;
+    return PC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// Shared declarations for the sm_100a kernels behind include/poccala_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/poccala_b200.h"
+
+#define PC_TILE_ROWS 128  // frames per work tile (one tcgen05 M=128 accumulator block)
+#define PC_NEG_INF (-INFINITY)
+
+// Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
+struct CorpusView {
+    int32_t n_utt;
+    int32_t n_units;
+    int64_t n_pairs;
+    int64_t n_tiles;
+    int32_t n_items;
+    int32_t max_frames;
+    int32_t max_labels;
+    const int64_t *frame_off;   // [n_utt+1] first row of the utterance in X
+    const int64_t *emis_off;    // [n_utt+1] first float of the utterance's [3L][Tpad] block
+    const int64_t *pair_off;    // [n_utt+1] first (utt, position) pair = first label
+    const int64_t *state_off;   // [n_utt+1] first composite state (3L+2 per utterance)
+    const int32_t *labels;      // [n_pairs] unit id, utterance-major
+    const int32_t *pair_utt;    // [n_pairs] utterance of each utterance-major pair
+    const int32_t *fb_order;    // [n_utt] utterances sorted by descending T*(3L+1)
+    // unit-major work decomposition for K1 / K3
+    const int64_t *sorted_pair;  // [n_pairs] utterance-major pair index, sorted by unit (stable)
+    const int64_t *unit_pair_off;  // [n_units+1] range of sorted pairs per unit
+    const int64_t *tile_pair;    // [n_tiles] utterance-major pair index of the tile
+    const int32_t *tile_t0;      // [n_tiles] first frame (within the utterance) of the tile
+    const int64_t *item_tile_lo;  // [n_items+1] tile range of each work item (one unit per item)
+    const int32_t *item_unit;     // [n_items]
+    float *scratch0;              // [total_frames] entry-state beta_hat (K2 scratch)
+};
+
+__host__ __device__ inline int pc_tpad(int t) { return (t + 3) & ~3; }
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// log(exp(a)+exp(b)) in fp32 with -inf handling (util.py:54-77 semantics: an infinite maximum is
+// returned unchanged).
+__device__ __forceinline__ float logadd_f(float a, float b) {
+    float m = fmaxf(a, b);
+    float d = -fabsf(a - b);              // NaN only when a == b == -inf
+    d = (m == PC_NEG_INF) ? 0.f : d;
+    return m + __logf(1.f + __expf(d));
+}
+
+// Host-side launch helpers (api.cu)
+const char *pc_set_error(const char *fmt, ...);
+#define PC_CUDA_TRY(expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            pc_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                       \
+            return PC_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+#define PC_REQUIRE(cond, ...)          \
+    do {                               \
+        if (!(cond)) {                 \
+            pc_set_error(__VA_ARGS__); \
+            return PC_ERR_INVALID;     \
+        }                              \
+    } while (0)
+#define PC_LAUNCH_CHECK()                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            pc_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                         __LINE__);                                                        \
+            return PC_ERR_CUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+struct pc_handle_s {
+    int device;
+    int sm_count;
+    int use_tc;          // option "tensor_core"
+    int fb_variant;      // option "fb_variant"
+    int64_t launches;    // kernels launched through this handle (bench: gpu_launches)
+    // workspace for the host-buffer entry point
+    void *ws;
+    size_t ws_bytes;
+    void *pinned;
+    size_t pinned_bytes;
+};
+
+struct pc_corpus_s {
+    pc_handle h;
+    CorpusView v;
+    int64_t total_frames;
+    int64_t emis_floats;
+    int64_t total_states;
+    void *dev_block;     // one allocation holding every table
+    int64_t *host_frame_off, *host_emis_off, *host_pair_off, *host_state_off;
+    int32_t items_per_chunk;
+};
+
+// Kernel launchers implemented in the per-kernel translation units.
+int launch_pack_gmm(pc_handle h, const double *mean, const double *var, const double *alpha,
+                    const double *shift, const double *inv_scale, int n_gauss, int dim, float *W,
+                    cudaStream_t st);
+int launch_prepare_frames(pc_handle h, const void *x, int is_f64, int64_t n, int dim,
+                          const double *shift, const double *inv_scale, float *X, cudaStream_t st);
+int launch_score_simt(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
+                      float *b, cudaStream_t st);
+int launch_score_dense_simt(pc_handle h, const float *X, int64_t n, const float *W, int n_states,
+                            int mix, float *out, cudaStream_t st);
+int launch_accumulate_simt(pc_handle h, const CorpusView &v, const float *X, const float *W,
+                           int mix, const float *b, const float *lgam, double *acc,
+                           cudaStream_t st);
+int launch_forward_backward(pc_handle h, const CorpusView &v, const float *b,
+                            const double *log_self, const double *log_next, float *lgam,
+                            float *scratch0, double *utt_logp, int32_t *utt_iters,
+                            float *pair_trans, cudaStream_t st);
+int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_logp,
+                           const float *pair_trans, double *tmax, cudaStream_t st);
+int launch_transitions_sum(pc_handle h, const CorpusView &v, const double *utt_logp,
+                           const float *pair_trans, const double *tmax, double *tsum,
+                           cudaStream_t st);
+int launch_update_params(pc_handle h, int n_units, int mix, int dim, const double *acc,
+                         const double *tmax, const double *tsum, const double *shift,
+                         const double *inv_scale, double c_cov, int fix_code, double *mean,
+                         double *var, double *alpha, double *transmat, cudaStream_t st);
+int launch_viterbi(pc_handle h, const CorpusView &v, const float *b, const double *b64,
+                   const double *log_self, const double *log_next, const double *utt_logpi,
+                   const double *state_logpi, int32_t *path, int32_t *unit_path, double *score,
+                   cudaStream_t st);

@@ -1,0 +1,139 @@
+// K6 (local part) and the M-step.
+//
+// Transition accumulators: LHMM.add_acc / init_acc (LHMM.py:149-161,256-290) keep
+// ksai_acc[3][5] / gamma_acc[3] per unit as log-sum-exp over every (utterance, label position) of
+// UNNORMALISED log values (Q6): value = utt_logp + log(expected count).  Magnitudes are 1e4..1e5,
+// so this reduction is done in fp64 as (max, sum of exp(value - max)); the split lets a cross-rank
+// allreduce(max) / allreduce(sum) sit between the two kernels.
+//
+// M-step: LHMM.update_param (LHMM.py:509-524) + Clustering.GMM.update_param (Clustering.py:682-693)
+// from the linear statistics.
+#include "common.cuh"
+
+__device__ __forceinline__ void atomic_max_double(double *addr, double val) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (true) {
+        double cur = __longlong_as_double((long long)old);
+        if (!(val > cur)) return;
+        unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(val));
+        if (prev == old) return;
+        old = prev;
+    }
+}
+
+__global__ void transitions_max_kernel(CorpusView v, const double *__restrict__ utt_logp,
+                                       const float *__restrict__ pair_trans, double *tmax) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (pair, slot)
+    if (i >= v.n_pairs * PC_TRANS_SLOTS) return;
+    int64_t pair = i / PC_TRANS_SLOTS;
+    int slot = (int)(i - pair * PC_TRANS_SLOTS);
+    double val = utt_logp[v.pair_utt[pair]] + (double)pair_trans[i];
+    if (val == -INFINITY || isnan(val)) return;
+    atomic_max_double(tmax + (size_t)v.labels[pair] * PC_TRANS_SLOTS + slot, val);
+}
+
+__global__ void transitions_sum_kernel(CorpusView v, const double *__restrict__ utt_logp,
+                                       const float *__restrict__ pair_trans,
+                                       const double *__restrict__ tmax, double *tsum) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n_pairs * PC_TRANS_SLOTS) return;
+    int64_t pair = i / PC_TRANS_SLOTS;
+    int slot = (int)(i - pair * PC_TRANS_SLOTS);
+    double val = utt_logp[v.pair_utt[pair]] + (double)pair_trans[i];
+    if (val == -INFINITY || isnan(val)) return;
+    size_t o = (size_t)v.labels[pair] * PC_TRANS_SLOTS + slot;
+    double m = tmax[o];
+    double e = exp(val - m);
+    if (e > 0.0) atomicAdd(tsum + o, e);
+}
+
+// One thread per (gaussian, dimension); GMM part of the M-step.
+__global__ void update_gmm_kernel(int n_units, int mix, int dim, const double *__restrict__ acc,
+                                  const double *__restrict__ shift,
+                                  const double *__restrict__ inv_scale, double c_cov,
+                                  double *mean, double *var, double *alpha) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n_g = (int64_t)n_units * PC_EMIT * mix;
+    if (i >= n_g * dim) return;
+    int64_t g = i / dim;
+    int d = (int)(i - g * dim);
+    int64_t state = g / mix;
+    double socc = 0.0;
+    for (int m = 0; m < mix; ++m) socc += acc[(size_t)(state * mix + m) * PC_KA + 2 * PC_DIM_MAX];
+    if (!(socc > 0.0)) return;  // unseen state: parameters stay (deviation D1)
+    const double *a = acc + (size_t)g * PC_KA;
+    double occ = a[2 * PC_DIM_MAX];
+    double sx = a[d], sxx = a[PC_DIM_MAX + d];
+    double sh = shift ? shift[d] : 0.0;
+    double is = inv_scale ? inv_scale[d] : 1.0;
+    double mu_old_s = (mean[i] - sh) * is;  // old mean in the standardised space of X
+    double mu_s = sx / occ;
+    double var_s = (sxx - 2.0 * mu_old_s * sx + mu_old_s * mu_old_s * occ) / occ;  // Q8: old mean
+    double v_new = var_s / (is * is);
+    if (v_new < c_cov) v_new = c_cov;  // Clustering.py:690-691
+    mean[i] = sh + mu_s / is;
+    var[i] = v_new;
+    if (d == 0) alpha[g] = occ / socc;
+}
+
+__global__ void update_transmat_kernel(int n_units, const double *__restrict__ tmax,
+                                       const double *__restrict__ tsum, double *transmat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;  // (unit, emitting row r)
+    if (i >= n_units * PC_EMIT) return;
+    int unit = i / PC_EMIT, r = i - unit * PC_EMIT;
+    const double *mx = tmax + (size_t)unit * PC_TRANS_SLOTS + r * 3;
+    const double *sm = tsum + (size_t)unit * PC_TRANS_SLOTS + r * 3;
+    double g = mx[2] + log(sm[2]);
+    if (!(sm[2] > 0.0) || mx[2] == -INFINITY) return;  // unit never observed: keep (deviation D1)
+    double ks = (sm[0] > 0.0) ? mx[0] + log(sm[0]) : -INFINITY;
+    double kn = (sm[1] > 0.0) ? mx[1] + log(sm[1]) : -INFINITY;
+    double *row = transmat + ((size_t)unit * PC_STATES + 1 + r) * PC_STATES;
+    for (int c = 0; c < PC_STATES; ++c) row[c] = 0.0;  // exp(-inf - g), LHMM.py:520
+    row[1 + r] = exp(ks - g);
+    row[2 + r] = exp(kn - g);
+}
+
+int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_logp,
+                           const float *pair_trans, double *tmax, cudaStream_t st) {
+    int64_t n = v.n_pairs * PC_TRANS_SLOTS;
+    if (n == 0) return PC_OK;
+    transitions_max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, utt_logp, pair_trans, tmax);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
+int launch_transitions_sum(pc_handle h, const CorpusView &v, const double *utt_logp,
+                           const float *pair_trans, const double *tmax, double *tsum,
+                           cudaStream_t st) {
+    int64_t n = v.n_pairs * PC_TRANS_SLOTS;
+    if (n == 0) return PC_OK;
+    transitions_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, utt_logp, pair_trans, tmax,
+                                                                        tsum);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
+int launch_update_params(pc_handle h, int n_units, int mix, int dim, const double *acc,
+                         const double *tmax, const double *tsum, const double *shift,
+                         const double *inv_scale, double c_cov, int fix_code, double *mean,
+                         double *var, double *alpha, double *transmat, cudaStream_t st) {
+    if (n_units == 0) return PC_OK;
+    if (!(fix_code & 2)) {
+        int64_t n = (int64_t)n_units * PC_EMIT * mix * dim;
+        update_gmm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_units, mix, dim, acc, shift,
+                                                                      inv_scale, c_cov, mean, var,
+                                                                      alpha);
+        PC_LAUNCH_CHECK();
+        h->launches++;
+    }
+    if (!(fix_code & 4)) {
+        int n = n_units * PC_EMIT;
+        update_transmat_kernel<<<(n + 127) / 128, 128, 0, st>>>(n_units, tmax, tsum, transmat);
+        PC_LAUNCH_CHECK();
+        h->launches++;
+    }
+    return PC_OK;
+}

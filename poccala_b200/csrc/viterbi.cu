@@ -1,0 +1,182 @@
+// K4: Viterbi forced alignment on the banded sentence HMM (one warp per utterance).
+//
+// Restates LHMM.viterbi (LHMM.py:546-609) as SURVEY A.6 verified bit-for-bit against the
+// reference: fp64 scores p_t(j) = max(p_{t-1}(j-1) + log A[j-1,j], p_{t-1}(j) + log A[j,j]) + B[j,t]
+// with the tie going to the LOWER predecessor index (np.where(tmp == max)[0][0]); end state = first
+// argmax over all states; traceback through 1-bit backpointers kept in shared memory.  Only fp64
+// adds and compares are used, so scores and paths are bit-identical to numpy given the same
+// emissions, log-transitions and log-pi (those logs are computed on the host with numpy).
+// A cell whose two candidates are both -inf gets backpointer 0 in the reference; such cells can
+// never lie on the traced path of a finite end state, and for an all -inf column both
+// implementations trace state 0, so one bit per cell is enough.
+#include "common.cuh"
+
+template <int SPL, typename E>
+__global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
+                               const double *__restrict__ log_self,
+                               const double *__restrict__ log_next,
+                               const double *__restrict__ utt_logpi,
+                               const double *__restrict__ state_logpi, int32_t *__restrict__ path,
+                               int32_t *__restrict__ unit_path, double *__restrict__ score,
+                               int words_per_warp) {
+    extern __shared__ uint32_t bp_s[];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (wid >= v.n_utt) return;
+    const int u = v.fb_order[wid];
+    uint32_t *bp = bp_s + (size_t)warp_in_block * words_per_warp;
+    const int64_t f0 = v.frame_off[u];
+    const int T = (int)(v.frame_off[u + 1] - f0);
+    const int64_t p0 = v.pair_off[u];
+    const int L = (int)(v.pair_off[u + 1] - p0);
+    const int NE = PC_EMIT * L;
+    const int tp = pc_tpad(T);
+    const E *bu = b + v.emis_off[u];
+    const double NINF = -INFINITY;
+
+    double ls[SPL], ln[SPL], p[SPL];
+    int kind[SPL];
+    int64_t row[SPL];
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        const int s = lane * SPL + q;
+        row[q] = 0;
+        if (s == 0) {
+            const int unit = v.labels[p0];
+            kind[q] = 0;
+            ls[q] = log_self[unit * PC_STATES];
+            ln[q] = log_next[unit * PC_STATES];
+        } else if (s <= NE) {
+            const int pp = (s - 1) / PC_EMIT, r = (s - 1) - pp * PC_EMIT;
+            const int unit = v.labels[p0 + pp];
+            kind[q] = 1;
+            row[q] = (int64_t)(s - 1) * tp;
+            ls[q] = log_self[unit * PC_STATES + 1 + r];
+            ln[q] = log_next[unit * PC_STATES + 1 + r];  // into the exit state for s == NE: unused
+        } else {
+            kind[q] = 2;  // exit state (emission log 0) and padding: score stays -inf
+            ls[q] = NINF;
+            ln[q] = NINF;
+        }
+        double lpi = state_logpi ? ((s <= NE + 1) ? state_logpi[v.state_off[u] + s] : NINF)
+                                 : utt_logpi[u];
+        double e0 = kind[q] == 1 ? (double)bu[row[q]] : (kind[q] == 0 ? 0.0 : NINF);
+        p[q] = (kind[q] == 2) ? NINF : lpi + e0;
+    }
+    uint32_t bits[SPL];
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) bits[q] = 0u;
+    for (int t = 1; t < T; ++t) {
+        double left = __shfl_up_sync(0xffffffffu, p[SPL - 1] + ln[SPL - 1], 1);
+        if (lane == 0) left = NINF;
+        double np_[SPL];
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            const double move = (q > 0) ? p[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
+            const double stay = p[q] + ls[q];
+            const bool take = move >= stay;  // tie -> lower index (j-1)
+            const double best = take ? move : stay;
+            const double e = kind[q] == 1 ? (double)bu[row[q] + t] : (kind[q] == 0 ? 0.0 : NINF);
+            np_[q] = (kind[q] == 2) ? NINF : best + e;
+            bits[q] |= (take ? 1u : 0u) << (t & 31);
+        }
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) p[q] = np_[q];
+        if ((t & 31) == 31 || t == T - 1) {
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                bp[((t >> 5) * SPL + q) * 32 + lane] = bits[q];
+                bits[q] = 0u;
+            }
+        }
+    }
+    if (T == 1) {
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) bp[q * 32 + lane] = 0u;
+    }
+    __syncwarp();
+    // end state: first argmax over all states (LHMM.py:591)
+    double best = NINF;
+    int best_s = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        const int s = lane * SPL + q;
+        if (p[q] > best) { best = p[q]; best_s = s; }
+    }
+    if (best == NINF) best_s = 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
+        if (ob > best || (ob == best && os < best_s)) { best = ob; best_s = os; }
+    }
+    if (best_s == 0x7fffffff) best_s = 0;  // every score -inf: np.where(p == max)[0][0] == 0
+    if (lane == 0) score[u] = best;
+    // traceback (every lane follows the same chain; lane t%32 keeps state t, stores are coalesced)
+    int cur = best_s;
+    int keep = 0;
+    for (int t = T - 1; t >= 0; --t) {
+        if ((t & 31) == lane) keep = cur;
+        if ((t & 31) == 0) {
+            const int tt = t + lane;
+            if (tt < T) {
+                path[f0 + tt] = keep;
+                if (unit_path) {
+                    const int pos = keep == 0 ? 0 : (keep > NE ? L - 1 : (keep - 1) / PC_EMIT);
+                    unit_path[f0 + tt] = v.labels[p0 + pos];
+                }
+            }
+        }
+        if (t > 0) {
+            const uint32_t wbits = bp[((t >> 5) * SPL + (cur % SPL)) * 32 + (cur / SPL)];
+            cur -= (int)((wbits >> (t & 31)) & 1u);
+        }
+    }
+}
+
+template <int SPL, typename E>
+static int launch_vit(pc_handle h, const CorpusView &v, const E *b, const double *log_self,
+                      const double *log_next, const double *utt_logpi, const double *state_logpi,
+                      int32_t *path, int32_t *unit_path, double *score, cudaStream_t st) {
+    const int words = ((v.max_frames + 31) / 32) * 32 * SPL;
+    const size_t per_warp = (size_t)words * sizeof(uint32_t);
+    int warps = (int)((200 * 1024) / per_warp);
+    if (warps < 1) {
+        pc_set_error("pc_viterbi: %d frames x %d labels needs %zu B of backpointers per utterance "
+                     "(limit 200 KiB)", v.max_frames, v.max_labels, per_warp);
+        return PC_ERR_UNSUPPORTED;
+    }
+    if (warps > 4) warps = 4;
+    const size_t smem = per_warp * warps;
+    auto kern = viterbi_kernel<SPL, E>;
+    PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (v.n_utt + warps - 1) / warps;
+    kern<<<blocks, warps * 32, smem, st>>>(v, b, log_self, log_next, utt_logpi, state_logpi, path,
+                                           unit_path, score, words);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
+template <typename E>
+static int dispatch_vit(pc_handle h, const CorpusView &v, const E *b, const double *log_self,
+                        const double *log_next, const double *utt_logpi, const double *state_logpi,
+                        int32_t *path, int32_t *unit_path, double *score, cudaStream_t st) {
+    const int states = PC_EMIT * v.max_labels + 2;
+    if (states <= 32) return launch_vit<1, E>(h, v, b, log_self, log_next, utt_logpi, state_logpi, path, unit_path, score, st);
+    if (states <= 64) return launch_vit<2, E>(h, v, b, log_self, log_next, utt_logpi, state_logpi, path, unit_path, score, st);
+    if (states <= 128) return launch_vit<4, E>(h, v, b, log_self, log_next, utt_logpi, state_logpi, path, unit_path, score, st);
+    if (states <= 256) return launch_vit<8, E>(h, v, b, log_self, log_next, utt_logpi, state_logpi, path, unit_path, score, st);
+    pc_set_error("pc_viterbi: %d labels per utterance exceeds the limit of 84", v.max_labels);
+    return PC_ERR_UNSUPPORTED;
+}
+
+int launch_viterbi(pc_handle h, const CorpusView &v, const float *b, const double *b64,
+                   const double *log_self, const double *log_next, const double *utt_logpi,
+                   const double *state_logpi, int32_t *path, int32_t *unit_path, double *score,
+                   cudaStream_t st) {
+    if (v.n_utt == 0) return PC_OK;
+    if (b64) return dispatch_vit<double>(h, v, b64, log_self, log_next, utt_logpi, state_logpi, path, unit_path, score, st);
+    return dispatch_vit<float>(h, v, b, log_self, log_next, utt_logpi, state_logpi, path, unit_path, score, st);
+}

@@ -1,0 +1,311 @@
+"""Host side of the E-step engine: device buffers (torch tensors), streams, the EM iteration and the
+NCCL reduction of the accumulators.  Every number is produced by the CUDA kernels behind the C ABI
+(poccala_b200/_native.py); torch is plumbing (memory, streams, torch.distributed).
+
+Mirrors the work AcousticModel.embedded_training orchestrates per utterance / per unit
+(AcousticModel.py:842-935): multi_embedded_training_1 (score -> sentence HMM -> Baum-Welch ->
+accumulate) becomes three batched kernels over a resident corpus; the file-based accumulator
+merge (LHMM.py:256-290, Clustering.py:314-367) becomes device reductions plus one NCCL allreduce;
+multi_embedded_training_2 (update_param per unit) becomes one M-step kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from ._native import _p
+
+EMIT, STATES, XS, KA, SLOTS = nat.EMIT, nat.STATES, nat.XS, nat.KA, nat.TRANS_SLOTS
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One per GPU (pc_handle)."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("poccala_b200.Engine needs a CUDA device (B200); there is no CPU path")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        nat.call("pc_create", int(device), C.byref(h))
+        self.h = h
+
+    def close(self):
+        if self.h is not None:
+            nat.lib().pc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        nat.call("pc_set_option", self.h, key.encode(), int(value))
+
+    def get_option(self, key):
+        return int(nat.lib().pc_get_option(self.h, key.encode()))
+
+    @property
+    def launches(self):
+        return self.get_option("launches")
+
+    # ------------------------------------------------------------------ buffers
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def corpus(self, labels, n_frames, n_units):
+        return Corpus(self, labels, n_frames, n_units)
+
+    # ------------------------------------------------------------------ kernels
+    def pack_gmm(self, mean, var, alpha, shift=None, inv_scale=None, out=None):
+        """mean/var [G,D] fp64 cuda, alpha [G] -> W [G,80] fp32 (pc_pack_gmm)."""
+        G, D = mean.shape
+        W = out if out is not None else self.empty((G, KA), torch.float32)
+        nat.call("pc_pack_gmm", self.h, _p(mean), _p(var), _p(alpha), _p(shift), _p(inv_scale), G, D, _p(W),
+                 _stream())
+        return W
+
+    def prepare_frames(self, x, shift=None, inv_scale=None, out=None):
+        """x [F,D] fp32/fp64 cuda -> X [F,40] fp32 standardised (pc_prepare_frames_*)."""
+        F, D = x.shape
+        if D > nat.DIM_MAX:
+            raise ValueError("feature dimension %d exceeds %d" % (D, nat.DIM_MAX))
+        x = x.contiguous()
+        X = out if out is not None else self.empty((F, XS), torch.float32)
+        fn = "pc_prepare_frames_f64" if x.dtype == torch.float64 else "pc_prepare_frames_f32"
+        if x.dtype not in (torch.float32, torch.float64):
+            raise TypeError("frames must be float32 or float64")
+        nat.call(fn, self.h, _p(x), F, D, _p(shift), _p(inv_scale), _p(X), _stream())
+        return X
+
+    def score_dense(self, X, W, n_states, mix, out=None):
+        F = X.shape[0]
+        out = out if out is not None else self.empty((F, n_states), torch.float32)
+        nat.call("pc_gmm_score_dense", self.h, _p(X), F, _p(W), n_states, mix, _p(out), _stream())
+        return out
+
+
+class Corpus:
+    """Descriptor tables of a set of utterances (pc_corpus) + the resident frame matrix."""
+
+    def __init__(self, engine, labels, n_frames, n_units):
+        self.engine = engine
+        n_frames = np.ascontiguousarray(n_frames, dtype=np.int32)
+        if isinstance(labels, np.ndarray) and labels.ndim == 2:
+            n_labels = np.full(labels.shape[0], labels.shape[1], dtype=np.int32)
+            flat = np.ascontiguousarray(labels.reshape(-1), dtype=np.int32)
+        else:
+            n_labels = np.array([len(l) for l in labels], dtype=np.int32)
+            flat = (np.ascontiguousarray(np.concatenate([np.asarray(l, dtype=np.int32) for l in labels]))
+                    if len(labels) else np.zeros(0, np.int32))
+        if len(n_labels) != len(n_frames):
+            raise ValueError("labels / n_frames length mismatch")
+        self.n_utt = len(n_frames)
+        self.n_units = int(n_units)
+        self.n_frames = n_frames
+        self.n_labels = n_labels
+        self.labels_flat = flat
+        c = C.c_void_p()
+        nat.call("pc_corpus_create", engine.h, self.n_utt, _p(n_frames), _p(n_labels), _p(flat), self.n_units,
+                 C.byref(c))
+        self.c = c
+        l = nat.lib()
+        self.total_frames = int(l.pc_corpus_total_frames(c))
+        self.emis_floats = int(l.pc_corpus_emission_floats(c))
+        self.n_pairs = int(l.pc_corpus_total_pairs(c))
+        self.total_states = int(l.pc_corpus_total_states(c))
+        offs = [np.empty(self.n_utt + 1, dtype=np.int64) for _ in range(4)]
+        nat.call("pc_corpus_offsets", c, *[_p(o) for o in offs])
+        self.frame_off, self.emis_off, self.pair_off, self.state_off = offs
+        self.X = None
+
+    def close(self):
+        if self.c is not None:
+            nat.lib().pc_corpus_destroy(self.c)
+            self.c = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def emission_view(self, buf, u):
+        """[3L, T] view of utterance u inside a b / lgam buffer."""
+        T, L = int(self.n_frames[u]), int(self.n_labels[u])
+        tp = (T + 3) & ~3
+        return buf[self.emis_off[u]:self.emis_off[u + 1]].view(EMIT * L, tp)[:, :T]
+
+
+class Model:
+    """GMM-HMM parameters resident on the device (fp64, the reference's precision).
+    mean/var [U,3,M,D], alpha [U,3,M], transmat [U,5,5]."""
+
+    def __init__(self, engine, mean, var, alpha, transmat):
+        dev = engine.device
+        self.engine = engine
+        self.mean = torch.as_tensor(np.asarray(mean), dtype=torch.float64).to(dev).contiguous()
+        self.var = torch.as_tensor(np.asarray(var), dtype=torch.float64).to(dev).contiguous()
+        self.alpha = torch.as_tensor(np.asarray(alpha), dtype=torch.float64).to(dev).contiguous()
+        self.transmat = torch.as_tensor(np.asarray(transmat), dtype=torch.float64).to(dev).contiguous()
+        self.n_units, _, self.mix, self.dim = self.mean.shape
+        self.n_gauss = self.n_units * EMIT * self.mix
+        self.W = engine.empty((self.n_gauss, KA), torch.float32)
+
+    def pack(self, shift=None, inv_scale=None):
+        self.engine.pack_gmm(self.mean.view(self.n_gauss, self.dim), self.var.view(self.n_gauss, self.dim),
+                             self.alpha.view(self.n_gauss), shift, inv_scale, out=self.W)
+        return self.W
+
+    def log_bands(self):
+        """log of the diagonal / super-diagonal of every unit transmat, [U,5] each (device, fp64)."""
+        with np.errstate(divide="ignore"):
+            ls = torch.log(torch.diagonal(self.transmat, dim1=1, dim2=2)).contiguous()
+            ln = torch.full_like(ls, float("-inf"))
+            ln[:, :-1] = torch.log(torch.diagonal(self.transmat, offset=1, dim1=1, dim2=2))
+        return ls, ln.contiguous()
+
+    def numpy(self):
+        return (self.mean.cpu().numpy(), self.var.cpu().numpy(), self.alpha.cpu().numpy(),
+                self.transmat.cpu().numpy())
+
+
+class EStep:
+    """Buffers and kernels of one EM iteration over a resident corpus."""
+
+    def __init__(self, engine, corpus, model, standardise=True):
+        self.engine, self.corpus, self.model = engine, corpus, model
+        e = engine
+        self.b = e.empty((max(corpus.emis_floats, 1),), torch.float32)
+        self.lgam = e.empty((max(corpus.emis_floats, 1),), torch.float32)
+        self.utt_logp = e.empty((corpus.n_utt,), torch.float64)
+        self.utt_iters = e.empty((corpus.n_utt,), torch.int32)
+        self.pair_trans = e.empty((max(corpus.n_pairs, 1), SLOTS), torch.float32)
+        self.acc = e.empty((model.n_gauss, KA), torch.float64)
+        self.tmax = e.empty((model.n_units, SLOTS), torch.float64)
+        self.tsum = e.empty((model.n_units, SLOTS), torch.float64)
+        self.shift = None
+        self.inv_scale = None
+        self.standardise = standardise
+
+    # frames -------------------------------------------------------------------------------
+    def load_frames(self, x):
+        """x: [F,D] float tensor on the device (utterances concatenated in corpus order)."""
+        if x.shape[0] != self.corpus.total_frames:
+            raise ValueError("expected %d frames, got %d" % (self.corpus.total_frames, x.shape[0]))
+        if self.standardise:
+            xd = x.to(torch.float64)
+            mu = xd.mean(dim=0)
+            sd = xd.std(dim=0, unbiased=False).clamp_min(1e-12)
+            self.shift = mu.contiguous()
+            self.inv_scale = (1.0 / sd).contiguous()
+        self.corpus.X = self.engine.prepare_frames(x, self.shift, self.inv_scale, out=self.corpus.X)
+        return self.corpus.X
+
+    # kernels ------------------------------------------------------------------------------
+    def score(self):
+        m = self.model
+        m.pack(self.shift, self.inv_scale)
+        nat.call("pc_gmm_score", self.engine.h, self.corpus.c, _p(self.corpus.X), _p(m.W), m.mix, _p(self.b),
+                 _stream())
+
+    def forward_backward(self):
+        ls, ln = self.model.log_bands()
+        nat.call("pc_forward_backward", self.engine.h, self.corpus.c, _p(self.b), _p(ls), _p(ln), _p(self.lgam),
+                 _p(self.utt_logp), _p(self.utt_iters), _p(self.pair_trans), _stream())
+
+    def accumulate(self):
+        m = self.model
+        self.acc.zero_()
+        nat.call("pc_accumulate", self.engine.h, self.corpus.c, _p(self.corpus.X), _p(m.W), m.mix, _p(self.b),
+                 _p(self.lgam), _p(self.acc), _stream())
+
+    def reduce_transitions(self, group=None):
+        self.tmax.fill_(float("-inf"))
+        self.tsum.zero_()
+        nat.call("pc_transitions_max", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
+                 _p(self.tmax), _stream())
+        if group is not None:
+            torch.distributed.all_reduce(self.tmax, op=torch.distributed.ReduceOp.MAX, group=group)
+        nat.call("pc_transitions_sum", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
+                 _p(self.tmax), _p(self.tsum), _stream())
+
+    def estep(self, fix_code=0, group=None):
+        """K1 -> K2 -> K3 -> transition reduction (+ allreduce when `group` is a process group)."""
+        self.score()
+        self.forward_backward()
+        if not (fix_code & 2):
+            self.accumulate()
+        else:
+            self.acc.zero_()
+        self.reduce_transitions(group)
+        if group is not None:
+            torch.distributed.all_reduce(self.acc, group=group)
+            torch.distributed.all_reduce(self.tsum, group=group)
+
+    def mstep(self, c_covariance=1e-3, fix_code=0):
+        m = self.model
+        nat.call("pc_update_params", self.engine.h, m.n_units, m.mix, m.dim, _p(self.acc), _p(self.tmax),
+                 _p(self.tsum), _p(self.shift), _p(self.inv_scale), float(c_covariance), int(fix_code),
+                 _p(m.mean), _p(m.var), _p(m.alpha), _p(m.transmat), _stream())
+
+    def em_iteration(self, c_covariance=1e-3, fix_code=0, group=None):
+        self.estep(fix_code, group)
+        self.mstep(c_covariance, fix_code)
+
+    # views --------------------------------------------------------------------------------
+    def transition_accumulators(self):
+        """(ksai_acc [U,3,5], gamma_acc [U,3]) in the reference's log domain (LHMM.py:84-85)."""
+        acc = (self.tmax + torch.log(self.tsum)).cpu().numpy().reshape(-1, EMIT, 3)
+        U = acc.shape[0]
+        ksai = np.full((U, EMIT, STATES), -np.inf)
+        for r in range(EMIT):
+            ksai[:, r, r + 1] = acc[:, r, 0]
+            ksai[:, r, r + 2] = acc[:, r, 1]
+        return ksai, acc[:, :, 2].copy()
+
+
+def viterbi(engine, corpus, b, log_self, log_next, utt_logpi=None, state_logpi=None, want_units=True):
+    """pc_viterbi.  b: float32 or float64 emission buffer (corpus layout); log_self/log_next
+    [U,5] fp64 device tensors computed on the host with numpy; logpi per utterance or per state."""
+    path = engine.empty((corpus.total_frames,), torch.int32)
+    units = engine.empty((corpus.total_frames,), torch.int32) if want_units else None
+    score = engine.empty((corpus.n_utt,), torch.float64)
+    b32 = b if b.dtype == torch.float32 else None
+    b64 = b if b.dtype == torch.float64 else None
+    nat.call("pc_viterbi", engine.h, corpus.c, _p(b32), _p(b64), _p(log_self), _p(log_next), _p(utt_logpi),
+             _p(state_logpi), _p(path), _p(units), _p(score), _stream())
+    return score, path, units
+
+
+def host_log_bands(transmat, device):
+    """np.log of the diagonal / super-diagonal of [U,5,5] transmat (host numpy: bit-exact with the
+    reference's np.log(transmat), LHMM.py:340,574)."""
+    tm = np.asarray(transmat, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        ls = np.log(np.diagonal(tm, axis1=1, axis2=2))
+        ln = np.full_like(ls, -np.inf)
+        ln[:, :-1] = np.log(np.diagonal(tm, offset=1, axis1=1, axis2=2))
+    return (torch.as_tensor(np.ascontiguousarray(ls)).to(device), torch.as_tensor(np.ascontiguousarray(ln)).to(device))
+
+
+def em_iteration_host(engine, corpus, frames, mean, var, alpha, transmat, c_covariance=1e-3, fix_code=0):
+    """pc_em_iteration_host: host numpy buffers in, parameters updated in place, returns sum logP."""
+    frames = np.ascontiguousarray(frames, dtype=np.float32)
+    for a in (mean, var, alpha, transmat):
+        if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
+            raise TypeError("parameters must be C-contiguous float64 numpy arrays (updated in place)")
+    U, _, M, D = mean.shape
+    out = C.c_double(0.0)
+    nat.call("pc_em_iteration_host", engine.h, corpus.c, _p(frames), D, U, M, _p(mean), _p(var), _p(alpha),
+             _p(transmat), float(c_covariance), int(fix_code), C.byref(out), _stream())
+    return out.value

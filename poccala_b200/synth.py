@@ -122,7 +122,7 @@ def make_corpus(n_utt, T, L, n_units, mix, cfg_seed, n_initials=None, ragged=Fal
 
 
 # --------------------------------------------------------------------------- torch (bench scale)
-def torch_corpus(n_utt, T, L, n_units, mix, seed, device, n_initials=None, dim=DIM):
+def torch_corpus(n_utt, T, L, n_units, mix, seed, device, n_initials=None, dim=DIM, data_seed=None):
     """Fixed-shape corpus generated on ``device``: returns (truth, init, labels[n_utt,L] int32 numpy,
     X[n_utt*T, D] float32 device tensor).  Durations are near-uniform with jitter; frames are drawn
     from the owning state's GMM.  Same hierarchical model as the numpy generator."""
@@ -130,9 +130,10 @@ def torch_corpus(n_utt, T, L, n_units, mix, seed, device, n_initials=None, dim=D
 
     truth = make_truth(n_units, mix, 1000 * seed + 7, dim)
     init = perturb(*truth, seed=1000 * seed + 11)
-    labels = random_labels(n_utt, L, n_units, 1000 * seed + 17, n_initials)
+    data_seed = seed if data_seed is None else data_seed  # same model, different utterances per rank
+    labels = random_labels(n_utt, L, n_units, 1000 * data_seed + 17, n_initials)
     g = torch.Generator(device=device)
-    g.manual_seed(1000 * seed + 19)
+    g.manual_seed(1000 * data_seed + 19)
     n_states = EMIT * L
     mean_t = torch.as_tensor(truth[0], dtype=torch.float32, device=device).reshape(n_units * EMIT, mix, dim)
     std_t = torch.as_tensor(np.sqrt(truth[1]), dtype=torch.float32, device=device).reshape(n_units * EMIT, mix, dim)

@@ -1,0 +1,281 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+vectors produced by the executed reference.  Tolerances are the ones BASELINE.json's north_star
+states: Viterbi paths bit-exact given identical emissions; log-likelihoods, posteriors and
+re-estimated parameters within 1e-4 relative (fp32 kernels vs the fp64 reference)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import fast  # noqa: E402  (test infrastructure: the checker)
+from poccala_b200 import synth  # noqa: E402
+from tests.helpers import load_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from poccala_b200.engine import Engine
+
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _corpus(eng, labels, utts, n_units):
+    from poccala_b200.engine import Corpus
+
+    return Corpus(eng, labels, np.array([len(x) for x in utts], dtype=np.int32), n_units)
+
+
+def _setup(eng, init, labels, utts, n_units, transmat=None, standardise=True):
+    from poccala_b200.engine import EStep, Model
+
+    mean, var, alpha = init
+    tm = synth.default_transmat(n_units) if transmat is None else transmat
+    corpus = _corpus(eng, labels, utts, n_units)
+    model = Model(eng, mean, var, alpha, tm)
+    es = EStep(eng, corpus, model, standardise=standardise)
+    es.load_frames(torch.as_tensor(np.concatenate(utts, axis=0)).to(eng.device))
+    return corpus, model, es, fast.Model(mean, var, alpha, tm)
+
+
+def _relerr(a, b, floor=1e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
+
+
+def _ragged(cfg_seed=3, n_utt=14, T=60, L=4, n_units=5, mix=4):
+    truth, init, labels, utts = synth.make_corpus(n_utt, T, L, n_units, mix, cfg_seed, ragged=True)
+    return init, labels, utts, n_units
+
+
+@pytest.mark.parametrize("standardise", [True, False])
+def test_scores_match_oracle(eng, standardise):
+    init, labels, utts, n_units = _ragged()
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units, standardise=standardise)
+    es.score()
+    torch.cuda.synchronize()
+    for u, (lab, X) in enumerate(zip(labels, utts)):
+        c = fast.score_components_direct(om, lab[None], X[None])
+        b_ref = fast.lse(c, axis=-1)[0].T  # [3L, T]
+        b_gpu = corpus.emission_view(es.b, u).cpu().numpy()
+        assert _relerr(b_gpu, b_ref) < REL
+        # what the kernels actually reach (fp32 contraction): two orders better than required
+        assert np.abs(b_gpu - b_ref).max() < 2e-3
+
+
+def test_forward_backward_matches_oracle(eng):
+    init, labels, utts, n_units = _ragged(cfg_seed=4, n_utt=20, T=90, L=5)
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
+    es.score()
+    es.forward_backward()
+    torch.cuda.synchronize()
+    logp = es.utt_logp.cpu().numpy()
+    iters = es.utt_iters.cpu().numpy()
+    pt = es.pair_trans.cpu().numpy()
+    for u, (lab, X) in enumerate(zip(labels, utts)):
+        r = fast.estep_batch(om, lab[None], X[None], keep=True)
+        assert abs(logp[u] - r["logp"][0]) <= REL * abs(r["logp"][0])
+        assert abs(logp[u] - r["logp"][0]) < 5e-3  # achieved: ~1e-7 relative
+        assert iters[u] == r["iters"][0]
+        g_gpu = np.exp(corpus.emission_view(es.lgam, u).cpu().numpy().astype(np.float64))
+        g_ref = np.exp(r["lgam"][0].T)
+        # posteriors: 1e-4 relative, with an absolute floor for posteriors below 1e-2
+        assert np.all(np.abs(g_gpu - g_ref) <= REL * np.maximum(g_ref, 1e-2))
+        L = len(lab)
+        p0 = corpus.pair_off[u]
+        for p in range(L):
+            for rr in range(3):
+                s = 1 + 3 * p + rr
+                ref = np.array([r["k_self"][0][s], r["k_next"][0][s], r["gamma"][0][s]])
+                got = logp[u] + pt[p0 + p, 3 * rr:3 * rr + 3].astype(np.float64)
+                fin = np.isfinite(ref)
+                assert (np.isfinite(got) == fin).all()
+                # unnormalised log accumulators (Q6), magnitude ~1e3..1e5
+                assert np.all(np.abs(got[fin] - ref[fin]) <= REL * np.abs(ref[fin]))
+                assert np.all(np.abs(got[fin] - ref[fin]) < 2e-2)
+
+
+def test_accumulators_and_mstep_match_oracle(eng):
+    init, labels, utts, n_units = _ragged(cfg_seed=5, n_utt=24, T=80, L=4, n_units=4)
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
+    es.estep()
+    torch.cuda.synchronize()
+    stats, info = fast.estep_corpus(om, labels, utts)
+    acc = es.acc.cpu().numpy().reshape(n_units, 3, om.mix, 80)
+    occ = acc[..., 78]
+    assert _relerr(occ, stats.occ, floor=1e-3) < REL
+    assert np.allclose(acc[..., 79], occ)
+    # first moments live in the standardised space of X: map the oracle's into it
+    sh = es.shift.cpu().numpy()
+    isc = es.inv_scale.cpu().numpy()
+    sx_ref = (stats.sx - sh * stats.occ[..., None]) * isc
+    assert np.all(np.abs(acc[..., :39] - sx_ref) <= REL * np.maximum(np.abs(sx_ref), 1e-2 * stats.occ[..., None] + 1e-3))
+    ksai, gam = es.transition_accumulators()
+    fin = np.isfinite(stats.ksai_acc)
+    assert (np.isfinite(ksai) == fin).all()
+    assert np.all(np.abs(ksai[fin] - stats.ksai_acc[fin]) <= REL * np.abs(stats.ksai_acc[fin]))
+    assert np.all(np.abs(gam - stats.gamma_acc) <= REL * np.abs(stats.gamma_acc))
+    es.mstep(c_covariance=1e-6)
+    torch.cuda.synchronize()
+    new = fast.mstep(om, stats, c_covariance=1e-6)
+    mean, var, alpha, tm = model.numpy()
+    assert _relerr(alpha, new.alpha, floor=1e-3) < REL
+    assert np.all(np.abs(mean - new.mean) <= REL * np.maximum(np.abs(new.mean), np.sqrt(new.var)))
+    assert _relerr(var, new.var) < 5 * REL  # variance = difference of moments: a few 1e-5 achieved
+    assert np.all(np.abs(tm - new.transmat) <= REL * np.maximum(new.transmat, 1e-2))
+
+
+def test_em_iteration_matches_executed_reference(eng):
+    """tests/golden/estep_small.npz holds one full file-based EM iteration run by the unmodified
+    reference (AcousticModel.multi_embedded_training_1/_2)."""
+    g = load_golden("estep_small.npz")
+    n = int(g["n_utt"])
+    labels = [g[f"u{k}_label"] for k in range(n)]
+    utts = [g[f"u{k}_X"] for k in range(n)]
+    init = (g["mean"], g["var"], g["alpha"])
+    corpus, model, es, om = _setup(eng, init, labels, utts, 3)
+    es.score()
+    es.forward_backward()
+    torch.cuda.synchronize()
+    for k in range(n):
+        B = g[f"u{k}_B"]
+        assert _relerr(corpus.emission_view(es.b, k).cpu().numpy(), B[1:-1]) < REL
+        ab = g[f"u{k}_alpha"] + g[f"u{k}_beta"]
+        lg_ref = ab - fast.lse(ab, axis=0, keepdims=True)
+        got = np.exp(corpus.emission_view(es.lgam, k).cpu().numpy().astype(np.float64))
+        assert np.all(np.abs(got - np.exp(lg_ref[1:-1])) <= REL * np.maximum(np.exp(lg_ref[1:-1]), 1e-2))
+    es.accumulate()
+    es.reduce_transitions()
+    es.mstep(c_covariance=1e-6)
+    torch.cuda.synchronize()
+    mean, var, alpha, tm = model.numpy()
+    assert _relerr(alpha, g["it1_alpha"], floor=1e-3) < REL
+    assert np.all(np.abs(mean - g["it1_mean"]) <= REL * np.maximum(np.abs(g["it1_mean"]), np.sqrt(g["it1_var"])))
+    assert _relerr(var, g["it1_var"]) < 5 * REL
+    assert np.all(np.abs(tm - g["it1_transmat"]) <= REL * np.maximum(g["it1_transmat"], 1e-2))
+
+
+def test_host_entry_point_matches_device_path(eng):
+    from poccala_b200.engine import em_iteration_host
+
+    init, labels, utts, n_units = _ragged(cfg_seed=6, n_utt=10, T=50, L=3, n_units=4)
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units, standardise=False)
+    es.em_iteration(c_covariance=1e-6)
+    torch.cuda.synchronize()
+    mean, var, alpha = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init]
+    tm = synth.default_transmat(n_units).copy()
+    slp = em_iteration_host(eng, corpus, np.concatenate(utts).astype(np.float32), mean, var, alpha, tm,
+                            c_covariance=1e-6)
+    m2, v2, a2, t2 = model.numpy()
+    assert abs(slp - float(es.utt_logp.sum())) < 1e-6 * abs(slp)
+    assert np.allclose(mean, m2, rtol=1e-5, atol=1e-6)
+    assert np.allclose(var, v2, rtol=1e-4, atol=1e-7)
+    assert np.allclose(alpha, a2, rtol=1e-5)
+    assert np.allclose(tm, t2, rtol=1e-5, atol=1e-9)
+
+
+def _viterbi_check(eng, labels, utts, init, n_units, transmat=None, emissions64=None):
+    from poccala_b200.engine import host_log_bands, viterbi
+
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units, transmat=transmat)
+    ls, ln = host_log_bands(om.transmat, eng.device)
+    logpi = torch.as_tensor(np.array([np.log(np.ones(3 * len(l) + 2) / (3 * len(l) + 2))[0] for l in labels])).to(eng.device)
+    if emissions64 is None:
+        es.score()
+        b = es.b
+    else:
+        b = emissions64
+    score, path, units = viterbi(eng, corpus, b, ls, ln, utt_logpi=logpi)
+    torch.cuda.synchronize()
+    score, path, units = score.cpu().numpy(), path.cpu().numpy(), units.cpu().numpy()
+    for u, lab in enumerate(labels):
+        e = corpus.emission_view(b, u).cpu().numpy().astype(np.float64)  # identical emission scores
+        ols, oln = fast.banded_transitions(om, np.asarray(lab)[None])
+        sc, pa = fast.viterbi_banded(ols, oln, fast.full_emissions(e.T[None]))
+        f0, f1 = corpus.frame_off[u], corpus.frame_off[u + 1]
+        assert score[u] == sc[0], (u, score[u], sc[0])  # bit-exact fp64
+        assert (path[f0:f1] == pa[0]).all()
+        unit_of_state = np.array([lab[0]] + [x for x in lab for _ in range(3)] + [lab[-1]])
+        assert (units[f0:f1] == unit_of_state[pa[0]]).all()
+    return corpus
+
+
+def test_viterbi_bit_exact_ragged(eng):
+    init, labels, utts, n_units = _ragged(cfg_seed=7, n_utt=30, T=120, L=6, n_units=6)
+    _viterbi_check(eng, labels, utts, init, n_units)
+
+
+def test_viterbi_bit_exact_two_states_per_lane(eng):
+    truth, init, labels, utts = synth.make_corpus(6, 200, 20, 8, 4, 9)  # N = 62 > 32 lanes
+    _viterbi_check(eng, labels, utts, init, 8)
+
+
+def test_viterbi_single_frame_and_trained_transitions(eng):
+    truth, init, labels, utts = synth.make_corpus(5, 40, 3, 4, 4, 10, ragged=True)
+    utts[0] = utts[0][:1]  # T = 1
+    rng = np.random.default_rng(0)
+    tm = synth.default_transmat(4)
+    for u in range(4):
+        for j in range(1, 4):
+            a = rng.uniform(0.2, 0.8)
+            tm[u, j, j], tm[u, j, j + 1] = a, 1 - a
+    _viterbi_check(eng, labels, utts, init, 4, transmat=tm)
+
+
+def test_viterbi_ties_golden(eng):
+    """Integer emissions force exact ties; expected paths come from the executed reference."""
+    from poccala_b200.engine import Corpus, host_log_bands, viterbi
+
+    v = load_golden("viterbi_ties.npz")
+    for k in range(int(v["n"])):
+        A, B = v[f"v{k}_A"], v[f"v{k}_B"]
+        N, T = B.shape
+        L = (N - 2) // 3
+        corpus = Corpus(eng, [np.zeros(L, dtype=np.int32)], np.array([T], dtype=np.int32), 1)
+        tp = (T + 3) & ~3
+        buf = np.zeros((3 * L, tp))
+        buf[:, :T] = B[1:-1]
+        b64 = torch.as_tensor(buf.reshape(-1)).to(eng.device)
+        tm = np.zeros((1, 5, 5))
+        tm[0, 0, 1] = 1.0
+        for j in range(1, 4):
+            tm[0, j, j] = tm[0, j, j + 1] = 0.5
+        ls, ln = host_log_bands(tm, eng.device)
+        logpi = torch.as_tensor(np.array([np.log(np.ones(N) / N)[0]])).to(eng.device)
+        score, path, _ = viterbi(eng, corpus, b64, ls, ln, utt_logpi=logpi)
+        assert float(score[0]) == float(v[f"v{k}_score"])
+        assert (path.cpu().numpy() == v[f"v{k}_path"].astype(np.int64)).all()
+
+
+def test_dense_scoring_matches_oracle(eng):
+    rng = np.random.default_rng(11)
+    n_states, mix, F = 7, 8, 300
+    mean = rng.normal(size=(n_states * mix, 39))
+    var = rng.uniform(0.5, 1.5, size=(n_states * mix, 39))
+    alpha = rng.dirichlet(np.full(mix, 2.0), size=n_states).reshape(-1)
+    x = rng.normal(size=(F, 39))
+    dev = eng.device
+    W = eng.pack_gmm(torch.as_tensor(mean).to(dev), torch.as_tensor(var).to(dev), torch.as_tensor(alpha).to(dev))
+    X = eng.prepare_frames(torch.as_tensor(x).to(dev))
+    out = eng.score_dense(X, W, n_states, mix).cpu().numpy()
+    d = x[:, None, :] - mean[None]
+    c = np.log(alpha) - 39 / 2 * np.log(2 * np.pi) - 0.5 * var.sum(-1) - 0.5 * (d * d / var).sum(-1)
+    ref = fast.lse(c.reshape(F, n_states, mix), axis=-1)
+    assert _relerr(out, ref) < REL
+
+
+def test_error_behaviour(eng):
+    from poccala_b200 import _native as nat
+    from poccala_b200.engine import Corpus
+
+    with pytest.raises(ValueError):
+        eng.prepare_frames(torch.zeros((4, 40), device=eng.device))  # DataDimensionError analogue
+    with pytest.raises(nat.NativeError):
+        Corpus(eng, [np.array([0, 7])], np.array([10], dtype=np.int32), 3)  # label outside the unit set
+    with pytest.raises(nat.NativeError):
+        Corpus(eng, [np.array([0])], np.array([0], dtype=np.int32), 3)  # empty utterance
