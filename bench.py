@@ -112,39 +112,60 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML every ~2 ms while the timed region runs
+    (nvidia-smi is too slow for a region of tens of milliseconds)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
+        self.max_mhz = None
+        self.err = None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except ValueError:
+                    idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop.is_set():
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h)),
+                                  time.perf_counter()))
+                self.stop.wait(0.002)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
         self.stop.set()
         self.th.join(timeout=6)
 
-    def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+    def summary(self, t0=None, t1=None):
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[2] <= t1]
+            self.rows = inside if inside else self.rows[-1:]
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n, b in bits.items() if r[1] & b})
+        out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+               "samples": len(sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -281,7 +302,7 @@ def run_gpu(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "l2": "256 MiB memset between timed steps (outside the per-step events)",
                    "wall_s_timed_region": wall, "parallelism": "dp%d" % world},
-        "clocks": clocks.summary(),
+        "clocks": clocks.summary(w0, w0 + wall),
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "api": "pc_em_iteration_host"},
         "gpu_launches": int(launches),

@@ -31,6 +31,16 @@ __device__ __forceinline__ float fb_emis(const FbState<SPL> &s, const float *__r
     return s.kind[q] == 1 ? bu[s.row[q] + t] : (s.kind[q] == 0 ? 0.f : PC_NEG_INF);
 }
 
+// online log-sum-exp accumulator: sum * exp(mx) += exp(x)
+__device__ __forceinline__ void acc_lse(float &mx, float &sum, float x) {
+    if (x == PC_NEG_INF) return;
+    if (x > mx) {
+        sum *= __expf(mx - x);
+        mx = x;
+    }
+    sum += __expf(x - mx);
+}
+
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -147,7 +157,9 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
     }
 
     // ---------------------------------------------------------------- forward (LHMM.py:335-351)
-    float ah[SPL], cs[SPL], cn[SPL], cg[SPL], bcur[SPL];
+    // transition counters are kept as (max, scaled sum) pairs so that counts far below the fp32
+    // range (states the alignment never visits) keep a finite log like the fp64 reference
+    float ah[SPL], cs[SPL], cn[SPL], cg[SPL], ms[SPL], mn[SPL], mg[SPL], bcur[SPL];
     double Ca;
     {
         float mx = PC_NEG_INF;
@@ -156,6 +168,7 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             ah[q] = (float)lp_used[q] + fb_emis(st, bu, q, 0);
             mx = fmaxf(mx, ah[q]);
             cs[q] = cn[q] = cg[q] = 0.f;
+            ms[q] = mn[q] = mg[q] = PC_NEG_INF;
         }
         mx = warp_max(mx);
         if (mx == PC_NEG_INF) mx = 0.f;
@@ -205,11 +218,20 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             for (int q = 0; q < SPL; ++q) {
                 const float nxt = (q + 1 < SPL) ? nb[(q + 1) % SPL] : up;
                 const float sv = st.ls[q] + nb[q], mv = st.ln[q] + nxt;
-                const float frac = (sv == PC_NEG_INF) ? 0.f : 1.f / (1.f + __expf(mv - sv));
-                const float g = __expf(lg[q]);
-                cg[q] += g;
-                cs[q] += g * frac;
-                cn[q] += g * (1.f - frac);
+                // log of the self / next shares of gamma_t(i): -softplus(mv-sv), (mv-sv)-softplus
+                float lfs, lfn;
+                if (sv == PC_NEG_INF) {
+                    lfs = PC_NEG_INF;
+                    lfn = (mv == PC_NEG_INF) ? PC_NEG_INF : 0.f;
+                } else {
+                    const float d = mv - sv;  // -inf when the successor carries no mass
+                    const float sp = fmaxf(d, 0.f) + __logf(1.f + __expf(-fabsf(d)));
+                    lfs = -sp;
+                    lfn = (d == PC_NEG_INF) ? PC_NEG_INF : d - sp;
+                }
+                acc_lse(mg[q], cg[q], lg[q]);
+                acc_lse(ms[q], cs[q], lg[q] + lfs);
+                acc_lse(mn[q], cn[q], lg[q] + lfn);
             }
         }
         // overwrite beta_hat_t with log gamma_t (beta_hat_{t+1} is already in registers)
@@ -243,9 +265,9 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             const int s = lane * SPL + q;
             float *o = pair_trans + (size_t)(p0 + (s - 1) / PC_EMIT) * PC_TRANS_SLOTS +
                        ((s - 1) % PC_EMIT) * 3;
-            o[0] = __logf(cs[q]);
-            o[1] = __logf(cn[q]);
-            o[2] = __logf(cg[q]);
+            o[0] = (ms[q] == PC_NEG_INF) ? PC_NEG_INF : ms[q] + __logf(cs[q]);
+            o[1] = (mn[q] == PC_NEG_INF) ? PC_NEG_INF : mn[q] + __logf(cn[q]);
+            o[2] = (mg[q] == PC_NEG_INF) ? PC_NEG_INF : mg[q] + __logf(cg[q]);
         }
     }
     if (lane == 0) {

@@ -48,6 +48,15 @@ def _relerr(a, b, floor=1e-6):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
 
+def _var_close(var, ref, utts):
+    """Variances come out of an fp32 contraction as a difference of moments (sxx - 2 mu sx + mu^2 occ),
+    so their absolute error scales with the spread of the data, not with the variance itself:
+    1e-4 relative for every variance above 1% of the feature's global variance, and the same
+    absolute error (1e-6 of the global variance) for collapsed components below that."""
+    gvar = np.concatenate(utts, axis=0).var(axis=0)
+    return np.all(np.abs(var - ref) <= REL * np.maximum(ref, 1e-2 * gvar))
+
+
 def _ragged(cfg_seed=3, n_utt=14, T=60, L=4, n_units=5, mix=4):
     truth, init, labels, utts = synth.make_corpus(n_utt, T, L, n_units, mix, cfg_seed, ragged=True)
     return init, labels, utts, n_units
@@ -126,7 +135,7 @@ def test_accumulators_and_mstep_match_oracle(eng):
     mean, var, alpha, tm = model.numpy()
     assert _relerr(alpha, new.alpha, floor=1e-3) < REL
     assert np.all(np.abs(mean - new.mean) <= REL * np.maximum(np.abs(new.mean), np.sqrt(new.var)))
-    assert _relerr(var, new.var) < 5 * REL  # variance = difference of moments: a few 1e-5 achieved
+    assert _var_close(var, new.var, utts)
     assert np.all(np.abs(tm - new.transmat) <= REL * np.maximum(new.transmat, 1e-2))
 
 
@@ -156,7 +165,7 @@ def test_em_iteration_matches_executed_reference(eng):
     mean, var, alpha, tm = model.numpy()
     assert _relerr(alpha, g["it1_alpha"], floor=1e-3) < REL
     assert np.all(np.abs(mean - g["it1_mean"]) <= REL * np.maximum(np.abs(g["it1_mean"]), np.sqrt(g["it1_var"])))
-    assert _relerr(var, g["it1_var"]) < 5 * REL
+    assert _var_close(var, g["it1_var"], utts)
     assert np.all(np.abs(tm - g["it1_transmat"]) <= REL * np.maximum(g["it1_transmat"], 1e-2))
 
 
