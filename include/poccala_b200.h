@@ -20,9 +20,9 @@
  *
  * Data layout in HBM
  *   X      float [n_frames_total][PC_XS]   standardised frames; cols [0,D) data, col 39 = 1.0
- *   W      float [n_gauss][PC_KA]          packed Gaussians: mu/var | -1/(2 var) | k_hi | k_lo
+ *   W      float [n_gauss][PC_KA]          packed Gaussians: mu/var (39), k_hi | -1/(2 var) (39), k_lo
  *   b,lgam float per utterance [3*L][Tpad] emitting-state rows, time contiguous (Tpad = T up to 4)
- *   acc    double[n_gauss][PC_KA]          sum gamma*x | sum gamma*x^2 | sum gamma | sum gamma
+ *   acc    double[n_gauss][PC_KA]          sum gamma*x (39), sum gamma | sum gamma*x^2 (39), sum gamma
  *   Gaussian index g = (unit*3 + state)*mix + m.
  */
 #ifndef POCCALA_B200_H
@@ -44,7 +44,7 @@ extern "C" {
 
 #define PC_DIM_MAX 39 /* feature dimension limit (39-dim MFCC, init.py:27-43) */
 #define PC_XS 40      /* floats per frame row of X */
-#define PC_KA 80      /* augmented contraction length [x, x^2, 1, 1] */
+#define PC_KA 80      /* augmented contraction length [x (39), 1 | x^2 (39), 1] */
 #define PC_EMIT 3     /* emitting states per unit HMM (state_num 5, AcousticModel.py:39) */
 #define PC_STATES 5
 #define PC_TRANS_SLOTS 9 /* per unit: 3 x (self, next, gamma) log-domain transition accumulators */

@@ -51,13 +51,8 @@ accumulate_simt_kernel(CorpusView v, const float *__restrict__ X, const float *_
         for (int i = threadIdx.x; i < rows * PC_XS; i += blockDim.x) {
             int f = i / PC_XS, d = i - f * PC_XS;
             float x = __ldg(X + (size_t)(v.frame_off[u] + t0 + f) * PC_XS + d);
-            if (d < PC_DIM_MAX) {
-                xa_s[f][d] = x;
-                xa_s[f][PC_DIM_MAX + d] = x * x;
-            } else {
-                xa_s[f][78] = 1.f;
-                xa_s[f][79] = 1.f;
-            }
+            xa_s[f][d] = x;  // [x (39), 1 | x^2 (39), 1]
+            xa_s[f][PC_XS + d] = x * x;
         }
         for (int i = threadIdx.x; i < PC_EMIT * rows; i += blockDim.x) {
             int rr = i / rows, f = i - rr * rows;

@@ -124,16 +124,23 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
         std::vector<int64_t> cur(unit_pair_off.begin(), unit_pair_off.end() - 1);
         for (int64_t p = 0; p < n_pairs; ++p) sorted_pair[cur[labels[p]]++] = p;
     }
-    std::vector<int64_t> tile_pair;
-    std::vector<int32_t> tile_t0;
+    std::vector<int64_t> tile_pair, tile_xrow, tile_boff;
+    std::vector<int32_t> tile_t0, tile_rows, tile_tp;
     std::vector<int64_t> unit_tile_off(n_units + 1, 0);
     for (int k = 0; k < n_units; ++k) {
         for (int64_t i = unit_pair_off[k]; i < unit_pair_off[k + 1]; ++i) {
             const int64_t p = sorted_pair[i];
-            const int T = n_frames[pair_utt[p]];
+            const int u = pair_utt[p];
+            const int T = n_frames[u];
+            const int tp = pc_tpad(T);
+            const int64_t pos = p - pair_off[u];
             for (int t0 = 0; t0 < T; t0 += PC_TILE_ROWS) {
                 tile_pair.push_back(p);
                 tile_t0.push_back(t0);
+                tile_rows.push_back(std::min(PC_TILE_ROWS, T - t0));
+                tile_tp.push_back(tp);
+                tile_xrow.push_back(frame_off[u] + t0);
+                tile_boff.push_back(emis_off[u] + PC_EMIT * pos * tp + t0);
             }
         }
         unit_tile_off[k + 1] = (int64_t)tile_pair.size();
@@ -141,7 +148,8 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     const int64_t n_tiles = (int64_t)tile_pair.size();
     // work items: runs of <= chunk tiles inside one unit; aim at >= 8 items per SM
     int64_t chunk = n_tiles / ((int64_t)h->sm_count * 8);
-    chunk = std::max<int64_t>(4, std::min<int64_t>(64, chunk));
+    // <= 16 tiles: the accumulation kernel keeps an item's sums in fp32 (TMEM) before the fp64 flush
+    chunk = std::max<int64_t>(4, std::min<int64_t>(16, chunk));
     std::vector<int64_t> item_tile_lo;
     std::vector<int32_t> item_unit;
     for (int k = 0; k < n_units; ++k)
@@ -174,6 +182,10 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_upo = add(unit_pair_off.data(), unit_pair_off.size() * 8);
     size_t o_tpair = add(tile_pair.data(), (size_t)n_tiles * 8);
     size_t o_tt0 = add(tile_t0.data(), (size_t)n_tiles * 4);
+    size_t o_trows = add(tile_rows.data(), (size_t)n_tiles * 4);
+    size_t o_ttp = add(tile_tp.data(), (size_t)n_tiles * 4);
+    size_t o_txrow = add(tile_xrow.data(), (size_t)n_tiles * 8);
+    size_t o_tboff = add(tile_boff.data(), (size_t)n_tiles * 8);
     size_t o_ilo = add(item_tile_lo.data(), item_tile_lo.size() * 8);
     size_t o_iunit = add(item_unit.data(), (size_t)n_items * 4);
     size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 4);
@@ -216,6 +228,10 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     v.unit_pair_off = (const int64_t *)(dev + o_upo);
     v.tile_pair = (const int64_t *)(dev + o_tpair);
     v.tile_t0 = (const int32_t *)(dev + o_tt0);
+    v.tile_rows = (const int32_t *)(dev + o_trows);
+    v.tile_tp = (const int32_t *)(dev + o_ttp);
+    v.tile_xrow = (const int64_t *)(dev + o_txrow);
+    v.tile_boff = (const int64_t *)(dev + o_tboff);
     v.item_tile_lo = (const int64_t *)(dev + o_ilo);
     v.item_unit = (const int32_t *)(dev + o_iunit);
     v.scratch0 = (float *)(dev + o_scratch);
@@ -310,6 +326,8 @@ int pc_gmm_score(pc_handle h, pc_corpus c, const float *X, const float *W, int32
     PC_REQUIRE(c && X && W && b, "pc_gmm_score: NULL argument");
     int rc = check_dim_mix("pc_gmm_score", 1, mix);
     if (rc) return rc;
+    if (h->use_tc && score_tc_supported(mix))
+        return launch_score_tc(h, c->v, X, W, mix, b, (cudaStream_t)stream);
     return launch_score_simt(h, c->v, X, W, mix, b, (cudaStream_t)stream);
 }
 
@@ -339,6 +357,8 @@ int pc_accumulate(pc_handle h, pc_corpus c, const float *X, const float *W, int3
     PC_REQUIRE(c && X && W && b && lgam && acc, "pc_accumulate: NULL argument");
     int rc = check_dim_mix("pc_accumulate", 1, mix);
     if (rc) return rc;
+    if (h->use_tc && accumulate_tc_supported(mix))
+        return launch_accumulate_tc(h, c->v, X, W, mix, b, lgam, acc, (cudaStream_t)stream);
     return launch_accumulate_simt(h, c->v, X, W, mix, b, lgam, acc, (cudaStream_t)stream);
 }
 
@@ -477,10 +497,20 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     }
     if ((rc = launch_prepare_frames(h, raw, 0, F, dim, nullptr, nullptr, X, st))) return rc;
     if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, W, st))) return rc;
-    if ((rc = launch_score_simt(h, c->v, X, W, mix, b, st))) return rc;
+    if (h->use_tc && score_tc_supported(mix)) {
+        if ((rc = launch_score_tc(h, c->v, X, W, mix, b, st))) return rc;
+    } else if ((rc = launch_score_simt(h, c->v, X, W, mix, b, st))) {
+        return rc;
+    }
     if ((rc = launch_forward_backward(h, c->v, b, ls, ln, lg, c->v.scratch0, logp, iters, pt, st))) return rc;
     if (!(fix_code & 2))
-        if ((rc = launch_accumulate_simt(h, c->v, X, W, mix, b, lg, acc, st))) return rc;
+    {
+        if (h->use_tc && accumulate_tc_supported(mix)) {
+            if ((rc = launch_accumulate_tc(h, c->v, X, W, mix, b, lg, acc, st))) return rc;
+        } else if ((rc = launch_accumulate_simt(h, c->v, X, W, mix, b, lg, acc, st))) {
+            return rc;
+        }
+    }
     if ((rc = launch_transitions_max(h, c->v, logp, pt, tmax, st))) return rc;
     if ((rc = launch_transitions_sum(h, c->v, logp, pt, tmax, tsum, st))) return rc;
     if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, nullptr, nullptr, c_cov,

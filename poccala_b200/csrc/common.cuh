@@ -31,6 +31,10 @@ struct CorpusView {
     const int64_t *unit_pair_off;  // [n_units+1] range of sorted pairs per unit
     const int64_t *tile_pair;    // [n_tiles] utterance-major pair index of the tile
     const int32_t *tile_t0;      // [n_tiles] first frame (within the utterance) of the tile
+    const int32_t *tile_rows;    // [n_tiles] frames in the tile (<= 128)
+    const int32_t *tile_tp;      // [n_tiles] row stride (Tpad) of the utterance's b / lgam block
+    const int64_t *tile_xrow;    // [n_tiles] first row of the tile in X
+    const int64_t *tile_boff;    // [n_tiles] float offset of (state 0 of the pair, frame t0) in b / lgam
     const int64_t *item_tile_lo;  // [n_items+1] tile range of each work item (one unit per item)
     const int32_t *item_unit;     // [n_items]
     float *scratch0;              // [total_frames] entry-state beta_hat (K2 scratch)
@@ -123,6 +127,12 @@ int launch_prepare_frames(pc_handle h, const void *x, int is_f64, int64_t n, int
                           const double *shift, const double *inv_scale, float *X, cudaStream_t st);
 int launch_score_simt(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                       float *b, cudaStream_t st);
+bool score_tc_supported(int mix);
+int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
+                    float *b, cudaStream_t st);
+bool accumulate_tc_supported(int mix);
+int launch_accumulate_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
+                         const float *b, const float *lgam, double *acc, cudaStream_t st);
 int launch_score_dense_simt(pc_handle h, const float *X, int64_t n, const float *W, int n_states,
                             int mix, float *out, cudaStream_t st);
 int launch_accumulate_simt(pc_handle h, const CorpusView &v, const float *X, const float *W,

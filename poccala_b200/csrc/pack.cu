@@ -3,7 +3,7 @@
 // pack_gmm: util.gaussian_function's log branch (util.py:20-36) plus the log(alpha) term of
 // Clustering.GMM.point (Clustering.py:753-757) folded into one fp32 row per Gaussian:
 //     score(x, g) = <[x', x'^2, 1, 1], W_g>,   x' = (x - shift) * inv_scale
-//     W_g = [ mu'/var' (39) | -1/(2 var') (39) | k_hi | k_lo ]
+//     W_g = [ mu'/var' (39), k_hi | -1/(2 var') (39), k_lo ]   (matches [x (39), 1 | x^2 (39), 1])
 //     k   = log alpha - D/2 log 2pi - 1/2 sum_d var_d (Q1: ORIGINAL variances, not log-det)
 //           - 1/2 sum_d mu'^2/var'
 // All arithmetic in fp64; k is stored as an fp32 pair so the constant keeps ~48 bits.
@@ -29,17 +29,17 @@ __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *_
             sum_var += v;
             quad += mu_s * mu_s / v_s;
             w[d] = (float)(mu_s / v_s);
-            w[PC_DIM_MAX + d] = (float)(-0.5 / v_s);
+            w[PC_XS + d] = (float)(-0.5 / v_s);
         } else {
             w[d] = 0.f;
-            w[PC_DIM_MAX + d] = 0.f;
+            w[PC_XS + d] = 0.f;
         }
     }
     double k = log(alpha[g]) - 0.5 * dim * LOG_2PI - 0.5 * sum_var - 0.5 * quad;
     float k_hi = (float)k;
     float k_lo = isfinite(k) ? (float)(k - (double)k_hi) : 0.f;
-    w[2 * PC_DIM_MAX] = k_hi;
-    w[2 * PC_DIM_MAX + 1] = k_lo;
+    w[PC_XS - 1] = k_hi;
+    w[PC_KA - 1] = k_lo;
 }
 
 template <typename T>

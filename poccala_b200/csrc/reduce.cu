@@ -60,11 +60,11 @@ __global__ void update_gmm_kernel(int n_units, int mix, int dim, const double *_
     int d = (int)(i - g * dim);
     int64_t state = g / mix;
     double socc = 0.0;
-    for (int m = 0; m < mix; ++m) socc += acc[(size_t)(state * mix + m) * PC_KA + 2 * PC_DIM_MAX];
+    for (int m = 0; m < mix; ++m) socc += acc[(size_t)(state * mix + m) * PC_KA + PC_XS - 1];
     if (!(socc > 0.0)) return;  // unseen state: parameters stay (deviation D1)
     const double *a = acc + (size_t)g * PC_KA;
-    double occ = a[2 * PC_DIM_MAX];
-    double sx = a[d], sxx = a[PC_DIM_MAX + d];
+    double occ = a[PC_XS - 1];
+    double sx = a[d], sxx = a[PC_XS + d];
     double sh = shift ? shift[d] : 0.0;
     double is = inv_scale ? inv_scale[d] : 1.0;
     double mu_old_s = (mean[i] - sh) * is;  // old mean in the standardised space of X

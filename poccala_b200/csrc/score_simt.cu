@@ -16,12 +16,10 @@ __device__ __forceinline__ void load_aug_row(const float *__restrict__ xrow, flo
         x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
     }
 #pragma unroll
-    for (int d = 0; d < PC_DIM_MAX; ++d) {
+    for (int d = 0; d < PC_XS; ++d) {  // [x (39), 1 | x^2 (39), 1]
         xa[d] = x[d];
-        xa[PC_DIM_MAX + d] = x[d] * x[d];
+        xa[PC_XS + d] = x[d] * x[d];
     }
-    xa[78] = 1.f;
-    xa[79] = 1.f;
 }
 
 __device__ __forceinline__ float dot_aug(const float (&xa)[PC_KA], const float *__restrict__ w) {

@@ -1,0 +1,277 @@
+// sm_100a building blocks used by the tensor-core kernels: mbarrier, TMA bulk copies, tcgen05
+// (TMEM allocation, MMA issue, commit, TMEM loads), UMMA descriptors.  Inline PTX only.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---------------------------------------------------------------- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("poccala_b200: mbarrier timeout (block %d thread %d bar %p parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, (void *)bar, parity);
+            __trap();
+        }
+    }
+}
+
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- TMA (bulk, 1-D)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---------------------------------------------------------------- tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_out, uint32_t cols) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(smem_out)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// arrive on an mbarrier when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 16 consecutive columns (one fp32 per lane and column) -> 16 registers
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---------------------------------------------------------------- UMMA descriptors
+// Shared-memory matrix descriptor, no swizzle ("interleave"): the operand is stored as 8x16-byte
+// core matrices (8 rows of the non-contracted dimension x 16 contiguous bytes of the other);
+// `lbo`/`sbo` are the byte strides between core matrices (see DESIGN.md §5 for which is which in
+// K-major and MN-major use).  Bits: [0,14) addr>>4, [16,30) lbo>>4, [32,46) sbo>>4, [46,48) = 1.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 D (format 1), M x N tile.
+// a_mn / b_mn = 1 selects an MN-major operand.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- fp16 error-compensated split
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits for |x| in the fp16
+// normal range.  Packs two values per 32-bit word.
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    __half2 h = __floats2half2_rn(a, b);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    lo = *reinterpret_cast<uint32_t *>(&l);
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------- shared operand builders
+namespace tc {
+
+constexpr int T_ROWS = PC_TILE_ROWS;   // 128 frames per tile
+constexpr int T_KCH = PC_KA / 8;       // 10 sixteen-byte chunks along the augmented dimension
+constexpr int T_PIECE = T_KCH * T_ROWS * 16;  // bytes of one fp16 piece (hi or lo) of a frame tile
+
+// Resident Gaussian operand: rows [0, n_real) of `wsrc` (fp32 [n][PC_KA]) -> fp16 hi / lo pieces
+// in the no-swizzle core-matrix layout (chunk c of row n at c*NPAD*16 + n*16), each row scaled by a
+// power of two so that it fits the fp16 range.  scale_s[n] undoes the scaling, bias_s[n] is -inf for
+// a row whose constant is not finite (alpha = 0) and whose weights are therefore stored as zero.
+// Called by 128 threads (tid 0..127) that share named barrier 1.
+template <int NPAD>
+__device__ __forceinline__ void load_gauss_operand(const float *__restrict__ wsrc, int n_real, int tid,
+                                                   uint8_t *b_hi, uint8_t *b_lo, float *scale_s,
+                                                   float *bias_s, uint32_t *rowmax_s) {
+    for (int n = tid; n < NPAD; n += 128) rowmax_s[n] = 0u;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int task = tid; task < n_real * 5; task += 128) {
+        const int n = task / 5, c = task - n * 5;
+        const float4 *src = reinterpret_cast<const float4 *>(wsrc + (size_t)n * PC_KA);
+        float m = 0.f;
+        bool dead = false;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 q0 = __ldg(src + (c + 5 * half) * 2), q1 = __ldg(src + (c + 5 * half) * 2 + 1);
+            float vals[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float a = fabsf(vals[e]);
+                if (a <= 3.0e38f) m = fmaxf(m, a);
+            }
+            if (c == 4 && half == 0 && !(fabsf(vals[7]) <= 3.0e38f)) dead = true;
+        }
+        atomicMax(&rowmax_s[n], dead ? 0xffffffffu : __float_as_uint(m));
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int task = tid; task < NPAD * 5; task += 128) {
+        const int n = task / 5, c = task - n * 5;
+        uint32_t hi8[2][4], lo8[2][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) hi8[half][e2] = lo8[half][e2] = 0u;
+        const uint32_t mbits = (n < n_real) ? rowmax_s[n] : 0xffffffffu;
+        if (mbits != 0xffffffffu) {
+            const float mx = __uint_as_float(mbits);
+            int e = 0;
+            if (mx > 16384.f) e = (int)((mbits >> 23) & 0xff) - 127 - 13;
+            const float inv = __uint_as_float((uint32_t)(127 - e) << 23);
+            const float4 *src = reinterpret_cast<const float4 *>(wsrc + (size_t)n * PC_KA);
+            float kres = 0.f;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 q0 = __ldg(src + (c + 5 * half) * 2), q1 = __ldg(src + (c + 5 * half) * 2 + 1);
+                float vals[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int e2 = 0; e2 < 8; ++e2) vals[e2] *= inv;
+                if (c == 4) {  // the constant: columns 39 (half 0) and 79 (half 1)
+                    if (half == 0) {
+                        const __half kh = __float2half_rn(vals[7]);
+                        const float r1 = vals[7] - __half2float(kh);
+                        kres = r1 - __half2float(__float2half_rn(r1));
+                    } else {
+                        vals[7] += kres;
+                    }
+                }
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2)
+                    split2(vals[2 * e2], vals[2 * e2 + 1], hi8[half][e2], lo8[half][e2]);
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int chunk = c + 5 * half;
+            *reinterpret_cast<uint4 *>(b_hi + chunk * NPAD * 16 + n * 16) =
+                make_uint4(hi8[half][0], hi8[half][1], hi8[half][2], hi8[half][3]);
+            *reinterpret_cast<uint4 *>(b_lo + chunk * NPAD * 16 + n * 16) =
+                make_uint4(lo8[half][0], lo8[half][1], lo8[half][2], lo8[half][3]);
+        }
+    }
+    for (int n = tid; n < NPAD; n += 128) {
+        const uint32_t mbits = (n < n_real) ? rowmax_s[n] : 0xffffffffu;
+        float sc = 1.f, bias = 0.f;
+        if (mbits == 0xffffffffu) {
+            bias = PC_NEG_INF;
+        } else if (__uint_as_float(mbits) > 16384.f) {
+            const int e = (int)((mbits >> 23) & 0xff) - 127 - 13;
+            sc = __uint_as_float((uint32_t)(127 + e) << 23);
+        }
+        scale_s[n] = sc;
+        bias_s[n] = bias;
+    }
+    fence_proxy_async();
+}
+
+// One raw frame row (40 floats: x (39), 1) -> [x | x^2] fp16 hi / lo rows of the operand tile.
+// Rows past the end of the tile are stored as zeros.
+__device__ __forceinline__ void convert_frame_row(const uint8_t *raw_stage, int r, bool valid,
+                                                  uint8_t *a_hi, uint8_t *a_lo) {
+    float x[PC_XS];
+    if (valid) {
+        const float4 *src = reinterpret_cast<const float4 *>(raw_stage + r * PC_XS * 4);
+#pragma unroll
+        for (int q = 0; q < PC_XS / 4; ++q) {
+            float4 t4 = src[q];
+            x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < PC_XS; ++q) x[q] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        uint32_t h[4], l[4], h2[4], l2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = x[8 * c + 2 * e], q = x[8 * c + 2 * e + 1];
+            split2(p, q, h[e], l[e]);
+            split2(p * p, q * q, h2[e], l2[e]);
+        }
+        *reinterpret_cast<uint4 *>(a_hi + c * T_ROWS * 16 + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(a_lo + c * T_ROWS * 16 + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4 *>(a_hi + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+        *reinterpret_cast<uint4 *>(a_lo + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+    }
+}
+
+}  // namespace tc

