@@ -19,8 +19,10 @@
  *   - there is NO CPU fallback: without a CUDA device pc_create fails with PC_ERR_CUDA.
  *
  * Data layout in HBM
- *   X      float [n_frames_total][PC_XS]   standardised frames; cols [0,D) data, col 39 = 1.0
- *   W      float [n_gauss][PC_KA]          packed Gaussians: mu/var (39), k_hi | -1/(2 var) (39), k_lo
+ *   X      pc_corpus_frames_bytes(c) bytes: float [F][PC_XS] standardised frames (cols [0,D) data,
+ *          col 39 = 1.0) followed by one fp16 (hi, lo) tensor-core operand image per 128-frame tile
+ *   W      pc_gmm_bytes(G) bytes: float [G][PC_KA] packed Gaussians (mu/var (39), k_hi |
+ *          -1/(2 var) (39), k_lo), float scale[G], int32 flags[G], one fp16 operand image per unit
  *   b,lgam float per utterance [3*L][Tpad] emitting-state rows, time contiguous (Tpad = T up to 4)
  *   acc    double[n_gauss][PC_KA]          sum gamma*x (39), sum gamma | sum gamma*x^2 (39), sum gamma
  *   Gaussian index g = (unit*3 + state)*mix + m.
@@ -48,11 +50,14 @@ extern "C" {
 #define PC_EMIT 3     /* emitting states per unit HMM (state_num 5, AcousticModel.py:39) */
 #define PC_STATES 5
 #define PC_TRANS_SLOTS 9 /* per unit: 3 x (self, next, gamma) log-domain transition accumulators */
+#define PC_W_BYTES_PER_GAUSS 760 /* upper bound: 320 (fp32 row) + 8 (scale, flags) + <= 427 (fp16 image) */
 
 typedef struct pc_handle_s *pc_handle;
 typedef struct pc_corpus_s *pc_corpus;
 
 int pc_abi_version(void);
+int64_t pc_rows_bytes(int64_t n_frames); /* size of a rows-only X buffer (pc_prepare_rows_*) */
+int64_t pc_gmm_bytes(int64_t n_gauss);   /* size of a W buffer */
 const char *pc_last_error(void);
 
 /* One handle per device.  Fails (PC_ERR_CUDA) when the device is absent or not sm_100. */
@@ -75,6 +80,7 @@ int64_t pc_corpus_total_frames(pc_corpus c);
 int64_t pc_corpus_emission_floats(pc_corpus c); /* length of the b / lgam buffers */
 int64_t pc_corpus_total_pairs(pc_corpus c);     /* number of (utterance, label position) pairs */
 int64_t pc_corpus_total_states(pc_corpus c);    /* sum over utterances of 3L+2 */
+int64_t pc_corpus_frames_bytes(pc_corpus c);    /* size of the corpus' X buffer */
 /* host_out[n_utt+1]: first frame / first float in b / first pair / first composite state. */
 int pc_corpus_offsets(pc_corpus c, int64_t *host_frame_off, int64_t *host_emis_off,
                       int64_t *host_pair_off, int64_t *host_state_off);
@@ -84,17 +90,27 @@ int pc_corpus_offsets(pc_corpus c, int64_t *host_frame_off, int64_t *host_emis_o
  * the log(alpha) term of Clustering.GMM.point (Clustering.py:753-757), folded into one row per
  * Gaussian so that score = <[x, x^2, 1, 1], W_g>.  mean/var/alpha: dev double [n_gauss][dim] /
  * [n_gauss]; shift/inv_scale: dev double [dim] or NULL (identity). */
+/* mix = components per state when the Gaussians are the [unit][3][mix] set of an acoustic model
+ * (builds the per-unit tensor-core operand images); mix = 0 for a flat list of Gaussians. */
 int pc_pack_gmm(pc_handle h, const double *dev_mean, const double *dev_var,
                 const double *dev_alpha, const double *dev_shift, const double *dev_inv_scale,
-                int32_t n_gauss, int32_t dim, float *dev_W, void *stream);
+                int32_t n_gauss, int32_t dim, int32_t mix, float *dev_W, void *stream);
 
-/* Frames [n][dim] (double or float, device) -> X [n][PC_XS] standardised float rows. */
-int pc_prepare_frames_f64(pc_handle h, const double *dev_x, int64_t n, int32_t dim,
+/* Corpus frames [F][dim] (double or float, device, utterances concatenated in corpus order) ->
+ * X buffer: standardised fp32 rows + per-tile fp16 operand images. */
+int pc_prepare_frames_f64(pc_handle h, pc_corpus c, const double *dev_x, int32_t dim,
                           const double *dev_shift, const double *dev_inv_scale, float *dev_X,
                           void *stream);
-int pc_prepare_frames_f32(pc_handle h, const float *dev_x, int64_t n, int32_t dim,
+int pc_prepare_frames_f32(pc_handle h, pc_corpus c, const float *dev_x, int32_t dim,
                           const double *dev_shift, const double *dev_inv_scale, float *dev_X,
                           void *stream);
+/* Frames without a corpus (dense scoring sweep): fp32 rows [n][PC_XS] only. */
+int pc_prepare_rows_f64(pc_handle h, const double *dev_x, int64_t n, int32_t dim,
+                        const double *dev_shift, const double *dev_inv_scale, float *dev_X,
+                        void *stream);
+int pc_prepare_rows_f32(pc_handle h, const float *dev_x, int64_t n, int32_t dim,
+                        const double *dev_shift, const double *dev_inv_scale, float *dev_X,
+                        void *stream);
 
 /* ---- K1: GMM scoring -----------------------------------------------------------------------
  * LHMM.cal_observation_pro -> GMM.point -> util.gaussian_function + util.log_sum_exp

@@ -44,6 +44,8 @@ def _p(x):
 _SIGS = {
     "pc_abi_version": (C.c_int, []),
     "pc_last_error": (C.c_char_p, []),
+    "pc_rows_bytes": (C.c_int64, [C.c_int64]),
+    "pc_gmm_bytes": (C.c_int64, [C.c_int64]),
     "pc_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "pc_destroy": (C.c_int, [C.c_void_p]),
     "pc_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
@@ -55,10 +57,13 @@ _SIGS = {
     "pc_corpus_emission_floats": (C.c_int64, [C.c_void_p]),
     "pc_corpus_total_pairs": (C.c_int64, [C.c_void_p]),
     "pc_corpus_total_states": (C.c_int64, [C.c_void_p]),
+    "pc_corpus_frames_bytes": (C.c_int64, [C.c_void_p]),
     "pc_corpus_offsets": (C.c_int, [C.c_void_p] * 5),
-    "pc_pack_gmm": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
-    "pc_prepare_frames_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4),
-    "pc_prepare_frames_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4),
+    "pc_pack_gmm": (C.c_int, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "pc_prepare_frames_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),
+    "pc_prepare_frames_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),
+    "pc_prepare_rows_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4),
+    "pc_prepare_rows_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4),
     "pc_gmm_score": (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "pc_gmm_score_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p]),

@@ -8,16 +8,17 @@
 // Restates LHMM.update_acc -> Clustering.GMM.update_acc (LHMM.py:473-507, Clustering.py:653-680)
 // in the linear-equivalent form of SURVEY A.4 (see accumulate_simt.cu).  All operands are fp16
 // (hi, lo) pairs and every contraction is the 3-product error-compensated sum, fp32 accumulation
-// in TMEM.  The frame tile written once by the converter warps serves BOTH contractions: as the
-// K-major A operand of MMA1 (K = feature) and, through an MN-major descriptor over the same
-// bytes, as the A operand of MMA2 (M = feature, K = frame).  P is written by the softmax warps as
-// the MN-major B operand of MMA2.  D2 stays in TMEM for a whole work item (<= 16 tiles of one
-// unit) and is flushed with fp64 atomics.
+// in TMEM.  The frame tile that TMA drops into shared memory serves BOTH contractions: as the
+// K-major A operand of MMA1 (K = feature) and, through an MN-major descriptor over the same bytes,
+// as the A operand of MMA2 (M = feature, K = frame).  P (scaled by 2^15 to sit in the fp16 range)
+// is written by the softmax warps as the MN-major B operand of MMA2.  Work is UNIT-major so that
+// D2 stays in TMEM for a whole work item (<= 16 tiles of one unit) before one fp64-atomic flush.
 //
-//   warp 8      TMA producer : raw X rows -> 2-stage ring (cp.async.bulk)
-//   warps 4-7   converters   : raw rows -> operand tile; once per item the unit's W rows -> B
-//   warp 9      MMA issuer   : MMA1(i), then MMA2(i-1) (software pipelined)
-//   warps 0-3   softmax      : tcgen05.ld S, exp2, hi/lo split, P tile; at item end the flush
+//   warp 19     TMA producer : per item the unit's Gaussian rows (B), per tile 20 x 2 KiB of frames
+//   warp 20     MMA issuer   : MMA1(i), then MMA2(i-1) (software pipelined), commits
+//   warps 0-15  softmax      : two tile groups x (2 column halves x 4 lane quarters): tcgen05.ld S,
+//                              exp2, hi/lo split, P tile
+//   warps 16-18 flush        : D2 (lane = feature) -> atomicAdd(double) into acc, once per item
 #include "tc_common.cuh"
 
 namespace {
@@ -25,10 +26,8 @@ namespace {
 using tc::T_KCH;
 using tc::T_PIECE;
 using tc::T_ROWS;
-constexpr int RAW_STAGES = 2;
-constexpr int A_STAGES = 2;
-constexpr int RAW_BYTES = T_ROWS * PC_XS * 4;
-constexpr int NTHREADS = 320;
+constexpr int W_FLUSH = 16, W_PROD = 19, W_MMA = 20;  // warps 0-15 softmax, 16-18 flush
+constexpr int NTHREADS = 21 * 32;
 constexpr float LOG2E = 1.4426950408889634f;
 // posteriors are stored as P * 2^15 so that the fp16 window [6e-8, 65504] covers [1.8e-12, 2]
 constexpr float P_SHIFT = 15.f;
@@ -43,188 +42,194 @@ struct Cfg {
     static constexpr int NPAD = (NC + 15) & ~15;
     static constexpr int B_PIECE = T_KCH * NPAD * 16;
     static constexpr int P_PIECE = (NPAD / 8) * T_ROWS * 16;
-    static constexpr int P_STAGES = NPAD <= 48 ? 2 : 1;
+    static constexpr int NA = NPAD <= 48 ? 3 : 2;
     static constexpr int S_STRIDE = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : 128);
-    static constexpr int S_BUFS = 2;
-    static constexpr int D2_COL = S_STRIDE * S_BUFS;
+    static constexpr int D2_COL = S_STRIDE * 2;
     static constexpr int TM_COLS = 512;
-    static constexpr int SMEM = 1024 + RAW_STAGES * RAW_BYTES + A_STAGES * 2 * T_PIECE + 2 * B_PIECE +
-                                P_STAGES * 2 * P_PIECE + 3 * NPAD * 4 + 256;
+    static constexpr int SMEM = 1024 + NA * 2 * T_PIECE + 2 * B_PIECE + 2 * 2 * P_PIECE;
     static_assert(N_UNIT % NC == 0, "slices must tile the unit");
     static_assert(D2_COL + NPAD <= 512, "TMEM budget");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 struct Bars {
-    uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
-    uint64_t a_full[A_STAGES], a_empty[A_STAGES];
+    uint64_t a_full[3], a_empty[3];
+    uint64_t b_full, b_empty;
     uint64_t s_full[2], s_empty[2];
     uint64_t p_full[2], p_empty[2];
-    uint64_t d2_full;
+    uint64_t d2_full, d2_empty;
     uint32_t tmem_base;
 };
 
-// S (TMEM, one frame per thread) -> P = exp2(S * scale * log2e + d) -> fp16 hi / lo rows of the
-// MN-major P tile.  G0 = first Gaussian of the slice inside the unit (selects the state of a column
-// at compile time).
-template <int MIX, int G0>
-__device__ __forceinline__ void softmax_tile(uint32_t taddr, const float (&dl)[PC_EMIT],
-                                             const float *__restrict__ scale_s, uint8_t *ph,
-                                             uint8_t *pl, int r) {
+// S (TMEM, one frame per thread) -> P = 2^15 * exp(S*scale + lgam - b) -> fp16 hi / lo rows of the
+// MN-major P tile, for the 8-Gaussian blocks [blk0, blk1) of the slice.  G0 = first Gaussian of the
+// slice inside the unit (fixes the state of a column at compile time).
+template <int MIX, int G0, bool SCALED, int HALF>
+__device__ __forceinline__ void softmax_blocks(uint32_t taddr, const float (&dl)[PC_EMIT],
+                                               const float *__restrict__ scale_g, uint8_t *ph,
+                                               uint8_t *pl, int r) {
     using C = Cfg<MIX>;
+    constexpr int NBLK = C::NPAD / 8;
+    constexpr int PER = (NBLK + 1) / 2;
 #pragma unroll
-    for (int j = 0; j < C::NPAD / 16; ++j) {
-        float t16[16];
-        tc::tmem_ld16(taddr + j * 16, t16);
+    for (int bb = 0; bb < PER; ++bb) {
+        constexpr int blk0 = HALF * PER;
+        const int blk = blk0 + bb;
+        if (blk >= NBLK) break;
+        float t8[8];
+        tc::tmem_ld8(taddr + blk * 8, t8);
         tc::tmem_ld_wait();
-        uint32_t h[8], l[8];
+        uint32_t h[4], l[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c0 = j * 16 + 2 * e, c1 = c0 + 1;
-            constexpr int SMAX = PC_EMIT - 1;
-            const int s0 = (G0 + c0) / MIX < SMAX ? (G0 + c0) / MIX : SMAX;
-            const int s1 = (G0 + c1) / MIX < SMAX ? (G0 + c1) / MIX : SMAX;
-            float p0 = exp2f(fmaf(t16[2 * e], scale_s[c0] * LOG2E, dl[s0]));
-            float p1 = exp2f(fmaf(t16[2 * e + 1], scale_s[c1] * LOG2E, dl[s1]));
-            if (c0 >= C::NC) p0 = 0.f;
-            if (c1 >= C::NC) p1 = 0.f;
-            tc::split2(p0, p1, h[e], l[e]);
+        for (int e = 0; e < 4; ++e) {
+            float p[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                // the state of a column is a compile-time constant after unrolling
+                const int col_in_blk = 2 * e + k;
+                const int col = blk * 8 + col_in_blk;
+                const int st = (G0 + col) / MIX;
+                const float d = dl[st < PC_EMIT ? st : PC_EMIT - 1];
+                const float mul = SCALED ? __ldg(scale_g + col) * LOG2E : LOG2E;
+                p[k] = (col < C::NC) ? tc::ex2(fmaf(t8[col_in_blk], mul, d)) : 0.f;
+            }
+            tc::split2(p[0], p[1], h[e], l[e]);
         }
-        // columns 16j..16j+7 -> Gaussian block 2j, 16j+8..16j+15 -> block 2j+1
-        *reinterpret_cast<uint4 *>(ph + (2 * j) * T_ROWS * 16 + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4 *>(pl + (2 * j) * T_ROWS * 16 + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
-        *reinterpret_cast<uint4 *>(ph + (2 * j + 1) * T_ROWS * 16 + r * 16) = make_uint4(h[4], h[5], h[6], h[7]);
-        *reinterpret_cast<uint4 *>(pl + (2 * j + 1) * T_ROWS * 16 + r * 16) = make_uint4(l[4], l[5], l[6], l[7]);
+        *reinterpret_cast<uint4 *>(ph + blk * T_ROWS * 16 + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(pl + blk * T_ROWS * 16 + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
 template <int MIX>
 __global__ void __launch_bounds__(NTHREADS, 1)
-accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W,
+accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W, int n_gauss,
                      const float *__restrict__ b, const float *__restrict__ lgam,
                      double *__restrict__ acc) {
     using C = Cfg<MIX>;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars *bars = reinterpret_cast<Bars *>(smem);
-    uint8_t *raw_s = smem + 1024;
-    uint8_t *a_s = raw_s + RAW_STAGES * RAW_BYTES;
-    uint8_t *b_s = a_s + A_STAGES * 2 * T_PIECE;
+    uint8_t *a_s = smem + 1024;
+    uint8_t *b_s = a_s + C::NA * 2 * T_PIECE;
     uint8_t *p_s = b_s + 2 * C::B_PIECE;
-    float *scale_s = reinterpret_cast<float *>(p_s + C::P_STAGES * 2 * C::P_PIECE);
-    float *bias_s = scale_s + C::NPAD;
-    uint32_t *rowmax_s = reinterpret_cast<uint32_t *>(bias_s + C::NPAD);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RAW_STAGES; ++i) { tc::mbar_init(&bars->raw_full[i], 1); tc::mbar_init(&bars->raw_empty[i], 4); }
-        for (int i = 0; i < A_STAGES; ++i) { tc::mbar_init(&bars->a_full[i], 4); tc::mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1); }
+        tc::mbar_init(&bars->b_full, 1);
+        tc::mbar_init(&bars->b_empty, 1);
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bars->s_full[i], 1); tc::mbar_init(&bars->s_empty[i], 4);
-            tc::mbar_init(&bars->p_full[i], 4); tc::mbar_init(&bars->p_empty[i], 1);
+            tc::mbar_init(&bars->s_full[i], 1); tc::mbar_init(&bars->s_empty[i], 8);
+            tc::mbar_init(&bars->p_full[i], 8); tc::mbar_init(&bars->p_empty[i], 1);
         }
         tc::mbar_init(&bars->d2_full, 1);
+        tc::mbar_init(&bars->d2_empty, 3);
         tc::mbar_fence_init();
     }
-    if (warp == 9) tc::tmem_alloc(&bars->tmem_base, C::TM_COLS);
+    // zero-fill the P tiles: Gaussian columns past the slice are never written
+    for (int i = threadIdx.x; i < (2 * 2 * C::P_PIECE) / 16; i += NTHREADS)
+        reinterpret_cast<uint4 *>(p_s)[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async();
+    if (warp == W_MMA) tc::tmem_alloc(&bars->tmem_base, C::TM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base_ = bars->tmem_base;
+    const uint32_t tmem_base = tmem_base_;
 
-    uint32_t n_raw = 0, n_a = 0, n_s = 0, n_p = 0, n_item = 0;
+    const uint8_t *x16 = reinterpret_cast<const uint8_t *>(X) + pc_x16_offset(v.total_frames);
+    const uint8_t *w16 = reinterpret_cast<const uint8_t *>(W) + pc_w16_offset(n_gauss);
+    const float *wscale = W + (size_t)n_gauss * PC_KA;
+    const bool scaled_rows = reinterpret_cast<const int *>(wscale + n_gauss)[0] != 0;
+    constexpr int UNIT_IMG = ((C::N_UNIT + 15) & ~15) / 8 * PC_WGROUP_BYTES;  // bytes of a unit image
+    constexpr uint32_t B_BYTES = C::NPAD / 8 * PC_WGROUP_BYTES;               // bytes of a slice
+
+    uint32_t n_tile = 0, n_item = 0;  // running counters (tiles, items) of this CTA
     const int n_work = v.n_items * C::N_SLICES;
     for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++n_item) {
         const int item = work / C::N_SLICES, slice = work - item * C::N_SLICES;
         const int unit = v.item_unit[item];
         const int g0 = slice * C::NC;  // first Gaussian of the slice inside the unit
+        const size_t gfirst = (size_t)unit * C::N_UNIT + g0;
         const int64_t lo = v.item_tile_lo[item], hi = v.item_tile_lo[item + 1];
-        const int n_tiles = (int)(hi - lo);
-        if (warp >= 4 && warp < 8) {
-            tc::load_gauss_operand<C::NPAD>(W + ((size_t)unit * C::N_UNIT + g0) * PC_KA, C::NC,
-                                            threadIdx.x - 128, b_s, b_s + C::B_PIECE, scale_s, bias_s,
-                                            rowmax_s);
-        }
-        __syncthreads();
+        const int n_tiles_ = (int)(hi - lo);
+        const int n_tiles = n_tiles_;
 
-        if (warp == 8) {
+        if (warp == W_PROD) {
             // ------------------------------------------------------------ TMA producer
-            for (int i = 0; i < n_tiles; ++i, ++n_raw) {
-                const int s = n_raw % RAW_STAGES;
-                tc::mbar_wait(&bars->raw_empty[s], ((n_raw / RAW_STAGES) & 1) ^ 1);
+            tc::mbar_wait(&bars->b_empty, (n_item & 1) ^ 1);
+            if (lane == 0) {
+                tc::mbar_expect_tx(&bars->b_full, B_BYTES);
+                tc::tma_load_1d(b_s, w16 + (size_t)unit * UNIT_IMG + (size_t)(g0 / 8) * PC_WGROUP_BYTES, B_BYTES,
+                                &bars->b_full);
+            }
+            __syncwarp();
+            for (int i = 0; i < n_tiles; ++i) {
+                const uint32_t n = n_tile + i;
+                const int slot = n % C::NA;
+                const int64_t tile = lo + i;
+                tc::mbar_wait(&bars->a_empty[slot], ((n / C::NA) & 1) ^ 1);
                 if (lane == 0) {
-                    const int64_t tile = lo + i;
-                    const uint32_t bytes = (uint32_t)v.tile_rows[tile] * PC_XS * 4;
-                    tc::mbar_expect_tx(&bars->raw_full[s], bytes);
-                    tc::tma_load_1d(raw_s + s * RAW_BYTES, X + (size_t)v.tile_xrow[tile] * PC_XS, bytes,
-                                    &bars->raw_full[s]);
+                    tc::mbar_expect_tx(&bars->a_full[slot], PC_XTILE_BYTES);
+                    tc::tma_load_1d(a_s + slot * 2 * T_PIECE, x16 + (size_t)v.tile_xblk[tile] * PC_XTILE_BYTES,
+                                    PC_XTILE_BYTES, &bars->a_full[slot]);
                 }
                 __syncwarp();
             }
-        } else if (warp >= 4 && warp < 8) {
-            // ------------------------------------------------------------ converters
-            const int r = threadIdx.x - 128;
-            for (int i = 0; i < n_tiles; ++i, ++n_raw, ++n_a) {
-                const int rs = n_raw % RAW_STAGES, as = n_a % A_STAGES;
-                const int rows = v.tile_rows[lo + i];
-                tc::mbar_wait(&bars->raw_full[rs], (n_raw / RAW_STAGES) & 1);
-                tc::mbar_wait(&bars->a_empty[as], ((n_a / A_STAGES) & 1) ^ 1);
-                uint8_t *ah = a_s + as * 2 * T_PIECE;
-                tc::convert_frame_row(raw_s + rs * RAW_BYTES, r, r < rows, ah, ah + T_PIECE);
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    tc::mbar_arrive(&bars->raw_empty[rs]);
-                    tc::mbar_arrive(&bars->a_full[as]);
-                }
-            }
-        } else if (warp == 9) {
+        } else if (warp == W_MMA) {
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc1 = tc::umma_idesc_f16(T_ROWS, C::NPAD, 0, 0);
             constexpr uint32_t idesc2 = tc::umma_idesc_f16(128, C::NPAD, 1, 1);
             const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s), p_base = tc::smem_u32(p_s);
+            // loop bounds / ring counters through redux.sync: uniform registers for the descriptors
+            const int n_tiles = __reduce_max_sync(0xffffffffu, n_tiles_);
+            const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, tmem_base_);
+            const uint32_t n_tile_u = __reduce_max_sync(0xffffffffu, n_tile);
             const uint32_t d2 = tmem_base + C::D2_COL;
-            uint32_t n_a2 = n_a, n_p2 = n_p;  // counters of the lagging MMA2 stream
+            tc::mbar_wait(&bars->b_full, n_item & 1);
             for (int i = 0; i <= n_tiles; ++i) {
                 if (i < n_tiles) {
-                    const int as = n_a % A_STAGES, sb = n_s % C::S_BUFS;
-                    tc::mbar_wait(&bars->a_full[as], (n_a / A_STAGES) & 1);
-                    tc::mbar_wait(&bars->s_empty[sb], ((n_s / C::S_BUFS) & 1) ^ 1);
+                    const uint32_t n = n_tile_u + i;
+                    const int slot = n % C::NA, sb = n & 1;
+                    tc::mbar_wait(&bars->a_full[slot], (n / C::NA) & 1);
+                    tc::mbar_wait(&bars->s_empty[sb], ((n >> 1) & 1) ^ 1);
                     tc::tc_fence_after();
                     if (lane == 0) {
                         const uint32_t d = tmem_base + sb * C::S_STRIDE;
-                        const uint32_t ah = a_base + as * 2 * T_PIECE, al = ah + T_PIECE;
-                        const uint32_t bh = b_base, bl = b_base + C::B_PIECE;
+                        const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
+                        const uint32_t bh = b_base, bl = b_base + PC_WGROUP_BYTES / 2;
                         uint32_t accum = 0;
 #pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-                            const uint32_t ap = (p == 2) ? al : ah;
-                            const uint32_t bp = (p == 1) ? bl : bh;
+                        for (int q = 0; q < 3; ++q) {
+                            const uint32_t ap = (q == 2) ? al : ah;
+                            const uint32_t bp = (q == 1) ? bl : bh;
 #pragma unroll
                             for (int k = 0; k < T_KCH / 2; ++k) {
                                 const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
-                                const uint64_t bd = tc::umma_desc(bp + 2 * k * C::NPAD * 16, C::NPAD * 16, 128);
+                                const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
                                 tc::mma_f16_ss(d, ad, bd, idesc1, accum);
                                 accum = 1;
                             }
                         }
                         tc::tc_commit(&bars->s_full[sb]);
+                        if (i == n_tiles - 1) tc::tc_commit(&bars->b_empty);  // last use of this item's B
                     }
                     __syncwarp();
-                    ++n_a;
-                    ++n_s;
                 }
                 if (i >= 1) {
                     // MMA2 of tile i-1: D2[f, g] += sum_t A[t, f] * P[t, g]
-                    const int as = n_a2 % A_STAGES, ps = n_p2 % C::P_STAGES;
-                    tc::mbar_wait(&bars->p_full[ps], (n_p2 / C::P_STAGES) & 1);
+                    const uint32_t n = n_tile_u + i - 1;
+                    const int slot = n % C::NA, ps = n & 1;
+                    tc::mbar_wait(&bars->p_full[ps], (n >> 1) & 1);
+                    if (i == 1) tc::mbar_wait(&bars->d2_empty, (n_item & 1) ^ 1);  // previous flush done
                     tc::tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t ah = a_base + as * 2 * T_PIECE, al = ah + T_PIECE;
+                        const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                         const uint32_t ph = p_base + ps * 2 * C::P_PIECE, pl = ph + C::P_PIECE;
                         uint32_t accum = (i == 1) ? 0u : 1u;  // first tile of the item resets D2
 #pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-                            const uint32_t ap = (p == 1) ? al : ah;
-                            const uint32_t pp = (p == 2) ? pl : ph;
+                        for (int q = 0; q < 3; ++q) {
+                            const uint32_t ap = (q == 1) ? al : ah;
+                            const uint32_t pp = (q == 2) ? pl : ph;
 #pragma unroll
                             for (int k = 0; k < T_ROWS / 16; ++k) {
                                 // MN-major views: 8 frames x 16 B core matrices; LBO = 128 B between
@@ -235,25 +240,27 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                                 accum = 1;
                             }
                         }
-                        tc::tc_commit(&bars->a_empty[as]);
+                        tc::tc_commit(&bars->a_empty[slot]);
                         tc::tc_commit(&bars->p_empty[ps]);
                         if (i == n_tiles) tc::tc_commit(&bars->d2_full);
                     }
                     __syncwarp();
-                    ++n_a2;
-                    ++n_p2;
                 }
             }
-            n_p = n_p2;
-        } else {
-            // ------------------------------------------------------------ softmax warps 0-3
-            const int r = threadIdx.x;
-            for (int i = 0; i < n_tiles; ++i, ++n_s, ++n_p) {
-                const int sb = n_s % C::S_BUFS, ps = n_p % C::P_STAGES;
+        } else if (warp < W_FLUSH) {
+            // ------------------------------------------------------------ softmax: 2 tile groups x
+            // (2 column halves x 4 lane quarters)
+            const int grp = warp >> 3, half = (warp >> 2) & 1;
+            const int r = (warp & 3) * 32 + lane;
+            const float *scale_g = wscale + gfirst;
+            for (int i = 0; i < n_tiles; ++i) {
+                const uint32_t n = n_tile + i;
+                if ((int)(n & 1) != grp) continue;
+                const int sb = n & 1, ps = n & 1;
                 const int64_t tile = lo + i;
                 const int rows = v.tile_rows[tile];
                 const int tp = v.tile_tp[tile];
-                // d = (lgam - b) * log2(e) for the states this slice touches; -inf kills the row
+                // d = (lgam - b) * log2(e) + 15 for the unit's three states; -inf kills the row
                 float dl[PC_EMIT];
                 {
                     const size_t o = (size_t)v.tile_boff[tile] + r;
@@ -267,15 +274,24 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                         dl[s] = d;
                     }
                 }
-                tc::mbar_wait(&bars->s_full[sb], (n_s / C::S_BUFS) & 1);
+                tc::mbar_wait(&bars->s_full[sb], (n >> 1) & 1);
                 tc::tc_fence_after();
-                tc::mbar_wait(&bars->p_empty[ps], ((n_p / C::P_STAGES) & 1) ^ 1);
-                const uint32_t taddr = tmem_base + sb * C::S_STRIDE + ((uint32_t)(warp * 32) << 16);
+                tc::mbar_wait(&bars->p_empty[ps], ((n >> 1) & 1) ^ 1);
+                const uint32_t taddr = tmem_base + sb * C::S_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
                 uint8_t *ph = p_s + ps * 2 * C::P_PIECE, *pl = ph + C::P_PIECE;
-                if (C::N_SLICES == 1 || slice == 0)
-                    softmax_tile<MIX, 0>(taddr, dl, scale_s, ph, pl, r);
-                else
-                    softmax_tile<MIX, C::NC>(taddr, dl, scale_s, ph, pl, r);
+#define PC_SOFTMAX(G0_, SC_)                                                              \
+    do {                                                                                  \
+        if (half == 0) softmax_blocks<MIX, G0_, SC_, 0>(taddr, dl, scale_g, ph, pl, r);   \
+        else softmax_blocks<MIX, G0_, SC_, 1>(taddr, dl, scale_g, ph, pl, r);             \
+    } while (0)
+                if (C::N_SLICES == 1 || slice == 0) {
+                    if (scaled_rows) PC_SOFTMAX(0, true);
+                    else PC_SOFTMAX(0, false);
+                } else {
+                    if (scaled_rows) PC_SOFTMAX(C::NC, true);
+                    else PC_SOFTMAX(C::NC, false);
+                }
+#undef PC_SOFTMAX
                 tc::tc_fence_before();
                 tc::fence_proxy_async();
                 __syncwarp();
@@ -284,34 +300,37 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     tc::mbar_arrive(&bars->p_full[ps]);
                 }
             }
-            // ---------------------------------------------------- flush D2 (lane = feature)
+        } else if (warp < W_PROD) {
+            // ------------------------------------------------------------ flush D2 (lane = feature)
+            const int q = warp - W_FLUSH;  // TMEM lane quarter == warp % 4
+            const int f = q * 32 + lane;
             tc::mbar_wait(&bars->d2_full, n_item & 1);
             tc::tc_fence_after();
-            if (warp < 3) {
-                const int f = threadIdx.x;
-                const uint32_t taddr = tmem_base + C::D2_COL + ((uint32_t)(warp * 32) << 16);
-                double *dst = acc + ((size_t)unit * C::N_UNIT + g0) * PC_KA + f;
+            const uint32_t taddr = tmem_base + C::D2_COL + ((uint32_t)(q * 32) << 16);
+            double *dst = acc + gfirst * PC_KA + f;
 #pragma unroll
-                for (int j = 0; j < C::NPAD / 16; ++j) {
-                    float t16[16];
-                    tc::tmem_ld16(taddr + j * 16, t16);
-                    tc::tmem_ld_wait();
-                    if (f < PC_KA) {
+            for (int j = 0; j < C::NPAD / 16; ++j) {
+                float t16[16];
+                tc::tmem_ld16(taddr + j * 16, t16);
+                tc::tmem_ld_wait();
+                if (f < PC_KA) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int g = j * 16 + e;
-                            if (g < C::NC && bias_s[g] == 0.f) atomicAdd(dst + (size_t)g * PC_KA, (double)(t16[e] * P_UNSHIFT));
-                        }
+                    for (int e = 0; e < 16; ++e) {
+                        const int g = j * 16 + e;
+                        if (g < C::NC)
+                            atomicAdd(dst + (size_t)g * PC_KA, (double)(t16[e] * P_UNSHIFT));
                     }
                 }
             }
             tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bars->d2_empty);
         }
-        __syncthreads();
+        n_tile += n_tiles;
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tmem_base, C::TM_COLS);
+    if (warp == W_MMA) tc::tmem_dealloc(tmem_base, C::TM_COLS);
 }
 
 template <int MIX>
@@ -321,7 +340,7 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
     PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MIX>::SMEM));
     const int n_work = v.n_items * Cfg<MIX>::N_SLICES;
     const int grid = n_work < h->sm_count ? n_work : h->sm_count;
-    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, b, lgam, acc);
+    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, acc);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

@@ -21,6 +21,8 @@ const char *pc_set_error(const char *fmt, ...) {
 extern "C" {
 
 int pc_abi_version(void) { return PC_ABI_VERSION; }
+int64_t pc_rows_bytes(int64_t n) { return n < 0 ? -1 : n * PC_XS * 4; }
+int64_t pc_gmm_bytes(int64_t n) { return n < 0 ? -1 : n * PC_W_BYTES_PER_GAUSS + 8192; }
 const char *pc_last_error(void) { return g_err; }
 
 int pc_create(int device, pc_handle *out) {
@@ -98,6 +100,16 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
         max_frames = std::max(max_frames, n_frames[u]);
         max_labels = std::max(max_labels, n_labels[u]);
     }
+    std::vector<int64_t> xtile_off(n_utt + 1, 0);
+    std::vector<int32_t> xtile_utt, xtile_t0;
+    for (int u = 0; u < n_utt; ++u) {
+        for (int t0 = 0; t0 < n_frames[u]; t0 += PC_TILE_ROWS) {
+            xtile_utt.push_back(u);
+            xtile_t0.push_back(t0);
+        }
+        xtile_off[u + 1] = (int64_t)xtile_utt.size();
+    }
+    const int64_t n_xtiles = xtile_off[n_utt];
     const int64_t n_pairs = pair_off[n_utt];
     std::vector<int32_t> pair_utt(n_pairs);
     for (int u = 0; u < n_utt; ++u)
@@ -124,7 +136,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
         std::vector<int64_t> cur(unit_pair_off.begin(), unit_pair_off.end() - 1);
         for (int64_t p = 0; p < n_pairs; ++p) sorted_pair[cur[labels[p]]++] = p;
     }
-    std::vector<int64_t> tile_pair, tile_xrow, tile_boff;
+    std::vector<int64_t> tile_pair, tile_xrow, tile_boff, tile_xblk;
     std::vector<int32_t> tile_t0, tile_rows, tile_tp;
     std::vector<int64_t> unit_tile_off(n_units + 1, 0);
     for (int k = 0; k < n_units; ++k) {
@@ -140,6 +152,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
                 tile_rows.push_back(std::min(PC_TILE_ROWS, T - t0));
                 tile_tp.push_back(tp);
                 tile_xrow.push_back(frame_off[u] + t0);
+                tile_xblk.push_back(xtile_off[u] + t0 / PC_TILE_ROWS);
                 tile_boff.push_back(emis_off[u] + PC_EMIT * pos * tp + t0);
             }
         }
@@ -160,6 +173,30 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     item_tile_lo.push_back(n_tiles);
     const int64_t n_items = (int64_t)item_unit.size();
     PC_REQUIRE(n_items < 2147483647LL, "pc_corpus_create: too many work items");
+    // utterance-major groups of <= 3 tiles for the scoring kernel, heaviest first
+    std::vector<int32_t> sitem_utt, sitem_t0, sitem_nt;
+    {
+        std::vector<int32_t> su, st0, snt;
+        for (int u = 0; u < n_utt; ++u) {
+            const int nt = (n_frames[u] + PC_TILE_ROWS - 1) / PC_TILE_ROWS;
+            for (int j = 0; j < nt; j += 3) {
+                su.push_back(u);
+                st0.push_back(j * PC_TILE_ROWS);
+                snt.push_back(std::min(3, nt - j));
+            }
+        }
+        std::vector<int32_t> ord(su.size());
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+            return (int64_t)snt[a] * n_labels[su[a]] > (int64_t)snt[b] * n_labels[su[b]];
+        });
+        for (int32_t i : ord) {
+            sitem_utt.push_back(su[i]);
+            sitem_t0.push_back(st0[i]);
+            sitem_nt.push_back(snt[i]);
+        }
+    }
+    const int64_t n_sitems = (int64_t)sitem_utt.size();
 
     // one device block for every table
     struct Seg { const void *src; size_t bytes; size_t off; };
@@ -189,6 +226,13 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_ilo = add(item_tile_lo.data(), item_tile_lo.size() * 8);
     size_t o_iunit = add(item_unit.data(), (size_t)n_items * 4);
     size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 4);
+    size_t o_sutt = add(sitem_utt.data(), (size_t)n_sitems * 4);
+    size_t o_st0 = add(sitem_t0.data(), (size_t)n_sitems * 4);
+    size_t o_snt = add(sitem_nt.data(), (size_t)n_sitems * 4);
+    size_t o_xoff = add(xtile_off.data(), xtile_off.size() * 8);
+    size_t o_xutt = add(xtile_utt.data(), (size_t)n_xtiles * 4);
+    size_t o_xt0 = add(xtile_t0.data(), (size_t)n_xtiles * 4);
+    size_t o_txblk = add(tile_xblk.data(), (size_t)n_tiles * 8);
     PC_CUDA_TRY(cudaSetDevice(h->device));
     char *dev = nullptr;
     PC_CUDA_TRY(cudaMalloc((void **)&dev, std::max<size_t>(total, 256)));
@@ -235,6 +279,16 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     v.item_tile_lo = (const int64_t *)(dev + o_ilo);
     v.item_unit = (const int32_t *)(dev + o_iunit);
     v.scratch0 = (float *)(dev + o_scratch);
+    v.total_frames = frame_off[n_utt];
+    v.n_sitems = (int32_t)n_sitems;
+    v.sitem_utt = (const int32_t *)(dev + o_sutt);
+    v.sitem_t0 = (const int32_t *)(dev + o_st0);
+    v.sitem_nt = (const int32_t *)(dev + o_snt);
+    v.n_xtiles = n_xtiles;
+    v.xtile_off = (const int64_t *)(dev + o_xoff);
+    v.xtile_utt = (const int32_t *)(dev + o_xutt);
+    v.xtile_t0 = (const int32_t *)(dev + o_xt0);
+    v.tile_xblk = (const int64_t *)(dev + o_txblk);
     c->host_frame_off = new int64_t[4 * (size_t)(n_utt + 1)];
     c->host_emis_off = c->host_frame_off + (n_utt + 1);
     c->host_pair_off = c->host_emis_off + (n_utt + 1);
@@ -260,6 +314,9 @@ int64_t pc_corpus_total_frames(pc_corpus c) { return c ? c->total_frames : -1; }
 int64_t pc_corpus_emission_floats(pc_corpus c) { return c ? c->emis_floats : -1; }
 int64_t pc_corpus_total_pairs(pc_corpus c) { return c ? c->v.n_pairs : -1; }
 int64_t pc_corpus_total_states(pc_corpus c) { return c ? c->total_states : -1; }
+int64_t pc_corpus_frames_bytes(pc_corpus c) {
+    return c ? (int64_t)(pc_x16_offset(c->total_frames) + (size_t)c->v.n_xtiles * PC_XTILE_BYTES) : -1;
+}
 
 int pc_corpus_offsets(pc_corpus c, int64_t *frame_off, int64_t *emis_off, int64_t *pair_off,
                       int64_t *state_off) {
@@ -292,32 +349,53 @@ static int check_dim_mix(const char *fn, int dim, int mix) {
 
 int pc_pack_gmm(pc_handle h, const double *mean, const double *var, const double *alpha,
                 const double *shift, const double *inv_scale, int32_t n_gauss, int32_t dim,
-                float *W, void *stream) {
+                int32_t mix, float *W, void *stream) {
     PC_ENTER(h);
     PC_REQUIRE(n_gauss >= 0, "pc_pack_gmm: n_gauss=%d", n_gauss);
     PC_REQUIRE(n_gauss == 0 || (mean && var && alpha && W), "pc_pack_gmm: NULL pointer");
     int rc = check_dim_mix("pc_pack_gmm", dim, 1);
     if (rc) return rc;
-    return launch_pack_gmm(h, mean, var, alpha, shift, inv_scale, n_gauss, dim, W,
+    PC_REQUIRE(mix >= 0, "pc_pack_gmm: mix=%d", mix);
+    PC_REQUIRE(mix == 0 || n_gauss % (PC_EMIT * mix) == 0,
+               "pc_pack_gmm: %d Gaussians is not a multiple of 3*mix (mix=%d)", n_gauss, mix);
+    return launch_pack_gmm(h, mean, var, alpha, shift, inv_scale, n_gauss, dim, mix, W,
                            (cudaStream_t)stream);
 }
 
-int pc_prepare_frames_f64(pc_handle h, const double *x, int64_t n, int32_t dim,
+int pc_prepare_frames_f64(pc_handle h, pc_corpus c, const double *x, int32_t dim,
                           const double *shift, const double *inv_scale, float *X, void *stream) {
     PC_ENTER(h);
-    PC_REQUIRE(n >= 0 && (n == 0 || (x && X)), "pc_prepare_frames_f64: bad arguments");
+    PC_REQUIRE(c && (c->total_frames == 0 || (x && X)), "pc_prepare_frames_f64: bad arguments");
     int rc = check_dim_mix("pc_prepare_frames_f64", dim, 1);
     if (rc) return rc;
-    return launch_prepare_frames(h, x, 1, n, dim, shift, inv_scale, X, (cudaStream_t)stream);
+    return launch_prepare_frames(h, c->v, x, 1, dim, shift, inv_scale, X, (cudaStream_t)stream);
 }
 
-int pc_prepare_frames_f32(pc_handle h, const float *x, int64_t n, int32_t dim, const double *shift,
+int pc_prepare_frames_f32(pc_handle h, pc_corpus c, const float *x, int32_t dim, const double *shift,
                           const double *inv_scale, float *X, void *stream) {
     PC_ENTER(h);
-    PC_REQUIRE(n >= 0 && (n == 0 || (x && X)), "pc_prepare_frames_f32: bad arguments");
+    PC_REQUIRE(c && (c->total_frames == 0 || (x && X)), "pc_prepare_frames_f32: bad arguments");
     int rc = check_dim_mix("pc_prepare_frames_f32", dim, 1);
     if (rc) return rc;
-    return launch_prepare_frames(h, x, 0, n, dim, shift, inv_scale, X, (cudaStream_t)stream);
+    return launch_prepare_frames(h, c->v, x, 0, dim, shift, inv_scale, X, (cudaStream_t)stream);
+}
+
+int pc_prepare_rows_f64(pc_handle h, const double *x, int64_t n, int32_t dim, const double *shift,
+                        const double *inv_scale, float *X, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n >= 0 && (n == 0 || (x && X)), "pc_prepare_rows_f64: bad arguments");
+    int rc = check_dim_mix("pc_prepare_rows_f64", dim, 1);
+    if (rc) return rc;
+    return launch_prepare_rows(h, x, 1, n, dim, shift, inv_scale, X, (cudaStream_t)stream);
+}
+
+int pc_prepare_rows_f32(pc_handle h, const float *x, int64_t n, int32_t dim, const double *shift,
+                        const double *inv_scale, float *X, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n >= 0 && (n == 0 || (x && X)), "pc_prepare_rows_f32: bad arguments");
+    int rc = check_dim_mix("pc_prepare_rows_f32", dim, 1);
+    if (rc) return rc;
+    return launch_prepare_rows(h, x, 0, n, dim, shift, inv_scale, X, (cudaStream_t)stream);
 }
 
 int pc_gmm_score(pc_handle h, pc_corpus c, const float *X, const float *W, int32_t mix, float *b,
@@ -459,9 +537,9 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     // workspace carve-up (256-byte aligned)
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    size_t o_raw = carve((size_t)F * dim * 4), o_X = carve((size_t)F * PC_XS * 4);
+    size_t o_raw = carve((size_t)F * dim * 4), o_X = carve((size_t)pc_corpus_frames_bytes(c));
     size_t o_b = carve((size_t)c->emis_floats * 4), o_lg = carve((size_t)c->emis_floats * 4);
-    size_t o_W = carve((size_t)G * PC_KA * 4), o_acc = carve((size_t)G * PC_KA * 8);
+    size_t o_W = carve((size_t)pc_gmm_bytes(G)), o_acc = carve((size_t)G * PC_KA * 8);
     size_t o_mean = carve((size_t)G * dim * 8), o_var = carve((size_t)G * dim * 8);
     size_t o_alpha = carve((size_t)G * 8), o_tm = carve((size_t)n_units * 25 * 8);
     size_t o_ls = carve((size_t)n_units * 5 * 8), o_ln = carve((size_t)n_units * 5 * 8);
@@ -495,8 +573,8 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
         PC_LAUNCH_CHECK();
         h->launches += 2;
     }
-    if ((rc = launch_prepare_frames(h, raw, 0, F, dim, nullptr, nullptr, X, st))) return rc;
-    if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, W, st))) return rc;
+    if ((rc = launch_prepare_frames(h, c->v, raw, 0, dim, nullptr, nullptr, X, st))) return rc;
+    if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, mix, W, st))) return rc;
     if (h->use_tc && score_tc_supported(mix)) {
         if ((rc = launch_score_tc(h, c->v, X, W, mix, b, st))) return rc;
     } else if ((rc = launch_score_simt(h, c->v, X, W, mix, b, st))) {

@@ -8,6 +8,12 @@
 #include "../../include/poccala_b200.h"
 
 #define PC_TILE_ROWS 128  // frames per work tile (one tcgen05 M=128 accumulator block)
+#define PC_XTILE_BYTES (2 * (PC_KA / 8) * PC_TILE_ROWS * 16)  // one frame-tile operand image (40 KiB)
+#define PC_WGROUP_BYTES (2 * (PC_KA / 8) * 128)               // 8 Gaussian rows of a unit image (2560 B)
+
+// byte offsets of the fp16 operand images inside the W / X buffers (pack.cu)
+__host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 #define PC_NEG_INF (-INFINITY)
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
@@ -38,6 +44,18 @@ struct CorpusView {
     const int64_t *item_tile_lo;  // [n_items+1] tile range of each work item (one unit per item)
     const int32_t *item_unit;     // [n_items]
     float *scratch0;              // [total_frames] entry-state beta_hat (K2 scratch)
+    // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
+    int64_t total_frames;
+    int32_t n_sitems;
+    const int32_t *sitem_utt;     // [n_sitems]
+    const int32_t *sitem_t0;      // [n_sitems] first frame of the group inside the utterance
+    const int32_t *sitem_nt;      // [n_sitems] tiles in the group (1..3)
+    // frame-tile operand images (one per 128-frame tile of every utterance, utterance-major)
+    int64_t n_xtiles;
+    const int64_t *xtile_off;     // [n_utt+1] first image of the utterance
+    const int32_t *xtile_utt;     // [n_xtiles]
+    const int32_t *xtile_t0;      // [n_xtiles] first frame of the image inside the utterance
+    const int64_t *tile_xblk;     // [n_tiles] image index of each unit-major work tile
 };
 
 __host__ __device__ inline int pc_tpad(int t) { return (t + 3) & ~3; }
@@ -121,9 +139,11 @@ struct pc_corpus_s {
 
 // Kernel launchers implemented in the per-kernel translation units.
 int launch_pack_gmm(pc_handle h, const double *mean, const double *var, const double *alpha,
-                    const double *shift, const double *inv_scale, int n_gauss, int dim, float *W,
-                    cudaStream_t st);
-int launch_prepare_frames(pc_handle h, const void *x, int is_f64, int64_t n, int dim,
+                    const double *shift, const double *inv_scale, int n_gauss, int dim, int mix,
+                    float *W, cudaStream_t st);
+int launch_prepare_rows(pc_handle h, const void *x, int is_f64, int64_t n, int dim,
+                        const double *shift, const double *inv_scale, float *X, cudaStream_t st);
+int launch_prepare_frames(pc_handle h, const CorpusView &cv, const void *x, int is_f64, int dim,
                           const double *shift, const double *inv_scale, float *X, cudaStream_t st);
 int launch_score_simt(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                       float *b, cudaStream_t st);

@@ -1,22 +1,56 @@
-// Model packing and frame preparation.
+// Model packing and frame preparation: the HBM-resident operand formats.
 //
 // pack_gmm: util.gaussian_function's log branch (util.py:20-36) plus the log(alpha) term of
-// Clustering.GMM.point (Clustering.py:753-757) folded into one fp32 row per Gaussian:
-//     score(x, g) = <[x', x'^2, 1, 1], W_g>,   x' = (x - shift) * inv_scale
-//     W_g = [ mu'/var' (39), k_hi | -1/(2 var') (39), k_lo ]   (matches [x (39), 1 | x^2 (39), 1])
+// Clustering.GMM.point (Clustering.py:753-757) folded into one row per Gaussian:
+//     score(x, g) = <[x' (39), 1 | x'^2 (39), 1], W_g>,   x' = (x - shift) * inv_scale
+//     W_g = [ mu'/var' (39), k_hi | -1/(2 var') (39), k_lo ]
 //     k   = log alpha - D/2 log 2pi - 1/2 sum_d var_d (Q1: ORIGINAL variances, not log-det)
 //           - 1/2 sum_d mu'^2/var'
-// All arithmetic in fp64; k is stored as an fp32 pair so the constant keeps ~48 bits.
+// All arithmetic in fp64.  W buffer layout (G Gaussians, U = G / (3*mix) units):
+//     [0, 320 G)              fp32 rows [G][80]                         (CUDA-core kernels)
+//     [320 G, 324 G)          float scale[G]
+//     [324 G, 328 G)          int32 flags[G]   (flags[0] != 0 <=> some row has scale != 1)
+//     [pc_w16_offset(G), ..)  per unit one tcgen05 operand image: fp16 [NPAD/8 row groups][2 (hi, lo)]
+//                             [10 chunks][8 rows][8 halves], NPAD = 3*mix rounded up to 16 (padding
+//                             rows are zero).  Every [8 rows][16 B] block is one UMMA core matrix
+//                             (LBO = 128 B between K chunks, SBO = 2560 B between row groups), units
+//                             and slices of units concatenate along N, and a unit is ONE cp.async.bulk.
+// A row is scaled by 2^-e so that it fits fp16 (scale = 2^e undoes it in the epilogue); a row whose
+// constant is not finite (alpha = 0 -> log 0) is stored as zero weights with the constant -60000,
+// which underflows to probability 0 against any live component (the fp32 row keeps -inf).
+//
+// prepare_frames: X buffer = fp32 rows [F][40] (cols [0,D) standardised data, col 39 = 1), then at
+// pc_x16_offset(F) one operand image per 128-frame tile of every utterance:
+// fp16 [2 (hi, lo)][10 chunks][128 rows][8] of the augmented row [x | x^2] (chunks 0-4 = x, 5-9 = x^2),
+// rows past the end of the utterance zero: a tile is ONE 40 KiB cp.async.bulk.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+
+__device__ __forceinline__ void split_h(float a, __half &hi, __half &lo) {
+    hi = __float2half_rn(a);
+    lo = __float2half_rn(a - __half2float(hi));
+}
 
 __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *__restrict__ var,
                                 const double *__restrict__ alpha, const double *__restrict__ shift,
-                                const double *__restrict__ inv_scale, int n_gauss, int dim,
+                                const double *__restrict__ inv_scale, int n_gauss, int dim, int n_unit,
                                 float *__restrict__ W) {
-    int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_gauss) return;
+    const int npad = (n_unit + 15) & ~15;
+    const int n_units = n_gauss / n_unit;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // (unit, padded row)
+    if (slot >= n_units * npad) return;
+    const int unit = slot / npad, row = slot - unit * npad;
+    uint8_t *img = reinterpret_cast<uint8_t *>(W) + pc_w16_offset(n_gauss) + (size_t)unit * 2 * (PC_KA / 8) * npad * 16;
+    if (row >= n_unit) {  // padding row of the operand image
+        for (int c = 0; c < 2 * (PC_KA / 8); ++c)
+            *reinterpret_cast<uint4 *>(img + (size_t)(row >> 3) * PC_WGROUP_BYTES + c * 128 + (row & 7) * 16) =
+                make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int g = unit * n_unit + row;
     const double LOG_2PI = 1.8378770664093453;  // np.log(2*pi), util.py:14
-    float *w = W + (size_t)g * PC_KA;
+    float w[PC_KA];
     double sum_var = 0.0, quad = 0.0;
     for (int d = 0; d < PC_DIM_MAX; ++d) {
         if (d < dim) {
@@ -35,61 +69,188 @@ __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *_
             w[PC_XS + d] = 0.f;
         }
     }
-    double k = log(alpha[g]) - 0.5 * dim * LOG_2PI - 0.5 * sum_var - 0.5 * quad;
-    float k_hi = (float)k;
-    float k_lo = isfinite(k) ? (float)(k - (double)k_hi) : 0.f;
+    const double k = log(alpha[g]) - 0.5 * dim * LOG_2PI - 0.5 * sum_var - 0.5 * quad;
+    const float k_hi = (float)k;
+    const float k_lo = isfinite(k) ? (float)(k - (double)k_hi) : 0.f;
     w[PC_XS - 1] = k_hi;
     w[PC_KA - 1] = k_lo;
+    float *wrow = W + (size_t)g * PC_KA;
+    for (int i = 0; i < PC_KA; ++i) wrow[i] = w[i];
+
+    // ---- fp16 operand image
+    float *scale = W + (size_t)n_gauss * PC_KA;
+    int *flags = reinterpret_cast<int *>(scale + n_gauss);
+    const bool dead = !isfinite(k);
+    float mx = 0.f;
+    for (int i = 0; i < PC_KA; ++i) {
+        float a = fabsf(w[i]);
+        if (a <= 3.0e38f) mx = fmaxf(mx, a);
+    }
+    int e = 0;
+    if (mx > 16384.f) e = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127 - 13;
+    const double inv = ldexp(1.0, -e);
+    scale[g] = dead ? 1.f : (float)ldexp(1.0, e);
+    if (!dead && e != 0) atomicOr(flags, 1);
+    // the constant keeps 4 fp16 pieces: (hi, lo) of k in column 39, (hi, lo) of the rest in column 79
+    __half k1h = __float2half_rn(-60000.f), k1l = __float2half_rn(0.f), k2h = k1l, k2l = k1l;
+    if (!dead) {
+        const double ks = k * inv;
+        k1h = __float2half_rn((float)ks);
+        double r = ks - (double)__half2float(k1h);
+        k1l = __float2half_rn((float)r);
+        r -= (double)__half2float(k1l);
+        k2h = __float2half_rn((float)r);
+        r -= (double)__half2float(k2h);
+        k2l = __float2half_rn((float)r);
+    }
+    for (int c = 0; c < PC_KA / 8; ++c) {
+        __half hi[8], lo[8];
+        for (int j = 0; j < 8; ++j) {
+            const int i = 8 * c + j;
+            if (i == PC_XS - 1) {
+                hi[j] = k1h; lo[j] = k1l;
+            } else if (i == PC_KA - 1) {
+                hi[j] = k2h; lo[j] = k2l;
+            } else if (dead) {
+                hi[j] = lo[j] = __float2half_rn(0.f);
+            } else {
+                split_h((float)((double)w[i] * inv), hi[j], lo[j]);
+            }
+        }
+        uint8_t *grp = img + (size_t)(row >> 3) * PC_WGROUP_BYTES + (row & 7) * 16;
+        *reinterpret_cast<uint4 *>(grp + c * 128) = *reinterpret_cast<uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(grp + PC_WGROUP_BYTES / 2 + c * 128) = *reinterpret_cast<uint4 *>(lo);
+    }
 }
 
+// fp32 rows only (dense scoring sweep; no corpus): one thread per (frame, 8-feature chunk)
 template <typename T>
-__global__ void prepare_frames_kernel(const T *__restrict__ x, int64_t n, int dim,
+__global__ void prepare_rows_kernel(const T *__restrict__ x, int64_t n, int dim,
+                                    const double *__restrict__ shift,
+                                    const double *__restrict__ inv_scale, float *__restrict__ X) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 5) return;
+    const int64_t f = i / 5;
+    const int c = (int)(i - f * 5);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = 8 * c + j;
+        float out;
+        if (d < dim) {
+            double val = (double)x[f * dim + d];
+            out = (float)((val - (shift ? shift[d] : 0.0)) * (inv_scale ? inv_scale[d] : 1.0));
+            out = fminf(fmaxf(out, -240.f), 240.f);
+        } else {
+            out = (d == PC_XS - 1) ? 1.f : 0.f;
+        }
+        v[j] = out;
+    }
+    float4 *row = reinterpret_cast<float4 *>(X + (size_t)f * PC_XS + 8 * c);
+    row[0] = make_float4(v[0], v[1], v[2], v[3]);
+    row[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// corpus frames: one thread per (tile image, row, 8-feature chunk)
+template <typename T>
+__global__ void prepare_frames_kernel(CorpusView cv, const T *__restrict__ x, int dim,
                                       const double *__restrict__ shift,
                                       const double *__restrict__ inv_scale, float *__restrict__ X) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output float
-    if (i >= n * PC_XS) return;
-    int64_t f = i / PC_XS;
-    int d = (int)(i - f * PC_XS);
-    float out;
-    if (d < dim) {
-        double v = (double)x[f * dim + d];
-        double sh = shift ? shift[d] : 0.0;
-        double is = inv_scale ? inv_scale[d] : 1.0;
-        out = (float)((v - sh) * is);
-    } else {
-        out = (d == PC_XS - 1) ? 1.f : 0.f;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cv.n_xtiles * PC_TILE_ROWS * 5) return;
+    const int64_t blk = i / (PC_TILE_ROWS * 5);
+    const int rem = (int)(i - blk * (PC_TILE_ROWS * 5));
+    const int c = rem / PC_TILE_ROWS, r = rem - c * PC_TILE_ROWS;  // consecutive threads -> consecutive rows
+    const int u = cv.xtile_utt[blk];
+    const int64_t f0 = cv.frame_off[u];
+    const int T_u = (int)(cv.frame_off[u + 1] - f0);
+    const int t = cv.xtile_t0[blk] + r;
+    const bool valid = t < T_u;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = 8 * c + j;
+        float out = 0.f;
+        if (valid) {
+            if (d < dim) {
+                double val = (double)x[(f0 + t) * dim + d];
+                out = (float)((val - (shift ? shift[d] : 0.0)) * (inv_scale ? inv_scale[d] : 1.0));
+                // keep x^2 inside the fp16 range of the tensor-core operands (|x'| is in standard
+                // deviations when the engine standardises, so this never triggers on sane data)
+                out = fminf(fmaxf(out, -240.f), 240.f);
+            } else {
+                out = (d == PC_XS - 1) ? 1.f : 0.f;
+            }
+        }
+        v[j] = out;
     }
-    X[i] = out;
+    if (valid) {
+        float4 *row = reinterpret_cast<float4 *>(X + (size_t)(f0 + t) * PC_XS + 8 * c);
+        row[0] = make_float4(v[0], v[1], v[2], v[3]);
+        row[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    uint8_t *img = reinterpret_cast<uint8_t *>(X) + pc_x16_offset(cv.total_frames) + (size_t)blk * PC_XTILE_BYTES;
+    __half xh[8], xl[8], qh[8], ql[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        split_h(v[j], xh[j], xl[j]);
+        split_h(v[j] * v[j], qh[j], ql[j]);
+    }
+    constexpr int CH = PC_TILE_ROWS * 16;   // bytes per chunk
+    constexpr int PIECE = (PC_KA / 8) * CH;  // bytes per piece
+    *reinterpret_cast<uint4 *>(img + (size_t)c * CH + r * 16) = *reinterpret_cast<uint4 *>(xh);
+    *reinterpret_cast<uint4 *>(img + (size_t)(c + 5) * CH + r * 16) = *reinterpret_cast<uint4 *>(qh);
+    *reinterpret_cast<uint4 *>(img + PIECE + (size_t)c * CH + r * 16) = *reinterpret_cast<uint4 *>(xl);
+    *reinterpret_cast<uint4 *>(img + PIECE + (size_t)(c + 5) * CH + r * 16) = *reinterpret_cast<uint4 *>(ql);
 }
 
 int launch_pack_gmm(pc_handle h, const double *mean, const double *var, const double *alpha,
-                    const double *shift, const double *inv_scale, int n_gauss, int dim, float *W,
-                    cudaStream_t st) {
+                    const double *shift, const double *inv_scale, int n_gauss, int dim, int mix,
+                    float *W, cudaStream_t st) {
     if (n_gauss == 0) return PC_OK;
-    int threads = 128;
-    int blocks = (n_gauss + threads - 1) / threads;
-    pack_gmm_kernel<<<blocks, threads, 0, st>>>(mean, var, alpha, shift, inv_scale, n_gauss, dim, W);
+    const int n_unit = mix > 0 ? PC_EMIT * mix : n_gauss;  // mix = 0: flat list = one pseudo unit
+    const int npad = (n_unit + 15) & ~15;
+    const int slots = (n_gauss / n_unit) * npad;
+    const int threads = 64;
+    const int blocks = (slots + threads - 1) / threads;
+    PC_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<char *>(W) + (size_t)n_gauss * 324, 0, sizeof(int), st));
+    pack_gmm_kernel<<<blocks, threads, 0, st>>>(mean, var, alpha, shift, inv_scale, n_gauss, dim, n_unit, W);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
 }
 
-int launch_prepare_frames(pc_handle h, const void *x, int is_f64, int64_t n, int dim,
-                          const double *shift, const double *inv_scale, float *X, cudaStream_t st) {
+int launch_prepare_rows(pc_handle h, const void *x, int is_f64, int64_t n, int dim,
+                        const double *shift, const double *inv_scale, float *X, cudaStream_t st) {
     if (n == 0) return PC_OK;
-    int threads = 256;
-    int64_t total = n * PC_XS;
-    int64_t blocks = (total + threads - 1) / threads;
+    const int threads = 256;
+    const int64_t blocks = (n * 5 + threads - 1) / threads;
+    if (blocks > 2147483647LL) {
+        pc_set_error("prepare_rows: too many frames for one launch");
+        return PC_ERR_UNSUPPORTED;
+    }
+    if (is_f64)
+        prepare_rows_kernel<double><<<(unsigned)blocks, threads, 0, st>>>((const double *)x, n, dim, shift, inv_scale, X);
+    else
+        prepare_rows_kernel<float><<<(unsigned)blocks, threads, 0, st>>>((const float *)x, n, dim, shift, inv_scale, X);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
+int launch_prepare_frames(pc_handle h, const CorpusView &cv, const void *x, int is_f64, int dim,
+                          const double *shift, const double *inv_scale, float *X, cudaStream_t st) {
+    if (cv.n_xtiles == 0) return PC_OK;
+    const int threads = 256;
+    const int64_t blocks = (cv.n_xtiles * PC_TILE_ROWS * 5 + threads - 1) / threads;
     if (blocks > 2147483647LL) {
         pc_set_error("prepare_frames: too many frames for one launch");
         return PC_ERR_UNSUPPORTED;
     }
     if (is_f64)
-        prepare_frames_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(
-            (const double *)x, n, dim, shift, inv_scale, X);
+        prepare_frames_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(cv, (const double *)x, dim, shift, inv_scale, X);
     else
-        prepare_frames_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(
-            (const float *)x, n, dim, shift, inv_scale, X);
+        prepare_frames_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(cv, (const float *)x, dim, shift, inv_scale, X);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

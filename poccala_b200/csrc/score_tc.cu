@@ -1,35 +1,36 @@
-// K1 (tensor-core generation): GMM scoring as a tcgen05 contraction with a fused log-sum-exp.
+// K1 (tensor-core generation): GMM scoring as a TMA-fed tcgen05 contraction with a fused
+// log-sum-exp.
 //
 // Same arithmetic as score_simt.cu (LHMM.cal_observation_pro -> GMM.point -> gaussian_function,
 // LHMM.py:163-187, Clustering.py:740-767, util.py:20-36,54-77):
 //     c[t, g] = <[x_t (39), 1 | x_t^2 (39), 1], W_g>,     b[t, s] = logsumexp_{g in s} c[t, g]
-// mapped on the 5th-generation tensor cores.  Both operands are split into fp16 (hi, lo) pairs
-// (x = hi + lo keeps 22 significant bits) and the contraction is the error-compensated sum
-//     A_hi*B_hi + A_hi*B_lo + A_lo*B_hi      (fp32 accumulation in TMEM)
-// which reproduces the fp32 result (a single fp16/bf16/tf32 pass does not meet the 1e-4 parity
-// bound).  Rows of W whose entries exceed the fp16 range are scaled by a power of two
-// and the accumulator is scaled back in the epilogue.
+// Both operands live in HBM as fp16 (hi, lo) pairs (pack.cu) and the contraction is the
+// error-compensated sum  A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  with fp32 accumulation in TMEM, which
+// reproduces the fp32 result (one fp16/bf16/tf32 pass does not meet the 1e-4 parity bound).
 //
-// One persistent CTA per SM walks work items (runs of 128-frame tiles of one unit):
-//   warp 8      TMA producer : cp.async.bulk of raw X rows (128 x 160 B) into a 3-stage ring
-//   warps 4-7   converters   : raw fp32 rows -> [x | x^2] fp16 hi/lo operand tiles (2 stages),
-//                              and once per item the unit's W rows -> resident B_hi / B_lo
-//   warp 9      MMA issuer   : 15 tcgen05.mma (M=128, N=NPAD, K=16) per tile, tcgen05.commit
-//   warps 0-3   epilogue     : tcgen05.ld (one frame per thread, all Gaussians in registers),
-//                              log-sum-exp per state, coalesced store of b
-// Shared-memory operand layout (no swizzle): 16-byte chunk c of row r at c*rows*16 + r*16, i.e.
-// 8x16 B core matrices, SBO = 128 B between 8-row groups, LBO = rows*16 B between K chunks.
+// Work decomposition is UTTERANCE-major: a work item is a group of <= G consecutive 128-frame
+// tiles of one utterance; the tiles stay in shared memory while the Gaussians of every label
+// position of the utterance stream through a ring of B stages.  Per SM this needs
+// (G*40 KB + L*|B|) of shared-memory fill per G*L tile contractions, which keeps the kernel on the
+// tensor pipe instead of the L2->SM fill rate.
+//
+//   warp 16     TMA producer : one cp.async.bulk per frame tile (40 KiB) and one per position (the
+//                              unit's operand image); operands land directly in the UMMA layout
+//   warp 17     MMA issuer   : 15 tcgen05.mma (M=128, N=NPAD, K=16) per (tile, position), commits
+//   warps 0-15  epilogue     : one warpgroup per TMEM buffer, alternating (tile, position) pairs: tcgen05.ld
+//                              (one frame per thread), log-sum-exp per state, coalesced store of b
+// Shared-memory operand layouts (no swizzle, 8 rows x 16 B core matrices): frame tiles keep 16-byte
+// chunk c of row r at c*2048 + r*16 (SBO = 128 B between 8-row groups, LBO = 2048 B between K chunks);
+// Gaussian images are row-group major (LBO = 128 B, SBO = 2560 B), see pack.cu.
 #include "tc_common.cuh"
+
+__device__ long long g_pc_dbg[8192];
 
 namespace {
 
-constexpr int ROWS = PC_TILE_ROWS;        // 128 frames per tile (UMMA M)
-constexpr int KCH = PC_KA / 8;            // 10 sixteen-byte chunks of 8 halves along K
-constexpr int RAW_STAGES = 3;
-constexpr int A_STAGES = 2;
-constexpr int RAW_BYTES = ROWS * PC_XS * 4;   // 20480
-constexpr int A_PIECE = KCH * ROWS * 16;      // 20480 per hi / lo piece
-constexpr int NTHREADS = 320;
+using tc::T_KCH;
+using tc::T_PIECE;
+using tc::T_ROWS;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -37,298 +38,271 @@ template <int MIX>
 struct Cfg {
     static constexpr int N_REAL = PC_EMIT * MIX;
     static constexpr int NPAD = (N_REAL + 15) & ~15;
-    static constexpr int B_PIECE = KCH * NPAD * 16;
+    static constexpr int B_PIECE = T_KCH * NPAD * 16;
+    static constexpr int B_STAGE = 2 * B_PIECE;  // hi, lo
+    static constexpr int G = MIX <= 16 ? 3 : 2;                                // tiles per group
+    static constexpr int NA = MIX <= 16 ? 4 : (MIX <= 32 ? 3 : 2);             // frame-tile slots
+    static constexpr int NB = MIX <= 16 ? 3 : 2;                               // B stages
     static constexpr int TM_STRIDE = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256));
     static constexpr int TM_BUFS = TM_STRIDE >= 256 ? 2 : 4;
     static constexpr int TM_COLS = TM_STRIDE * TM_BUFS;
-    static constexpr int SMEM = 1024 + RAW_STAGES * RAW_BYTES + A_STAGES * 2 * A_PIECE + 2 * B_PIECE +
-                                3 * NPAD * 4 + 256;
+    static constexpr int EPI_GROUPS = TM_BUFS;                // one epilogue warpgroup per TMEM buffer
+    static constexpr int W_PROD = 4 * EPI_GROUPS, W_MMA = W_PROD + 1;
+    static constexpr int NTHREADS = (W_MMA + 1) * 32;
+    static constexpr int SMEM = 1024 + NA * 2 * T_PIECE + NB * B_STAGE;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 struct Bars {
-    uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
-    uint64_t a_full[A_STAGES], a_empty[A_STAGES];
+    uint64_t a_full[4], a_empty[4];
+    uint64_t b_full[3], b_empty[3];
     uint64_t tm_full[4], tm_empty[4];
     uint32_t tmem_base;
 };
 
+// log-sum-exp of one state's MIX component scores held in TMEM columns [col0, col0 + MIX) of the
+// calling thread's lane.  SCALED: multiply by the per-Gaussian power-of-two scale first.
+template <int MIX, bool SCALED>
+__device__ __forceinline__ float state_lse(const float (&v_in)[MIX], const float *__restrict__ scale) {
+    float v[MIX];
+#pragma unroll
+    for (int e = 0; e < MIX; ++e) v[e] = SCALED ? v_in[e] * __ldg(scale + e) : v_in[e];
+    float m0 = v[0], m1 = v[1 % MIX], m2 = v[2 % MIX], m3 = v[3 % MIX];
+#pragma unroll
+    for (int e = 4; e + 3 < MIX; e += 4) {
+        m0 = fmaxf(m0, v[e]); m1 = fmaxf(m1, v[e + 1]); m2 = fmaxf(m2, v[e + 2]); m3 = fmaxf(m3, v[e + 3]);
+    }
+    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    const float ms = mx * LOG2E;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int e = 0; e + 3 < MIX; e += 4) {
+        s0 += tc::ex2(fmaf(v[e], LOG2E, -ms));
+        s1 += tc::ex2(fmaf(v[e + 1], LOG2E, -ms));
+        s2 += tc::ex2(fmaf(v[e + 2], LOG2E, -ms));
+        s3 += tc::ex2(fmaf(v[e + 3], LOG2E, -ms));
+    }
+    return mx + LN2 * tc::lg2((s0 + s1) + (s2 + s3));
+}
+
+template <int MIX, bool SCALED>
+__device__ __forceinline__ void epilogue_pair(uint32_t taddr, const float *__restrict__ scale,
+                                              float (&res)[PC_EMIT]) {
+    using C = Cfg<MIX>;
+    if constexpr (MIX >= 16) {
+#pragma unroll
+        for (int s = 0; s < PC_EMIT; ++s) {
+            float v[MIX];
+#pragma unroll
+            for (int jj = 0; jj < MIX / 16; ++jj) {
+                float t16[16];
+                tc::tmem_ld16(taddr + s * MIX + jj * 16, t16);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[jj * 16 + e] = t16[e];
+            }
+            tc::tmem_ld_wait();
+            res[s] = state_lse<MIX, SCALED>(v, scale + s * MIX);
+        }
+    } else {
+        float all[C::NPAD];
+#pragma unroll
+        for (int jj = 0; jj < C::NPAD / 16; ++jj) {
+            float t16[16];
+            tc::tmem_ld16(taddr + jj * 16, t16);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) all[jj * 16 + e] = t16[e];
+        }
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int s = 0; s < PC_EMIT; ++s) {
+            float v[MIX];
+#pragma unroll
+            for (int e = 0; e < MIX; ++e) v[e] = all[s * MIX + e];
+            res[s] = state_lse<MIX, SCALED>(v, scale + s * MIX);
+        }
+    }
+}
+
 template <int MIX>
-__global__ void __launch_bounds__(NTHREADS, 1)
-score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W,
-                float *__restrict__ b) {
+__global__ void __launch_bounds__(Cfg<MIX>::NTHREADS, 1)
+score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W, int n_gauss,
+                float *__restrict__ b, int dbg) {
     using C = Cfg<MIX>;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars *bars = reinterpret_cast<Bars *>(smem);
-    uint8_t *raw_s = smem + 1024;
-    uint8_t *a_s = raw_s + RAW_STAGES * RAW_BYTES;
-    uint8_t *b_s = a_s + A_STAGES * 2 * A_PIECE;
-    float *scale_s = reinterpret_cast<float *>(b_s + 2 * C::B_PIECE);
-    float *bias_s = scale_s + C::NPAD;
-    uint32_t *rowmax_s = reinterpret_cast<uint32_t *>(bias_s + C::NPAD);
+    uint8_t *a_s = smem + 1024;
+    uint8_t *b_s = a_s + C::NA * 2 * T_PIECE;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RAW_STAGES; ++i) { tc::mbar_init(&bars->raw_full[i], 1); tc::mbar_init(&bars->raw_empty[i], 4); }
-        for (int i = 0; i < A_STAGES; ++i) { tc::mbar_init(&bars->a_full[i], 4); tc::mbar_init(&bars->a_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) { tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], 4); }
+        for (int i = 0; i < 4; ++i) {
+            tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1);
+            tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], 4);
+        }
+        for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars->b_full[i], 1); tc::mbar_init(&bars->b_empty[i], 1); }
         tc::mbar_fence_init();
     }
-    if (warp == 9) tc::tmem_alloc(&bars->tmem_base, C::TM_COLS);
+    if (warp == C::W_MMA) tc::tmem_alloc(&bars->tmem_base, C::TM_COLS);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base_ = bars->tmem_base;
+    const uint32_t tmem_base = tmem_base_;
 
-    uint32_t n_raw = 0, n_a = 0, n_tm = 0;  // per-role running tile counters (stage / parity)
-    for (int item = blockIdx.x; item < v.n_items; item += gridDim.x) {
-        const int64_t lo = v.item_tile_lo[item], hi = v.item_tile_lo[item + 1];
-        const int n_tiles = (int)(hi - lo);
-        // ------------------------------------------------ resident B operand for this item's unit
-        if (warp >= 4 && warp < 8) {
-            const int tid = threadIdx.x - 128;
-            const float *wu = W + (size_t)v.item_unit[item] * C::N_REAL * PC_KA;
-            for (int n = tid; n < C::NPAD; n += 128) rowmax_s[n] = 0u;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // pass 1: row maxima (the bit pattern of |w| orders like the value); a row whose
-            // constant is not finite (alpha = 0 -> log 0) is marked dead with 0xffffffff
-            for (int task = tid; task < C::N_REAL * 5; task += 128) {
-                const int n = task / 5, c = task - n * 5;
-                const float4 *src = reinterpret_cast<const float4 *>(wu + (size_t)n * PC_KA);
-                float m = 0.f;
-                bool dead = false;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 q0 = __ldg(src + (c + 5 * half) * 2), q1 = __ldg(src + (c + 5 * half) * 2 + 1);
-                    float vals[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float a = fabsf(vals[e]);
-                        if (a <= 3.0e38f) m = fmaxf(m, a);
+    const uint8_t *x16 = reinterpret_cast<const uint8_t *>(X) + pc_x16_offset(v.total_frames);
+    const uint8_t *w16 = reinterpret_cast<const uint8_t *>(W) + pc_w16_offset(n_gauss);
+    const float *wscale = W + (size_t)n_gauss * PC_KA;
+    const bool scaled_rows = reinterpret_cast<const int *>(wscale + n_gauss)[0] != 0;
+
+    uint32_t n_a = 0, n_b = 0, n_pair = 0;  // running counters: frame tiles, B stages, (tile, position) pairs
+    for (int item = blockIdx.x; item < v.n_sitems; item += gridDim.x) {
+        const int u = v.sitem_utt[item];
+        const int64_t f0 = v.frame_off[u];
+        const int T = (int)(v.frame_off[u + 1] - f0);
+        const int64_t p0 = v.pair_off[u];
+        const int L_ = (int)(v.pair_off[u + 1] - p0);
+        const int L = L_;
+        const int t_item = v.sitem_t0[item];
+        const int nt_item = v.sitem_nt[item];
+        for (int jg = 0; jg < nt_item; jg += C::G) {  // sub-groups of G tiles
+            const int nt_ = min(C::G, nt_item - jg);
+            const int nt = nt_;
+            const int t_first = t_item + jg * T_ROWS;
+            if (warp == C::W_PROD) {
+                // -------------------------------------------------------- TMA producer
+                // order = consumption order of the MMA warp: A_0, B_0, A_1 .. A_{nt-1}, B_1 .. B_{L-1}
+                for (int step = 0; step < nt + L; ++step) {
+                    const bool is_a = (step == 0) || (step >= 2 && step <= nt);
+                    if (is_a) {
+                        const int j = (step == 0) ? 0 : step - 1;
+                        const int slot = n_a % C::NA;
+                        const int t0 = t_first + j * T_ROWS;
+                        tc::mbar_wait(&bars->a_empty[slot], ((n_a / C::NA) & 1) ^ 1);
+                        if (lane == 0 && (dbg & 8)) {
+                            tc::mbar_arrive(&bars->a_full[slot]);
+                        } else if (lane == 0) {
+                            tc::mbar_expect_tx(&bars->a_full[slot], PC_XTILE_BYTES);
+                            tc::tma_load_1d(a_s + slot * 2 * T_PIECE,
+                                            x16 + (size_t)(v.xtile_off[u] + t0 / T_ROWS) * PC_XTILE_BYTES,
+                                            PC_XTILE_BYTES, &bars->a_full[slot]);
+                        }
+                        ++n_a;
+                    } else {
+                        const int p = (step == 1) ? 0 : step - nt;
+                        const int stage = n_b % C::NB;
+                        const int unit = v.labels[p0 + p];
+                        uint8_t *dst = b_s + stage * C::B_STAGE;
+                        tc::mbar_wait(&bars->b_empty[stage], ((n_b / C::NB) & 1) ^ 1);
+                        if (lane == 0 && (dbg & 4)) {
+                            tc::mbar_arrive(&bars->b_full[stage]);
+                        } else if (lane == 0) {
+                            tc::mbar_expect_tx(&bars->b_full[stage], C::B_STAGE);
+                            tc::tma_load_1d(dst, w16 + (size_t)unit * C::B_STAGE, C::B_STAGE, &bars->b_full[stage]);
+                        }
+                        ++n_b;
                     }
-                    if (c == 4 && half == 0 && !(fabsf(vals[7]) <= 3.0e38f)) dead = true;
+                    __syncwarp();
                 }
-                atomicMax(&rowmax_s[n], dead ? 0xffffffffu : __float_as_uint(m));
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            // pass 2: scale by 2^-e so that the row fits fp16, split into hi / lo, store chunks.
-            // Task (n, c) converts chunks c and c+5 of row n (the constant's two columns 39 / 79
-            // are both in task c = 4, so the residual of the first pair can be folded into the second).
-            for (int task = tid; task < C::NPAD * 5; task += 128) {
-                const int n = task / 5, c = task - n * 5;
-                uint32_t hi8[2][4], lo8[2][4];
+            } else if (warp == C::W_MMA) {
+                // -------------------------------------------------------- MMA issuer
+                // loop bounds and ring counters go through redux.sync so that the compiler can keep
+                // them (and the UMMA descriptors derived from them) in uniform registers
+                constexpr uint32_t idesc = tc::umma_idesc_f16(T_ROWS, C::NPAD, 0, 0);
+                const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s);
+                const int L = __reduce_max_sync(0xffffffffu, L_);
+                const int nt = __reduce_max_sync(0xffffffffu, nt_);
+                const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, tmem_base_);
+                n_a = __reduce_max_sync(0xffffffffu, n_a);
+                n_b = __reduce_max_sync(0xffffffffu, n_b);
+                n_pair = __reduce_max_sync(0xffffffffu, n_pair);
+                const uint32_t na0 = n_a;
+                for (int p = 0; p < L; ++p, ++n_b) {
+                    const int stage = n_b % C::NB;
+                    tc::mbar_wait(&bars->b_full[stage], (n_b / C::NB) & 1);
+                    for (int j = 0; j < nt; ++j, ++n_pair) {
+                        const uint32_t na = na0 + j;
+                        const int slot = na % C::NA, tb = n_pair % C::TM_BUFS;
+                        const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n_pair < 1000;
+                        if (rec) g_pc_dbg[n_pair * 8 + 0] = clock64();
+                        if (p == 0) tc::mbar_wait(&bars->a_full[slot], (na / C::NA) & 1);
+                        if (rec) g_pc_dbg[n_pair * 8 + 1] = clock64();
+                        tc::mbar_wait(&bars->tm_empty[tb], ((n_pair / C::TM_BUFS) & 1) ^ 1);
+                        if (rec) g_pc_dbg[n_pair * 8 + 2] = clock64();
+                        tc::tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t d = tmem_base + tb * C::TM_STRIDE;
+                            const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
+                            const uint32_t bh = b_base + stage * C::B_STAGE, bl = bh + PC_WGROUP_BYTES / 2;
+                            uint32_t accum = 0;
 #pragma unroll
-                for (int half = 0; half < 2; ++half)
+                            for (int q = 0; q < 3; ++q) {
+                                const uint32_t ap = (q == 2) ? al : ah;
+                                const uint32_t bp = (q == 1) ? bl : bh;
+                                if (dbg & 2) break;
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) hi8[half][e2] = lo8[half][e2] = 0u;
-                const uint32_t mbits = (n < C::N_REAL) ? rowmax_s[n] : 0xffffffffu;
-                if (mbits != 0xffffffffu) {
-                    const float mx = __uint_as_float(mbits);
-                    int e = 0;
-                    if (mx > 16384.f) e = (int)((mbits >> 23) & 0xff) - 127 - 13;
-                    const float inv = __uint_as_float((uint32_t)(127 - e) << 23);
-                    const float4 *src = reinterpret_cast<const float4 *>(wu + (size_t)n * PC_KA);
-                    float kres = 0.f;  // what the first (hi, lo) pair of the constant leaves over
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float4 q0 = __ldg(src + (c + 5 * half) * 2), q1 = __ldg(src + (c + 5 * half) * 2 + 1);
-                        float vals[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                        for (int e2 = 0; e2 < 8; ++e2) vals[e2] *= inv;
-                        if (c == 4) {
-                            if (half == 0) {
-                                const __half kh = __float2half_rn(vals[7]);
-                                const float r1 = vals[7] - __half2float(kh);
-                                kres = r1 - __half2float(__float2half_rn(r1));
-                            } else {
-                                vals[7] += kres;
+                                for (int k = 0; k < T_KCH / 2; ++k) {
+                                    const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
+                                    const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
+                                    tc::mma_f16_ss(d, ad, bd, idesc, accum);
+                                    accum = 1;
+                                }
                             }
+                            tc::tc_commit(&bars->tm_full[tb]);
+                            if (p == L - 1) tc::tc_commit(&bars->a_empty[slot]);
+                            if (j == nt - 1) tc::tc_commit(&bars->b_empty[stage]);
                         }
-#pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2)
-                            tc::split2(vals[2 * e2], vals[2 * e2 + 1], hi8[half][e2], lo8[half][e2]);
+                        if (rec) g_pc_dbg[n_pair * 8 + 3] = clock64();
+                        __syncwarp();
                     }
                 }
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int chunk = c + 5 * half;
-                    uint4 *dh = reinterpret_cast<uint4 *>(b_s + chunk * C::NPAD * 16 + n * 16);
-                    uint4 *dl = reinterpret_cast<uint4 *>(b_s + C::B_PIECE + chunk * C::NPAD * 16 + n * 16);
-                    *dh = make_uint4(hi8[half][0], hi8[half][1], hi8[half][2], hi8[half][3]);
-                    *dl = make_uint4(lo8[half][0], lo8[half][1], lo8[half][2], lo8[half][3]);
-                }
-            }
-            for (int n = tid; n < C::NPAD; n += 128) {
-                const uint32_t mbits = (n < C::N_REAL) ? rowmax_s[n] : 0xffffffffu;
-                float sc = 1.f, bias = 0.f;
-                if (mbits == 0xffffffffu) {
-                    bias = PC_NEG_INF;  // dead row: weights are zero, score = log 0
-                } else if (__uint_as_float(mbits) > 16384.f) {
-                    const int e = (int)((mbits >> 23) & 0xff) - 127 - 13;
-                    sc = __uint_as_float((uint32_t)(127 + e) << 23);
-                }
-                scale_s[n] = sc;
-                bias_s[n] = bias;
-            }
-            tc::fence_proxy_async();
-        }
-        __syncthreads();
-
-        if (warp == 8) {
-            // ------------------------------------------------------------ TMA producer
-            for (int i = 0; i < n_tiles; ++i, ++n_raw) {
-                const int s = n_raw % RAW_STAGES;
-                tc::mbar_wait(&bars->raw_empty[s], ((n_raw / RAW_STAGES) & 1) ^ 1);
-                if (lane == 0) {
-                    const int64_t tile = lo + i;
-                    const uint32_t bytes = (uint32_t)v.tile_rows[tile] * PC_XS * 4;
-                    tc::mbar_expect_tx(&bars->raw_full[s], bytes);
-                    tc::tma_load_1d(raw_s + s * RAW_BYTES, X + (size_t)v.tile_xrow[tile] * PC_XS, bytes,
-                                    &bars->raw_full[s]);
-                }
-                __syncwarp();
-            }
-        } else if (warp >= 4 && warp < 8) {
-            // ------------------------------------------------------------ converters
-            const int r = threadIdx.x - 128;  // row of the tile
-            for (int i = 0; i < n_tiles; ++i, ++n_raw, ++n_a) {
-                const int rs = n_raw % RAW_STAGES, as = n_a % A_STAGES;
-                const int rows = v.tile_rows[lo + i];
-                tc::mbar_wait(&bars->raw_full[rs], (n_raw / RAW_STAGES) & 1);
-                float x[PC_XS];
-                if (r < rows) {
-                    const float4 *src = reinterpret_cast<const float4 *>(raw_s + rs * RAW_BYTES + r * PC_XS * 4);
-#pragma unroll
-                    for (int q = 0; q < PC_XS / 4; ++q) {
-                        float4 t4 = src[q];
-                        x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < PC_XS; ++q) x[q] = 0.f;
-                }
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars->raw_empty[rs]);
-                tc::mbar_wait(&bars->a_empty[as], ((n_a / A_STAGES) & 1) ^ 1);
-                uint8_t *ah = a_s + as * 2 * A_PIECE, *al = ah + A_PIECE;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    uint32_t h[4], l[4], h2[4], l2[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p = x[8 * c + 2 * e], q = x[8 * c + 2 * e + 1];
-                        tc::split2(p, q, h[e], l[e]);
-                        tc::split2(p * p, q * q, h2[e], l2[e]);
-                    }
-                    *reinterpret_cast<uint4 *>(ah + c * ROWS * 16 + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(al + c * ROWS * 16 + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<uint4 *>(ah + (c + 5) * ROWS * 16 + r * 16) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
-                    *reinterpret_cast<uint4 *>(al + (c + 5) * ROWS * 16 + r * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
-                }
-                tc::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars->a_full[as]);
-            }
-        } else if (warp == 9) {
-            // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = tc::umma_idesc_f16(ROWS, C::NPAD, 0, 0);
-            const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s);
-            for (int i = 0; i < n_tiles; ++i, ++n_a, ++n_tm) {
-                const int as = n_a % A_STAGES, tb = n_tm % C::TM_BUFS;
-                tc::mbar_wait(&bars->a_full[as], (n_a / A_STAGES) & 1);
-                tc::mbar_wait(&bars->tm_empty[tb], ((n_tm / C::TM_BUFS) & 1) ^ 1);
-                tc::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t d = tmem_base + tb * C::TM_STRIDE;
-                    const uint32_t ah = a_base + as * 2 * A_PIECE, al = ah + A_PIECE;
-                    const uint32_t bh = b_base, bl = b_base + C::B_PIECE;
-                    uint32_t accum = 0;
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const uint32_t ap = (p == 2) ? al : ah;
-                        const uint32_t bp = (p == 1) ? bl : bh;
-#pragma unroll
-                        for (int k = 0; k < KCH / 2; ++k) {
-                            const uint64_t ad = tc::umma_desc(ap + 2 * k * ROWS * 16, ROWS * 16, 128);
-                            const uint64_t bd = tc::umma_desc(bp + 2 * k * C::NPAD * 16, C::NPAD * 16, 128);
-                            tc::mma_f16_ss(d, ad, bd, idesc, accum);
-                            accum = 1;
+                n_a = na0 + nt;
+            } else {
+                // -------------------------------------------------------- epilogue warpgroups
+                const int grp = warp >> 2;
+                const int r = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane
+                const int tp = pc_tpad(T);
+                for (int p = 0; p < L; ++p) {
+                    const float *scale_g = wscale + (size_t)v.labels[p0 + p] * C::N_REAL;
+                    for (int j = 0; j < nt; ++j, ++n_pair) {
+                        if ((int)(n_pair % C::EPI_GROUPS) != grp) continue;
+                        const int tb = n_pair % C::TM_BUFS;
+                        const int t0 = t_first + j * T_ROWS;
+                        const int rows = min(T_ROWS, T - t0);
+                        float *out = b + v.emis_off[u] + (size_t)(PC_EMIT * p) * tp + t0 + r;
+                        const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && n_pair < 1000;
+                        if (rec) g_pc_dbg[n_pair * 8 + 4] = clock64();
+                        tc::mbar_wait(&bars->tm_full[tb], (n_pair / C::TM_BUFS) & 1);
+                        if (rec) g_pc_dbg[n_pair * 8 + 5] = clock64();
+                        tc::tc_fence_after();
+                        const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
+                        float res[PC_EMIT] = {0.f, 0.f, 0.f};
+                        if (dbg & 16) {
+                            tc::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
+                            continue;
                         }
-                    }
-                    tc::tc_commit(&bars->a_empty[as]);
-                    tc::tc_commit(&bars->tm_full[tb]);
-                }
-                __syncwarp();
-            }
-        } else {
-            // ------------------------------------------------------------ epilogue (warps 0-3)
-            const int r = threadIdx.x;  // row of the tile == TMEM lane
-            for (int i = 0; i < n_tiles; ++i, ++n_tm) {
-                const int tb = n_tm % C::TM_BUFS;
-                const int64_t tile = lo + i;
-                const int rows = v.tile_rows[tile];
-                const int tp = v.tile_tp[tile];
-                float *out = b + v.tile_boff[tile] + r;
-                tc::mbar_wait(&bars->tm_full[tb], (n_tm / C::TM_BUFS) & 1);
-                tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + ((uint32_t)(warp * 32) << 16);
-                float res[PC_EMIT];
-                constexpr int LD_PER_STATE = MIX >= 16 ? MIX / 16 : 0;
-                float small[MIX >= 16 ? 1 : C::NPAD];
-                if constexpr (MIX < 16) {
+                        if (dbg & 1) {
+                        } else if (scaled_rows)
+                            epilogue_pair<MIX, true>(taddr, scale_g, res);
+                        else
+                            epilogue_pair<MIX, false>(taddr, scale_g, res);
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
+                        if (r < rows) {
 #pragma unroll
-                    for (int j = 0; j < C::NPAD / 16; ++j) {
-                        float t16[16];
-                        tc::tmem_ld16(taddr + j * 16, t16);
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) small[j * 16 + e] = t16[e];
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < PC_EMIT; ++s) {
-                    float mx = PC_NEG_INF, sum = 0.f;
-                    float vbuf[MIX];
-                    if constexpr (MIX >= 16) {
-#pragma unroll
-                        for (int j = 0; j < LD_PER_STATE; ++j) {
-                            float t16[16];
-                            tc::tmem_ld16(taddr + s * MIX + j * 16, t16);
-                            tc::tmem_ld_wait();
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) vbuf[j * 16 + e] = t16[e];
+                            for (int s = 0; s < PC_EMIT; ++s) out[(size_t)s * tp] = res[s];
                         }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < MIX; ++e) vbuf[e] = small[s * MIX + e];
+                        if (rec) g_pc_dbg[n_pair * 8 + 6] = clock64();
                     }
-#pragma unroll
-                    for (int e = 0; e < MIX; ++e) {
-                        vbuf[e] = fmaf(vbuf[e], scale_s[s * MIX + e], bias_s[s * MIX + e]);
-                        mx = fmaxf(mx, vbuf[e]);
-                    }
-                    if (mx == PC_NEG_INF) {
-                        res[s] = PC_NEG_INF;
-                    } else {
-                        const float ms = mx * LOG2E;
-#pragma unroll
-                        for (int e = 0; e < MIX; ++e) sum += exp2f(fmaf(vbuf[e], LOG2E, -ms));
-                        res[s] = mx + LN2 * log2f(sum);
-                    }
-                }
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
-                if (r < rows) {
-#pragma unroll
-                    for (int s = 0; s < PC_EMIT; ++s) out[(size_t)s * tp] = res[s];
                 }
             }
         }
-        __syncthreads();  // the item's MMAs are complete (epilogue consumed the last tile): B may change
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tmem_base, C::TM_COLS);
+    if (warp == C::W_MMA) tc::tmem_dealloc(tmem_base, C::TM_COLS);
 }
 
 template <int MIX>
@@ -336,8 +310,8 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
                cudaStream_t st) {
     auto kern = score_tc_kernel<MIX>;
     PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MIX>::SMEM));
-    int grid = v.n_items < h->sm_count ? v.n_items : h->sm_count;
-    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, b);
+    int grid = v.n_sitems < h->sm_count ? v.n_sitems : h->sm_count;
+    kern<<<grid, Cfg<MIX>::NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, h->fb_variant);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -345,11 +319,15 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
 
 }  // namespace
 
+extern "C" int pc_debug_read(long long *host_out, int n) {
+    return cudaMemcpyFromSymbol(host_out, g_pc_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+
 bool score_tc_supported(int mix) { return mix == 4 || mix == 8 || mix == 16 || mix == 32 || mix == 64; }
 
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                     float *b, cudaStream_t st) {
-    if (v.n_items == 0) return PC_OK;
+    if (v.n_sitems == 0) return PC_OK;
     switch (mix) {
         case 4: return launch_mix<4>(h, v, X, W, b, st);
         case 8: return launch_mix<8>(h, v, X, W, b, st);

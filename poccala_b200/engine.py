@@ -66,25 +66,43 @@ class Engine:
         return Corpus(self, labels, n_frames, n_units)
 
     # ------------------------------------------------------------------ kernels
-    def pack_gmm(self, mean, var, alpha, shift=None, inv_scale=None, out=None):
-        """mean/var [G,D] fp64 cuda, alpha [G] -> W [G,80] fp32 (pc_pack_gmm)."""
+    def pack_gmm(self, mean, var, alpha, shift=None, inv_scale=None, out=None, mix=0):
+        """mean/var [G,D] fp64 cuda, alpha [G] -> W buffer (pc_gmm_bytes(G) bytes: fp32 rows, scale,
+        flags, per-unit fp16 tensor-core images; pc_pack_gmm).  mix = components per state of an
+        acoustic model laid out [unit][3][mix]; 0 for a flat list of Gaussians."""
         G, D = mean.shape
-        W = out if out is not None else self.empty((G, KA), torch.float32)
-        nat.call("pc_pack_gmm", self.h, _p(mean), _p(var), _p(alpha), _p(shift), _p(inv_scale), G, D, _p(W),
-                 _stream())
+        W = out if out is not None else self.empty((int(nat.lib().pc_gmm_bytes(G)),), torch.uint8)
+        nat.call("pc_pack_gmm", self.h, _p(mean), _p(var), _p(alpha), _p(shift), _p(inv_scale), G, D, int(mix),
+                 _p(W), _stream())
         return W
 
-    def prepare_frames(self, x, shift=None, inv_scale=None, out=None):
-        """x [F,D] fp32/fp64 cuda -> X [F,40] fp32 standardised (pc_prepare_frames_*)."""
+    def prepare_rows(self, x, shift=None, inv_scale=None):
+        """x [F,D] fp32/fp64 cuda -> fp32 rows [F,40] (dense scoring sweep; pc_prepare_rows_*)."""
         F, D = x.shape
         if D > nat.DIM_MAX:
             raise ValueError("feature dimension %d exceeds %d" % (D, nat.DIM_MAX))
-        x = x.contiguous()
-        X = out if out is not None else self.empty((F, XS), torch.float32)
-        fn = "pc_prepare_frames_f64" if x.dtype == torch.float64 else "pc_prepare_frames_f32"
         if x.dtype not in (torch.float32, torch.float64):
             raise TypeError("frames must be float32 or float64")
+        x = x.contiguous()
+        X = self.empty((F, XS), torch.float32)
+        fn = "pc_prepare_rows_f64" if x.dtype == torch.float64 else "pc_prepare_rows_f32"
         nat.call(fn, self.h, _p(x), F, D, _p(shift), _p(inv_scale), _p(X), _stream())
+        return X
+
+    def prepare_frames(self, corpus, x, shift=None, inv_scale=None, out=None):
+        """x [F,D] fp32/fp64 cuda (utterances concatenated in corpus order) -> the corpus' X buffer
+        (standardised fp32 rows + one fp16 tensor-core image per 128-frame tile; pc_prepare_frames_*)."""
+        F, D = x.shape
+        if D > nat.DIM_MAX:
+            raise ValueError("feature dimension %d exceeds %d" % (D, nat.DIM_MAX))
+        if F != corpus.total_frames:
+            raise ValueError("expected %d frames, got %d" % (corpus.total_frames, F))
+        if x.dtype not in (torch.float32, torch.float64):
+            raise TypeError("frames must be float32 or float64")
+        x = x.contiguous()
+        X = out if out is not None else self.empty((int(nat.lib().pc_corpus_frames_bytes(corpus.c)),), torch.uint8)
+        fn = "pc_prepare_frames_f64" if x.dtype == torch.float64 else "pc_prepare_frames_f32"
+        nat.call(fn, self.h, corpus.c, _p(x), D, _p(shift), _p(inv_scale), _p(X), _stream())
         return X
 
     def score_dense(self, X, W, n_states, mix, out=None):
@@ -159,11 +177,11 @@ class Model:
         self.transmat = torch.as_tensor(np.asarray(transmat), dtype=torch.float64).to(dev).contiguous()
         self.n_units, _, self.mix, self.dim = self.mean.shape
         self.n_gauss = self.n_units * EMIT * self.mix
-        self.W = engine.empty((self.n_gauss, KA), torch.float32)
+        self.W = engine.empty((int(nat.lib().pc_gmm_bytes(self.n_gauss)),), torch.uint8)
 
     def pack(self, shift=None, inv_scale=None):
         self.engine.pack_gmm(self.mean.view(self.n_gauss, self.dim), self.var.view(self.n_gauss, self.dim),
-                             self.alpha.view(self.n_gauss), shift, inv_scale, out=self.W)
+                             self.alpha.view(self.n_gauss), shift, inv_scale, out=self.W, mix=self.mix)
         return self.W
 
     def log_bands(self):
@@ -208,7 +226,7 @@ class EStep:
             sd = xd.std(dim=0, unbiased=False).clamp_min(1e-12)
             self.shift = mu.contiguous()
             self.inv_scale = (1.0 / sd).contiguous()
-        self.corpus.X = self.engine.prepare_frames(x, self.shift, self.inv_scale, out=self.corpus.X)
+        self.corpus.X = self.engine.prepare_frames(self.corpus, x, self.shift, self.inv_scale, out=self.corpus.X)
         return self.corpus.X
 
     # kernels ------------------------------------------------------------------------------

@@ -353,7 +353,7 @@ def test_dense_scoring_matches_oracle(eng):
     x = rng.normal(size=(F, 39))
     dev = eng.device
     W = eng.pack_gmm(torch.as_tensor(mean).to(dev), torch.as_tensor(var).to(dev), torch.as_tensor(alpha).to(dev))
-    X = eng.prepare_frames(torch.as_tensor(x).to(dev))
+    X = eng.prepare_rows(torch.as_tensor(x).to(dev))
     out = eng.score_dense(X, W, n_states, mix).cpu().numpy()
     d = x[:, None, :] - mean[None]
     c = np.log(alpha) - 39 / 2 * np.log(2 * np.pi) - 0.5 * var.sum(-1) - 0.5 * (d * d / var).sum(-1)
@@ -366,7 +366,7 @@ def test_error_behaviour(eng):
     from poccala_b200.engine import Corpus
 
     with pytest.raises(ValueError):
-        eng.prepare_frames(torch.zeros((4, 40), device=eng.device))  # DataDimensionError analogue
+        eng.prepare_rows(torch.zeros((4, 40), device=eng.device))  # DataDimensionError analogue
     with pytest.raises(nat.NativeError):
         Corpus(eng, [np.array([0, 7])], np.array([10], dtype=np.int32), 3)  # label outside the unit set
     with pytest.raises(nat.NativeError):
