@@ -23,7 +23,7 @@
  *          col 39 = 1.0) followed by one fp16 (hi, lo) tensor-core operand image per 128-frame tile
  *   W      pc_gmm_bytes(G) bytes: float [G][PC_KA] packed Gaussians (mu/var (39), k_hi |
  *          -1/(2 var) (39), k_lo), float scale[G], int32 flags[G], one fp16 operand image per unit
- *   b,lgam float per utterance [3*L][Tpad] emitting-state rows, time contiguous (Tpad = T up to 4)
+ *   b,lgam float per utterance [T][SP] time-major emissions, s = 3*position + state, SP = 3L up to 8
  *   acc    double[n_gauss][PC_KA]          sum gamma*x (39), sum gamma | sum gamma*x^2 (39), sum gamma
  *   Gaussian index g = (unit*3 + state)*mix + m.
  */

@@ -46,7 +46,7 @@ accumulate_simt_kernel(CorpusView v, const float *__restrict__ X, const float *_
         const int T = (int)(v.frame_off[u + 1] - v.frame_off[u]);
         const int t0 = v.tile_t0[tile];
         const int rows = min(PC_TILE_ROWS, T - t0);
-        const int tp = pc_tpad(T);
+        const int sp = pc_spad((int)(v.pair_off[u + 1] - v.pair_off[u]));
         __syncthreads();  // previous tile fully consumed
         for (int i = threadIdx.x; i < rows * PC_XS; i += blockDim.x) {
             int f = i / PC_XS, d = i - f * PC_XS;
@@ -56,7 +56,7 @@ accumulate_simt_kernel(CorpusView v, const float *__restrict__ X, const float *_
         }
         for (int i = threadIdx.x; i < PC_EMIT * rows; i += blockDim.x) {
             int rr = i / rows, f = i - rr * rows;
-            size_t o = v.emis_off[u] + (size_t)(PC_EMIT * pos + rr) * tp + t0 + f;
+            size_t o = v.emis_off[u] + (size_t)(t0 + f) * sp + PC_EMIT * pos + rr;
             float lg = __ldg(lgam + o), bb = __ldg(b + o);
             d_s[rr][f] = (lg == PC_NEG_INF) ? PC_NEG_INF : lg - bb;
         }

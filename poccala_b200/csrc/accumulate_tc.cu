@@ -263,12 +263,12 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                 // d = (lgam - b) * log2(e) + 15 for the unit's three states; -inf kills the row
                 float dl[PC_EMIT];
                 {
-                    const size_t o = (size_t)v.tile_boff[tile] + r;
+                    const size_t o = (size_t)v.tile_boff[tile] + (size_t)r * tp;
 #pragma unroll
                     for (int s = 0; s < PC_EMIT; ++s) {
                         float d = PC_NEG_INF;
                         if (r < rows) {
-                            const float lg = __ldg(lgam + o + (size_t)s * tp), bb = __ldg(b + o + (size_t)s * tp);
+                            const float lg = __ldg(lgam + o + s), bb = __ldg(b + o + s);
                             d = (lg == PC_NEG_INF) ? PC_NEG_INF : fmaf(lg - bb, LOG2E, P_SHIFT);
                         }
                         dl[s] = d;

@@ -95,7 +95,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
         PC_REQUIRE(n_labels[u] >= 1, "pc_corpus_create: utterance %d has %d labels", u, n_labels[u]);
         frame_off[u + 1] = frame_off[u] + n_frames[u];
         pair_off[u + 1] = pair_off[u] + n_labels[u];
-        emis_off[u + 1] = emis_off[u] + (int64_t)PC_EMIT * n_labels[u] * pc_tpad(n_frames[u]);
+        emis_off[u + 1] = emis_off[u] + (int64_t)n_frames[u] * pc_spad(n_labels[u]);
         state_off[u + 1] = state_off[u] + PC_EMIT * n_labels[u] + 2;
         max_frames = std::max(max_frames, n_frames[u]);
         max_labels = std::max(max_labels, n_labels[u]);
@@ -144,7 +144,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
             const int64_t p = sorted_pair[i];
             const int u = pair_utt[p];
             const int T = n_frames[u];
-            const int tp = pc_tpad(T);
+            const int tp = pc_spad(n_labels[u]);
             const int64_t pos = p - pair_off[u];
             for (int t0 = 0; t0 < T; t0 += PC_TILE_ROWS) {
                 tile_pair.push_back(p);
@@ -153,7 +153,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
                 tile_tp.push_back(tp);
                 tile_xrow.push_back(frame_off[u] + t0);
                 tile_xblk.push_back(xtile_off[u] + t0 / PC_TILE_ROWS);
-                tile_boff.push_back(emis_off[u] + PC_EMIT * pos * tp + t0);
+                tile_boff.push_back(emis_off[u] + (int64_t)t0 * tp + PC_EMIT * pos);
             }
         }
         unit_tile_off[k + 1] = (int64_t)tile_pair.size();
@@ -225,7 +225,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_tboff = add(tile_boff.data(), (size_t)n_tiles * 8);
     size_t o_ilo = add(item_tile_lo.data(), item_tile_lo.size() * 8);
     size_t o_iunit = add(item_unit.data(), (size_t)n_items * 4);
-    size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 4);
+    size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 16);  // float4 per frame (K2)
     size_t o_sutt = add(sitem_utt.data(), (size_t)n_sitems * 4);
     size_t o_st0 = add(sitem_t0.data(), (size_t)n_sitems * 4);
     size_t o_snt = add(sitem_nt.data(), (size_t)n_sitems * 4);

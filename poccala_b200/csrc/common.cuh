@@ -26,7 +26,7 @@ struct CorpusView {
     int32_t max_frames;
     int32_t max_labels;
     const int64_t *frame_off;   // [n_utt+1] first row of the utterance in X
-    const int64_t *emis_off;    // [n_utt+1] first float of the utterance's [3L][Tpad] block
+    const int64_t *emis_off;    // [n_utt+1] first float of the utterance's [T][SP] emission block
     const int64_t *pair_off;    // [n_utt+1] first (utt, position) pair = first label
     const int64_t *state_off;   // [n_utt+1] first composite state (3L+2 per utterance)
     const int32_t *labels;      // [n_pairs] unit id, utterance-major
@@ -38,12 +38,12 @@ struct CorpusView {
     const int64_t *tile_pair;    // [n_tiles] utterance-major pair index of the tile
     const int32_t *tile_t0;      // [n_tiles] first frame (within the utterance) of the tile
     const int32_t *tile_rows;    // [n_tiles] frames in the tile (<= 128)
-    const int32_t *tile_tp;      // [n_tiles] row stride (Tpad) of the utterance's b / lgam block
+    const int32_t *tile_tp;      // [n_tiles] frame stride SP (floats) of the utterance's b / lgam block
     const int64_t *tile_xrow;    // [n_tiles] first row of the tile in X
-    const int64_t *tile_boff;    // [n_tiles] float offset of (state 0 of the pair, frame t0) in b / lgam
+    const int64_t *tile_boff;    // [n_tiles] float offset of (frame t0, state 0 of the pair) in b / lgam
     const int64_t *item_tile_lo;  // [n_items+1] tile range of each work item (one unit per item)
     const int32_t *item_unit;     // [n_items]
-    float *scratch0;              // [total_frames] entry-state beta_hat (K2 scratch)
+    float *scratch0;              // [total_frames] float4 per frame (K2 scratch: g, shift_b, entry beta)
     // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
     int64_t total_frames;
     int32_t n_sitems;
@@ -58,7 +58,8 @@ struct CorpusView {
     const int64_t *tile_xblk;     // [n_tiles] image index of each unit-major work tile
 };
 
-__host__ __device__ inline int pc_tpad(int t) { return (t + 3) & ~3; }
+// emissions are time-major: b[t][s], s = 3*position + state, frame stride SP = 3L rounded up to 8
+__host__ __device__ inline int pc_spad(int n_labels) { return (PC_EMIT * n_labels + 7) & ~7; }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

@@ -76,14 +76,14 @@ score_simt_kernel(CorpusView v, const float *__restrict__ X, const float *__rest
         if (t >= T) continue;
         float xa[PC_KA];
         load_aug_row(X + (size_t)(v.frame_off[u] + t) * PC_XS, xa);
-        const int tp = pc_tpad(T);
-        float *out = b + v.emis_off[u] + (size_t)(PC_EMIT * pos) * tp + t;
+        const int sp = pc_spad((int)(v.pair_off[u + 1] - v.pair_off[u]));
+        float *out = b + v.emis_off[u] + (size_t)t * sp + PC_EMIT * pos;
         for (int r = 0; r < PC_EMIT; ++r) {
             Lse l;
             l.init();
             const float *wr = w_s + (size_t)r * mix * PC_KA;
             for (int m = 0; m < mix; ++m) l.add(dot_aug(xa, wr + (size_t)m * PC_KA));
-            out[(size_t)r * tp] = l.value();
+            out[r] = l.value();
         }
     }
 }

@@ -260,7 +260,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                 // -------------------------------------------------------- epilogue warpgroups
                 const int grp = warp >> 2;
                 const int r = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane
-                const int tp = pc_tpad(T);
+                const int sp = pc_spad(L);
                 for (int p = 0; p < L; ++p) {
                     const float *scale_g = wscale + (size_t)v.labels[p0 + p] * C::N_REAL;
                     for (int j = 0; j < nt; ++j, ++n_pair) {
@@ -268,7 +268,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         const int tb = n_pair % C::TM_BUFS;
                         const int t0 = t_first + j * T_ROWS;
                         const int rows = min(T_ROWS, T - t0);
-                        float *out = b + v.emis_off[u] + (size_t)(PC_EMIT * p) * tp + t0 + r;
+                        float *out = b + v.emis_off[u] + (size_t)(t0 + r) * sp + PC_EMIT * p;
                         const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && n_pair < 1000;
                         if (rec) g_pc_dbg[n_pair * 8 + 4] = clock64();
                         tc::mbar_wait(&bars->tm_full[tb], (n_pair / C::TM_BUFS) & 1);
@@ -292,7 +292,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
                         if (r < rows) {
 #pragma unroll
-                            for (int s = 0; s < PC_EMIT; ++s) out[(size_t)s * tp] = res[s];
+                            for (int s = 0; s < PC_EMIT; ++s) out[s] = res[s];
                         }
                         if (rec) g_pc_dbg[n_pair * 8 + 6] = clock64();
                     }

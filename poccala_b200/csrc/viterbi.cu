@@ -31,7 +31,7 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
     const int64_t p0 = v.pair_off[u];
     const int L = (int)(v.pair_off[u + 1] - p0);
     const int NE = PC_EMIT * L;
-    const int tp = pc_tpad(T);
+    const int sp = pc_spad(L);
     const E *bu = b + v.emis_off[u];
     const double NINF = -INFINITY;
 
@@ -51,7 +51,7 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
             const int pp = (s - 1) / PC_EMIT, r = (s - 1) - pp * PC_EMIT;
             const int unit = v.labels[p0 + pp];
             kind[q] = 1;
-            row[q] = (int64_t)(s - 1) * tp;
+            row[q] = s - 1;
             ls[q] = log_self[unit * PC_STATES + 1 + r];
             ln[q] = log_next[unit * PC_STATES + 1 + r];  // into the exit state for s == NE: unused
         } else {
@@ -61,7 +61,7 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
         }
         double lpi = state_logpi ? ((s <= NE + 1) ? state_logpi[v.state_off[u] + s] : NINF)
                                  : utt_logpi[u];
-        double e0 = kind[q] == 1 ? (double)bu[row[q]] : (kind[q] == 0 ? 0.0 : NINF);
+        double e0 = kind[q] == 1 ? (double)bu[row[q]] : (kind[q] == 0 ? 0.0 : NINF);  // frame 0
         p[q] = (kind[q] == 2) ? NINF : lpi + e0;
     }
     uint32_t bits[SPL];
@@ -77,7 +77,7 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
             const double stay = p[q] + ls[q];
             const bool take = move >= stay;  // tie -> lower index (j-1)
             const double best = take ? move : stay;
-            const double e = kind[q] == 1 ? (double)bu[row[q] + t] : (kind[q] == 0 ? 0.0 : NINF);
+            const double e = kind[q] == 1 ? (double)bu[(int64_t)t * sp + row[q]] : (kind[q] == 0 ? 0.0 : NINF);
             np_[q] = (kind[q] == 2) ? NINF : best + e;
             bits[q] |= (take ? 1u : 0u) << (t & 31);
         }

@@ -158,10 +158,10 @@ class Corpus:
             pass
 
     def emission_view(self, buf, u):
-        """[3L, T] view of utterance u inside a b / lgam buffer."""
+        """[3L, T] view of utterance u inside a b / lgam buffer (stored time-major [T][SP])."""
         T, L = int(self.n_frames[u]), int(self.n_labels[u])
-        tp = (T + 3) & ~3
-        return buf[self.emis_off[u]:self.emis_off[u + 1]].view(EMIT * L, tp)[:, :T]
+        sp = (EMIT * L + 7) & ~7
+        return buf[self.emis_off[u]:self.emis_off[u + 1]].view(T, sp)[:, :EMIT * L].t()
 
 
 class Model:

@@ -329,9 +329,9 @@ def test_viterbi_ties_golden(eng):
         N, T = B.shape
         L = (N - 2) // 3
         corpus = Corpus(eng, [np.zeros(L, dtype=np.int32)], np.array([T], dtype=np.int32), 1)
-        tp = (T + 3) & ~3
-        buf = np.zeros((3 * L, tp))
-        buf[:, :T] = B[1:-1]
+        sp = (3 * L + 7) & ~7
+        buf = np.zeros((T, sp))
+        buf[:, :3 * L] = B[1:-1].T
         b64 = torch.as_tensor(buf.reshape(-1)).to(eng.device)
         tm = np.zeros((1, 5, 5))
         tm[0, 0, 1] = 1.0
