@@ -183,12 +183,33 @@ int pc_viterbi(pc_handle h, pc_corpus c, const float *dev_b, const double *dev_b
 
 /* ---- K5: k-means initialisation ------------------------------------------------------------
  * ClusterInitialization.kmeans(algorithm=1) greedy passes (Clustering.py:894-940) with the
- * dimension-0 metric of cal_distance (:796-801, Q2).  One call runs the passes to convergence
- * for `n_problems` independent problems (one per HMM state).  See DESIGN.md §K5. */
-int pc_kmeans_run(pc_handle h, int32_t n_problems, const int64_t *dev_point_off,
-                  const double *dev_x0, int32_t k, const int32_t *dev_seed_points,
-                  int32_t *dev_owner, int32_t *dev_member_list, int32_t *dev_member_count,
-                  int32_t *dev_passes, int64_t max_passes, void *stream);
+ * dimension-0 metric of cal_distance (:796-801, Q2), run to convergence for `n_problems`
+ * independent problems (one per HMM state, AcousticModel.py:553-554) in one launch.
+ *   host_point_off [n_problems+1]  HOST array: rows of dev_x belonging to each problem
+ *   dev_x          double [total_points][dim]
+ *   dev_seed_points int32 [n_problems][k]: point index (within the problem) of each seed, drawn by
+ *                  the caller with Python's `random` exactly like Clustering.py:975-1020
+ *   dev_workspace  pc_kmeans_workspace_bytes(...) bytes of scratch
+ * Outputs: dev_owner int32 [total_points] (cluster owning each point, -1 = never claimed);
+ * dev_member_list int32 [total_points + n_problems*k]: problem p's region starts at
+ * host_point_off[p] + p*k and holds its clusters back to back, each in the reference's dict
+ * insertion order (seed first); dev_member_count int32 [n_problems][k]; dev_passes int32
+ * [n_problems]; dev_moves int64 [n_problems] (= number of random.random() key draws the reference
+ * makes, Clustering.py:932).  See DESIGN.md "K5". */
+int64_t pc_kmeans_workspace_bytes(int32_t n_problems, const int64_t *host_point_off, int32_t k);
+int pc_kmeans_run(pc_handle h, int32_t n_problems, const int64_t *host_point_off,
+                  const double *dev_x, int32_t dim, int32_t k, const int32_t *dev_seed_points,
+                  void *dev_workspace, int32_t *dev_owner, int32_t *dev_member_list,
+                  int32_t *dev_member_count, int32_t *dev_passes, int64_t *dev_moves,
+                  int64_t max_passes, void *stream);
+/* Cluster statistics the reference returns (Clustering.py:880-891 cal_center, :807-832
+ * cal_variance(algorithm='kmeans') with its 1e-4 floor, :947 alpha = len/n): sequential fp64 sums
+ * in insertion order.  dev_mean / dev_var double [n_problems][k][dim], dev_alpha [n_problems][k].
+ * dev_workspace is the buffer pc_kmeans_run used (it holds the problem table). */
+int pc_kmeans_finish(pc_handle h, int32_t n_problems, const int64_t *host_point_off,
+                     const double *dev_x, int32_t dim, int32_t k, const void *dev_workspace,
+                     const int32_t *dev_member_list, const int32_t *dev_member_count,
+                     double *dev_mean, double *dev_var, double *dev_alpha, void *stream);
 
 /* ---- host-buffer entry point (end-to-end) --------------------------------------------------
  * One full EM iteration the way AcousticModel.embedded_training runs it (AcousticModel.py:842-882)

@@ -1,0 +1,352 @@
+"""Device-backed mirror of the reference's StatisticalModel/Clustering.py surface for the E-step
+hot path: `Clustering.GMM` (scoring, Baum-Welch accumulators, re-estimation) and
+`Clustering.ClusterInitialization` (k-means initialisation).  Same class / method / property
+names and argument meaning as the reference (Clustering.py:36-767, 773-1044); every number is
+produced by the sm_100a kernels behind include/poccala_b200.h - there is no CPU path.
+
+Differences a maintainer should know:
+  * accumulators are kept in the linear domain (sum gamma, sum gamma x, sum gamma (x-mu)^2) and the
+    log-domain views the reference exposes (`acc`, `alpha_acc`, `mean_acc`) are derived on access;
+  * `covariance` is the reference's [M,D,D] stack of diagonal matrices; only the diagonal is used
+    (the reference extracts `.diagonal()` in util.gaussian_function, util.py:20-36);
+  * the stand-alone `em()` / SMEM split-merge trainer (Clustering.py:483-651,695-719) is outside
+    the hot path and raises NotImplementedError.
+"""
+from __future__ import annotations
+
+import random as _random
+
+import numpy as np
+import torch
+
+from . import engine as _eng
+from .runtime import NullLog, get_engine
+
+
+class DataDimensionError(Exception):
+    """Exceptions.DataDimensionError (Exceptions.py:76): raised by GMM.point on a wrong-length frame."""
+
+
+def _diag_stack(var):
+    var = np.asarray(var, dtype=np.float64)
+    M, D = var.shape
+    out = np.zeros((M, D, D))
+    idx = np.arange(D)
+    out[:, idx, idx] = var
+    return out
+
+
+class Clustering(object):
+    class LogInfoPrint(NullLog):
+        """Clustering.LogInfoPrint stand-in (console logger of the reference)."""
+
+    class GMM(object):
+        def __init__(self, log=None, dimension=1, mix_level=1, data=None, alpha=None, mean=None, variance=None,
+                     covariance=None, differentiation=True, gmm_id=0):
+            """Clustering.py:37-104 (same arguments and defaults)."""
+            self.log = log if log else Clustering.LogInfoPrint()
+            self.__dimension = dimension
+            self.__mix_level = mix_level
+            self.__data = np.array(data) if data else None
+            if mean is None:
+                mean = np.random.random((mix_level, dimension)) if differentiation else np.zeros((mix_level, dimension))
+            self.__mean = np.asarray(mean, dtype=np.float64)
+            if covariance is not None:
+                self.__covariance = np.asarray(covariance, dtype=np.float64)
+            elif variance is not None:
+                self.__covariance = _diag_stack(variance)
+            elif differentiation:
+                self.__covariance = _diag_stack(np.repeat(np.random.random((1, dimension)), mix_level, axis=0))
+            else:
+                self.__covariance = _diag_stack(np.ones((mix_level, dimension)))
+            self.__alpha = (np.ones((mix_level,)) / mix_level) if alpha is None else np.asarray(alpha, dtype=np.float64)
+            self.__bias = 100.
+            self.__gmm_id = gmm_id
+            self.__record = []
+            self._clear_acc()
+
+        # ---- parameters (Clustering.py:122-229) -------------------------------------------
+        @property
+        def mean(self):
+            return self.__mean
+
+        @mean.setter
+        def mean(self, value):
+            self.__mean = np.asarray(value, dtype=np.float64)
+
+        @property
+        def covariance(self):
+            return self.__covariance
+
+        @covariance.setter
+        def covariance(self, value):
+            self.__covariance = np.asarray(value, dtype=np.float64)
+
+        @property
+        def variance(self):
+            """[M,D] diagonal of `covariance` (what the scoring arithmetic uses)."""
+            return np.ascontiguousarray(np.diagonal(self.__covariance, axis1=1, axis2=2))
+
+        @property
+        def alpha(self):
+            return self.__alpha
+
+        @alpha.setter
+        def alpha(self, value):
+            self.__alpha = np.asarray(value, dtype=np.float64)
+
+        @property
+        def dimension(self):
+            return self.__dimension
+
+        @property
+        def mixture(self):
+            return self.__mix_level
+
+        @property
+        def data(self):
+            return self.__data
+
+        @property
+        def bias(self):
+            return self.__bias
+
+        @property
+        def gmm_id(self):
+            return self.__gmm_id
+
+        def add_data(self, data):
+            d = np.array(data)
+            self.__data = d if self.__data is None else np.append(self.__data, d, axis=0)
+
+        def clear_data(self):
+            self.__data = None
+
+        # ---- accumulators: log-domain views of the linear statistics (Clustering.py:98-101) ----
+        def _clear_acc(self):
+            M, D = self.__mix_level, self.__dimension
+            self._occ = np.zeros(M)
+            self._socc = 0.0
+            self._sx = np.zeros((M, D))
+            self._scc = np.zeros((M, D))  # sum gamma (x - mu_old)^2 (Q8)
+
+        def _add_linear(self, occ, socc, sx, sxx):
+            """Fold statistics of one accumulation call in: occ [M], socc scalar, sx / sxx [M,D]
+            (raw moments); the centred second moment uses the CURRENT mean (Clustering.py:677)."""
+            mu = self.__mean
+            self._occ += occ
+            self._socc += float(socc)
+            self._sx += sx
+            self._scc += sxx - 2.0 * mu * sx + mu * mu * occ[:, None]
+
+        @property
+        def acc(self):
+            with np.errstate(divide="ignore"):
+                return np.log(self._occ)
+
+        @property
+        def alpha_acc(self):
+            with np.errstate(divide="ignore"):
+                return np.log(self._socc)
+
+        @property
+        def mean_acc(self):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                return np.log(self._sx + self.__bias * self._occ[:, None])
+
+        @property
+        def covariance_acc(self):
+            return self.__bias  # Q14: the reference's getter returns the bias (Clustering.py:206-209)
+
+        @property
+        def covariance_acc_log(self):
+            """What the reference keeps in its private __covariance_acc: log sum gamma (x-mu_old)^2."""
+            with np.errstate(divide="ignore"):
+                return [np.log(np.maximum(r, 0.0)) for r in self._scc]
+
+        # ---- scoring (Clustering.py:740-767 -> util.py:20-36) -------------------------------
+        def _pack(self, eng):
+            mean = torch.as_tensor(self.__mean).to(eng.device)
+            var = torch.as_tensor(self.variance).to(eng.device)
+            alpha = torch.as_tensor(self.__alpha).to(eng.device)
+            return eng.pack_gmm(mean, var, alpha, mix=0)
+
+        def score_frames(self, X):
+            """log p(x_t) for every row of X [T,D] (batched `point(log=True)`): K1 dense kernel."""
+            X = np.asarray(X, dtype=np.float64)
+            if X.ndim != 2 or X.shape[1] != self.__dimension:
+                raise DataDimensionError("expected frames of dimension %d" % self.__dimension)
+            eng = get_engine()
+            W = self._pack(eng)
+            rows = eng.prepare_rows(torch.as_tensor(X).to(eng.device))
+            out = eng.score_dense(rows, W, 1, self.__mix_level)
+            return out[:, 0].double().cpu().numpy()
+
+        def point(self, x, log=False, standard=False, record=False):
+            """Score one frame.  `record=True` remembers the frame so that a following
+            update_acc can rebuild the per-component posteriors (the reference stores the
+            M component scores, Clustering.py:759-760)."""
+            x = np.asarray(x, dtype=np.float64).reshape(-1)
+            if len(x) != self.__dimension:
+                raise DataDimensionError("frame has %d dimensions, the model %d" % (len(x), self.__dimension))
+            if standard:
+                raise NotImplementedError("standard=True (unit-Gaussian scoring) is outside the E-step path")
+            lp = float(self.score_frames(x[None, :])[0])
+            if record:
+                self.__record.append(x)
+            return lp if log else float(np.exp(lp))
+
+        def gmm(self, x, mean, covariance, alpha, log=False, standard=False):
+            """Clustering.py:721-738: mixture density with explicit parameters."""
+            g = Clustering.GMM(self.log, self.__dimension, len(alpha), alpha=alpha, mean=mean, covariance=covariance)
+            return g.point(x, log=log, standard=standard)
+
+        # ---- Baum-Welch accumulation (Clustering.py:653-680) --------------------------------
+        def update_acc(self, l_value, b_value, o_value):
+            """l_value[T] = log gamma_t of this state, b_value[T] = its emission log-likelihoods,
+            o_value[T,D] = the frames.  Runs the K3 contraction on the device for a one-state
+            pseudo unit and folds the result into this GMM's accumulators; clears the record."""
+            from .engine import Corpus, EStep, Model
+
+            X = np.asarray(o_value, dtype=np.float64)
+            T = len(X)
+            l_value = np.asarray(l_value, dtype=np.float64).reshape(-1)
+            b_value = np.asarray(b_value, dtype=np.float64).reshape(-1)
+            assert len(l_value) == T and len(b_value) == T
+            eng = get_engine()
+            M, D = self.__mix_level, self.__dimension
+            mean = np.broadcast_to(self.__mean, (1, 3, M, D)).copy()
+            var = np.broadcast_to(self.variance, (1, 3, M, D)).copy()
+            alpha = np.broadcast_to(self.__alpha, (1, 3, M)).copy()
+            tm = np.zeros((1, 5, 5))
+            corpus = Corpus(eng, [np.zeros(1, dtype=np.int32)], np.array([T], dtype=np.int32), 1)
+            model = Model(eng, mean, var, alpha, tm)
+            es = EStep(eng, corpus, model)
+            es.load_frames(torch.as_tensor(X).to(eng.device))
+            model.pack(es.shift, es.inv_scale)
+            sp = _eng.nat.lib().pc_corpus_emission_floats(corpus.c) // T
+            b = torch.zeros((T, sp), dtype=torch.float32, device=eng.device)  # unused states: b = 0, gamma = 0
+            lg = torch.full((T, sp), float("-inf"), dtype=torch.float32, device=eng.device)
+            b[:, 0] = torch.as_tensor(b_value, dtype=torch.float32)
+            lg[:, 0] = torch.as_tensor(l_value, dtype=torch.float32)
+            es.b.copy_(b.reshape(-1))
+            es.lgam.copy_(lg.reshape(-1))
+            es.accumulate()
+            occ, sx, sxx = es.linear_stats()
+            with np.errstate(over="ignore"):
+                socc = float(np.exp(l_value[np.isfinite(l_value)]).sum())
+            self._add_linear(occ[0, 0], socc, sx[0, 0], sxx[0, 0])
+            self.__record = []
+
+        # ---- M-step (Clustering.py:682-693) ---------------------------------------------------
+        def update_param(self, show_q=False, c_covariance=1e-3):
+            """alpha = occ/socc, mean = sx/occ, var = max(E[(x-mu_old)^2], c_covariance)."""
+            eng = get_engine()
+            M, D = self.__mix_level, self.__dimension
+            dev = eng.device
+            mu = self.__mean
+            # pc_update_params consumes [G,80] rows (sum gamma x | sum gamma x^2) around the old mean
+            sxx = self._scc + 2.0 * mu * self._sx - mu * mu * self._occ[:, None]
+            acc = np.zeros((1, 3, M, _eng.KA))
+            acc[0, :, :, :D] = self._sx
+            acc[0, :, :, _eng.XS - 1] = self._occ
+            acc[0, :, :, _eng.XS:_eng.XS + D] = sxx
+            acc[0, :, :, _eng.KA - 1] = self._occ
+            # alpha's denominator is the state occupancy (alpha_acc); the kernel derives it from the
+            # component occupancies, which is the same number (sum_m gamma(j,m) = gamma(j))
+            mean = torch.as_tensor(np.broadcast_to(mu, (1, 3, M, D)).copy()).to(dev)
+            var = torch.as_tensor(np.broadcast_to(self.variance, (1, 3, M, D)).copy()).to(dev)
+            alpha = torch.as_tensor(np.broadcast_to(self.__alpha, (1, 3, M)).copy()).to(dev)
+            tm = torch.zeros((1, 5, 5), dtype=torch.float64, device=dev)
+            tmax = torch.full((1, _eng.SLOTS), float("-inf"), dtype=torch.float64, device=dev)
+            tsum = torch.zeros((1, _eng.SLOTS), dtype=torch.float64, device=dev)
+            _eng.nat.call("pc_update_params", eng.h, 1, M, D, _eng._p(torch.as_tensor(acc).to(dev)), _eng._p(tmax),
+                          _eng._p(tsum), None, None, float(c_covariance), 4, _eng._p(mean), _eng._p(var),
+                          _eng._p(alpha), _eng._p(tm), _eng._stream())
+            self.__mean = mean[0, 0].cpu().numpy()
+            self.__covariance = _diag_stack(var[0, 0].cpu().numpy())
+            self.__alpha = alpha[0, 0].cpu().numpy()
+            if show_q:
+                self.log.note("GMM %s re-estimated" % self.__gmm_id, cls="i")
+            self._clear_acc()
+
+        # ---- outside the hot path --------------------------------------------------------------
+        def em(self, *a, **k):
+            raise NotImplementedError("stand-alone GMM.em() / SMEM (Clustering.py:483-651,695-719) is outside the "
+                                      "E-step hot path (SURVEY §8 f2)")
+
+        expectation = maximization = q_function = theta = em
+
+    class ClusterInitialization(object):
+        def __init__(self, data, k, dimension, log=None):
+            """Clustering.py:774-790: data = list (or array) of D-vectors, k clusters."""
+            self.__data = data
+            self.__k = k
+            self.__dimension = dimension
+            self.log = log if log else Clustering.LogInfoPrint()
+            self.passes = None
+            self.moves = None
+
+        @staticmethod
+        def cal_distance(d1, d2, arg=2):
+            """Clustering.py:796-801 (Q2): the loop returns in its first iteration, so only
+            dimension 0 contributes.  Scalar helper kept for API parity; the device kernel
+            evaluates the same expression for every point."""
+            return float((abs(d1[0] - d2[0]) ** arg) ** (1 / arg))
+
+        @staticmethod
+        def cal_variance(cluster, algorithm=None):
+            """Clustering.py:807-832: per-dimension standard deviation of `cluster` = [centre,
+            points] with the 1e-4 variance floor, computed by pc_kmeans_finish."""
+            centre, points = cluster[0], cluster[1]
+            if algorithm == "kmeans":
+                points = list(points.values())
+            pts = np.ascontiguousarray(points, dtype=np.float64)
+            centre = np.asarray(centre, dtype=np.float64)
+            eng = get_engine()
+            n, D = pts.shape
+            x = torch.as_tensor(pts).to(eng.device)
+            off = np.array([0, n], dtype=np.int64)
+            # pc_kmeans_run writes the problem table pc_kmeans_finish reads; one pass is enough here
+            out = _eng.kmeans_run(eng, x, off, 1, np.zeros((1, 1), np.int32), max_passes=1)
+            ml = torch.arange(n, dtype=torch.int32, device=eng.device)  # the caller's point order
+            mc = torch.tensor([[n]], dtype=torch.int32, device=eng.device)
+            mean = torch.empty((1, 1, D), dtype=torch.float64, device=eng.device)
+            var = torch.empty_like(mean)
+            al = torch.empty((1, 1), dtype=torch.float64, device=eng.device)
+            _eng.nat.call("pc_kmeans_finish", eng.h, 1, _eng._p(off), _eng._p(x), D, 1, _eng._p(out["workspace"]),
+                          _eng._p(ml), _eng._p(mc), _eng._p(mean), _eng._p(var), _eng._p(al), _eng._stream())
+            if not np.allclose(mean[0, 0].cpu().numpy(), centre, rtol=1e-12, atol=1e-12):
+                raise NotImplementedError("cal_variance about a centre other than the cluster mean is not used by "
+                                          "the reference's k-means (Clustering.py:938-944)")
+            return list(np.sqrt(var[0, 0].cpu().numpy()))
+
+        def kmeans(self, algorithm=0, cov_matrix=False):
+            """Clustering.py:838-1044 with algorithm=1 (k-means++ style seeding drawn from Python's
+            `random`, greedy passes on the device).  Returns (mean[K,D], std[K,D] or cov[K,D,D],
+            alpha list, clustered_data list of point lists in insertion order)."""
+            if algorithm != 1:
+                raise NotImplementedError("only algorithm=1 is used by AcousticModel (AcousticModel.py:499,553)")
+            data = np.asarray(self.__data, dtype=np.float64)
+            if data.ndim != 2 or data.shape[1] != self.__dimension:
+                raise DataDimensionError("expected [n, %d] data" % self.__dimension)
+            n, K = len(data), self.__k
+            eng = get_engine()
+            seeds = _eng.kmeans_seed_points(np.ascontiguousarray(data[:, 0]), K, _random)
+            x = torch.as_tensor(data).to(eng.device)
+            out = _eng.kmeans_run(eng, x, np.array([0, n]), K, np.array([seeds], dtype=np.int32))
+            counts = out["member_count"][0].cpu().numpy()
+            ml = out["member_list"].cpu().numpy()
+            self.passes, self.moves = int(out["passes"][0]), int(out["moves"][0])
+            for _ in range(self.moves):  # the reference draws one dict key per move (Clustering.py:932)
+                _random.random()
+            mean = out["mean"][0].cpu().numpy()
+            var = out["var"][0].cpu().numpy()
+            alpha = [float(a) for a in out["alpha"][0].cpu().numpy()]
+            clustered, o = [], 0
+            for kk in range(K):
+                clustered.append([data[i] for i in ml[o:o + counts[kk]]])
+                o += counts[kk]
+            if cov_matrix:
+                return mean, _diag_stack(var), alpha, clustered
+            return mean, np.sqrt(var), alpha, clustered

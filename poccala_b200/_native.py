@@ -74,8 +74,11 @@ _SIGS = {
     "pc_update_params": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5
                          + [C.c_double, C.c_int32] + [C.c_void_p] * 5),
     "pc_viterbi": (C.c_int, [C.c_void_p] * 12),
-    "pc_kmeans_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 5
-                      + [C.c_int64, C.c_void_p]),
+    "pc_kmeans_workspace_bytes": (C.c_int64, [C.c_int32, C.c_void_p, C.c_int32]),
+    "pc_kmeans_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+                      + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p]),
+    "pc_kmeans_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+                         + [C.c_void_p] * 7),
     "pc_em_iteration_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
                              + [C.c_void_p] * 4 + [C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
 }

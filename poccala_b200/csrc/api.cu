@@ -480,13 +480,6 @@ int pc_viterbi(pc_handle h, pc_corpus c, const float *b, const double *b64, cons
                           unit_path, score, (cudaStream_t)stream);
 }
 
-int pc_kmeans_run(pc_handle h, int32_t, const int64_t *, const double *, int32_t, const int32_t *,
-                  int32_t *, int32_t *, int32_t *, int32_t *, int64_t, void *) {
-    PC_ENTER(h);
-    pc_set_error("pc_kmeans_run: not built yet");
-    return PC_ERR_UNSUPPORTED;
-}
-
 // --------------------------------------------------------------------------------- host e2e
 static int ensure_ws(pc_handle h, size_t bytes) {
     if (h->ws_bytes >= bytes) return PC_OK;

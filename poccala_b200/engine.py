@@ -281,6 +281,21 @@ class EStep:
         self.mstep(c_covariance, fix_code)
 
     # views --------------------------------------------------------------------------------
+    def linear_stats(self):
+        """Accumulators in the ORIGINAL feature coordinates (fp64 numpy): occ [U,3,M] = sum gamma,
+        sx [U,3,M,D] = sum gamma x, sxx [U,3,M,D] = sum gamma x^2 (SURVEY A.4's linear-equivalent
+        form of Clustering.GMM's log-domain accumulators, Clustering.py:653-680)."""
+        m = self.model
+        a = self.acc.view(m.n_units, EMIT, m.mix, KA)
+        D = m.dim
+        occ = a[..., XS - 1]
+        sx, sxx = a[..., :D], a[..., XS:XS + D]
+        if self.shift is not None:
+            sh, isc = self.shift[:D], self.inv_scale[:D]
+            sx = sx / isc + sh * occ[..., None]
+            sxx = sxx / (isc * isc) + 2 * sh * sx - sh * sh * occ[..., None]
+        return occ.cpu().numpy(), sx.cpu().numpy(), sxx.cpu().numpy()
+
     def transition_accumulators(self):
         """(ksai_acc [U,3,5], gamma_acc [U,3]) in the reference's log domain (LHMM.py:84-85)."""
         acc = (self.tmax + torch.log(self.tsum)).cpu().numpy().reshape(-1, EMIT, 3)
@@ -327,3 +342,70 @@ def em_iteration_host(engine, corpus, frames, mean, var, alpha, transmat, c_cova
     nat.call("pc_em_iteration_host", engine.h, corpus.c, _p(frames), D, U, M, _p(mean), _p(var), _p(alpha),
              _p(transmat), float(c_covariance), int(fix_code), C.byref(out), _stream())
     return out.value
+
+
+# ------------------------------------------------------------------------------------ K5 k-means
+def kmeans_seed_points(x0, k, rnd):
+    """Seeding of ClusterInitialization.kmeans(algorithm=1) (Clustering.py:975-1020):
+    the draws come from Python's `random` (module or random.Random), so this part is host code by
+    construction.  x0: metric coordinate (dimension 0, Q2) of the problem's points, fp64 numpy.
+    Returns the k seed point indices (duplicates possible, Q9)."""
+    n = len(x0)
+    c0 = rnd.randint(0, n - 1)
+    d = np.abs(x0[c0] - x0)
+    dl = np.sqrt(d * d)  # (|d| ** 2) ** 0.5
+    total = float(np.add.accumulate(dl)[-1])  # sequential fp64 sum in index order
+    seeds = [c0]
+    if total == 0.0:
+        idx = rnd.sample(range(0, n), k - 1)
+        if k > 2:
+            raise AssertionError("all points coincide in dimension 0: the reference asserts for k > 2 "
+                                 "(Clustering.py:1004-1008)")
+        seeds.extend(idx)
+        return seeds
+    for _ in range(1, k):
+        r = rnd.randint(0, int(total))
+        run = np.subtract.accumulate(np.concatenate(([float(r)], dl)))[1:]  # r -= dl[i], sequentially
+        hit = np.nonzero(run < 0)[0]
+        if len(hit) == 0:
+            raise AssertionError("k-means seeding found no point (Clustering.py:1008)")
+        seeds.append(int(hit[0]))
+    return seeds
+
+
+def kmeans_run(engine, x, point_off, k, seeds, max_passes=1 << 40):
+    """pc_kmeans_run + pc_kmeans_finish for a batch of independent problems.
+    x: [P,D] fp64 cuda tensor (problems concatenated), point_off: host int64 [n_problems+1],
+    seeds: int32 [n_problems,k] point indices inside each problem.
+    Returns dict(owner, member_list, member_count, passes, moves, mean, var, alpha) of device tensors
+    (member_list region of problem p starts at point_off[p] + p*k)."""
+    point_off = np.ascontiguousarray(point_off, dtype=np.int64)
+    n_problems = len(point_off) - 1
+    P, D = x.shape
+    if x.dtype != torch.float64:
+        raise TypeError("k-means data must be float64 (the reference's precision)")
+    if int(point_off[-1]) != P:
+        raise ValueError("point_off[-1]=%d but x has %d rows" % (int(point_off[-1]), P))
+    x = x.contiguous()
+    dev = engine.device
+    seeds_d = torch.as_tensor(np.ascontiguousarray(seeds, dtype=np.int32).reshape(n_problems, k)).to(dev)
+    ws_bytes = int(nat.lib().pc_kmeans_workspace_bytes(n_problems, _p(point_off), int(k)))
+    if ws_bytes < 0:
+        raise ValueError("k-means: bad problem sizes or k outside [1,127]")
+    ws = engine.empty((max(ws_bytes, 1),), torch.uint8)
+    out = dict(owner=engine.empty((P,), torch.int32),
+               member_list=engine.empty((P + n_problems * k,), torch.int32),
+               member_count=engine.empty((n_problems, k), torch.int32),
+               passes=engine.empty((n_problems,), torch.int32),
+               moves=engine.empty((n_problems,), torch.int64),
+               mean=engine.empty((n_problems, k, D), torch.float64),
+               var=engine.empty((n_problems, k, D), torch.float64),
+               alpha=engine.empty((n_problems, k), torch.float64))
+    nat.call("pc_kmeans_run", engine.h, n_problems, _p(point_off), _p(x), D, int(k), _p(seeds_d), _p(ws),
+             _p(out["owner"]), _p(out["member_list"]), _p(out["member_count"]), _p(out["passes"]),
+             _p(out["moves"]), int(max_passes), _stream())
+    nat.call("pc_kmeans_finish", engine.h, n_problems, _p(point_off), _p(x), D, int(k), _p(ws),
+             _p(out["member_list"]), _p(out["member_count"]), _p(out["mean"]), _p(out["var"]),
+             _p(out["alpha"]), _stream())
+    out["workspace"] = ws  # keep alive until the stream has run
+    return out

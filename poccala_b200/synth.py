@@ -166,4 +166,4 @@ def torch_corpus(n_utt, T, L, n_units, mix, seed, device, n_initials=None, dim=D
 def reference_unit_file():
     """Path of the IF unit file shipped with this package (same content/format as the reference's
     AcousticModel/Unit/IF)."""
-    return os.path.join(os.path.dirname(__file__), "AcousticModel", "Unit", "IF")
+    return os.path.join(os.path.dirname(__file__), "Unit", "IF")

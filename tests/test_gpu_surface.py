@@ -1,0 +1,186 @@
+"""The reference-shaped Python surface (poccala_b200.LHMM / Clustering / AcousticModel) replaying
+the reference's own call sequence (AcousticModel.py:884-935) against the golden
+vectors dumped from the executed reference.  Tolerance: 1e-4 relative (fp32 kernels vs the fp64
+reference) for likelihoods, accumulators and parameters; Viterbi paths and k-means memberships
+bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from tests.helpers import UNITS3, load_golden  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def _am(g, mix=4):
+    from poccala_b200.AcousticModel import AcousticModel
+
+    am = AcousticModel(None, "T", state_num=5, mix_level=mix)
+    am.set_units(UNITS3)
+    am.set_parameters(g["mean"], g["var"], g["alpha"])
+    return am
+
+
+def _close(a, b, rel=REL, floor=1e-3):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    fin = np.isfinite(b)
+    assert (np.isfinite(a) == fin).all()
+    return np.all(np.abs(a[fin] - b[fin]) <= rel * np.maximum(np.abs(b[fin]), floor))
+
+
+def test_replay_reference_call_sequence_per_utterance():
+    """multi_embedded_training_1 per utterance, then multi_embedded_training_2 per unit: the
+    reference's file-based iteration (golden it1_*)."""
+    g = load_golden("estep_small.npz")
+    am = _am(g)
+    n = int(g["n_utt"])
+    for k in range(n):
+        label = [UNITS3[i] for i in g[f"u{k}_label"]]
+        eh = am.multi_embedded_training_1(label, g[f"u{k}_X"], True, False, k + 1, n, 0)
+        # the sentence HMM the mirror assembled is the reference's
+        assert eh.iterations == [3]
+    for i, u in enumerate(UNITS3):
+        am.multi_embedded_training_2(u, True, False, False, 1e-6, i + 1, 3, 3, 0)
+    mean, var, alpha, tm = am.get_parameters()
+    assert _close(tm, g["it1_transmat"], floor=1e-6)
+    assert _close(alpha, g["it1_alpha"], floor=1e-3)
+    assert _close(mean, g["it1_mean"], floor=1.0)
+    assert np.all(np.abs(var - g["it1_var"]) <= REL * np.maximum(g["it1_var"], 1e-2))
+
+
+def test_unit_accumulators_match_reference_log_domain():
+    """After one utterance the unit HMMs hold the reference's log-domain accumulators
+    (hmm.ksai_acc / gamma_acc, gmm.acc / alpha_acc / mean_acc incl. the +100 bias, Q6/Q7)."""
+    from poccala_b200.LHMM import LHMM
+
+    g = load_golden("estep_small.npz")
+    for k in (0, 2):
+        am = _am(g)
+        label = [UNITS3[i] for i in g[f"u{k}_label"]]
+        X = g[f"u{k}_X"]
+        hmm_list = []
+        for u in label:
+            h = am.init_unit(u)
+            am.init_parameter(u, h)
+            h.cal_observation_pro([X], [len(X)])
+            hmm_list.append(h)
+        states, A, B, pi = am.embedded(label, hmm_list, 0, 15)
+        assert np.array_equal(A, g[f"u{k}_A"])
+        assert _close(B, g[f"u{k}_B"], rel=2e-6, floor=1.0)  # emissions: fp32 resolution
+        eh = LHMM(states, 5, None, transmat=A, probmat=[B], pi=pi, hmm_list=hmm_list, fix_code=0)
+        eh.add_data([X])
+        eh.add_T([len(X)])
+        eh.baulm_welch()
+        assert _close(eh.pi, g[f"u{k}_pi_next"], floor=1e-3)
+        for p, h in enumerate(hmm_list):
+            # log-domain values of magnitude 1e3: compare the linear ratios they encode
+            assert _close(h.ksai_acc, g[f"u{k}_p{p}_ksai_acc"], rel=2e-6, floor=1.0)
+            assert _close(h.gamma_acc, g[f"u{k}_p{p}_gamma_acc"], rel=2e-6, floor=1.0)
+            for gi, gm in enumerate(h.profunction[1:-1]):
+                ref_occ = np.exp(g[f"u{k}_p{p}_g{gi}_acc"])
+                big = ref_occ > 1e-3
+                assert _close(np.exp(gm.acc)[big], ref_occ[big])
+                assert _close(np.exp(gm.alpha_acc), np.exp(g[f"u{k}_p{p}_g{gi}_alpha_acc"]))
+                assert _close(np.exp(gm.mean_acc)[big], np.exp(g[f"u{k}_p{p}_g{gi}_mean_acc"])[big])
+                assert gm.covariance_acc == 100.0  # Q14
+
+
+def test_batched_training_equals_per_utterance_path_and_reference():
+    g = load_golden("estep_small.npz")
+    am = _am(g)
+    n = int(g["n_utt"])
+    labels = [[UNITS3[i] for i in g[f"u{k}_label"]] for k in range(n)]
+    data = [g[f"u{k}_X"] for k in range(n)]
+    am.add_corpus(labels, data)
+    ll = am.embedded_training(UNITS3, c_covariance=1e-6)
+    mean, var, alpha, tm = am.get_parameters()
+    assert np.isfinite(ll)
+    assert _close(tm, g["it1_transmat"], floor=1e-6)
+    assert _close(alpha, g["it1_alpha"], floor=1e-3)
+    assert _close(mean, g["it1_mean"], floor=1.0)
+    assert np.all(np.abs(var - g["it1_var"]) <= REL * np.maximum(g["it1_var"], 1e-2))
+    # a second iteration runs from the updated parameters and increases the likelihood
+    ll2 = am.embedded_training(UNITS3, c_covariance=1e-6)
+    assert ll2 > ll
+
+
+def test_lhmm_viterbi_golden_paths_and_ties():
+    from poccala_b200.LHMM import LHMM, UnsupportedModel
+
+    g = load_golden("estep_small.npz")
+    for k in range(int(g["n_utt"])):
+        A, B = g[f"u{k}_A"], g[f"u{k}_B"]
+        N = len(A)
+        states = {i: i for i in range(N)}
+        sc, path = LHMM.viterbi(None, states, A, B, np.ones(N) / N)
+        assert sc == float(g[f"u{k}_vit_score"])
+        assert path.dtype == np.float64 and (path == g[f"u{k}_vit_path"]).all()
+    v = load_golden("viterbi_ties.npz")
+    for k in range(int(v["n"])):
+        A, B = v[f"v{k}_A"], v[f"v{k}_B"]
+        N = len(A)
+        sc, path = LHMM.viterbi(None, {i: "a" for i in range(N)}, A, B, np.ones(N) / N)
+        assert sc == float(v[f"v{k}_score"]) and (path == v[f"v{k}_path"]).all()
+    dense = np.ones((5, 5)) / 5
+    with pytest.raises(UnsupportedModel):
+        LHMM.viterbi(None, {i: "a" for i in range(5)}, dense, np.zeros((5, 4)), np.ones(5) / 5)
+
+
+def test_acoustic_model_viterbi_returns_unit_labels():
+    g = load_golden("estep_small.npz")
+    am = _am(g)
+    for k in range(int(g["n_utt"])):
+        label = [UNITS3[i] for i in g[f"u{k}_label"]]
+        states = dict(enumerate([label[0]] + [u for u in label for _ in range(3)] + [label[-1]]))
+        N = len(states)
+        sc, units = am.viterbi(states, g[f"u{k}_A"], g[f"u{k}_B"], np.ones(N) / N)
+        assert sc == float(g[f"u{k}_vit_score"])
+        assert [UNITS3.index(u) for u in units] == list(g[f"u{k}_vit_units"])
+        runs = am.discriminate(label[0], units)
+        assert all(np.all(np.diff(r) == 1) for r in runs)
+
+
+def test_cluster_initialization_kmeans_golden():
+    from poccala_b200.Clustering import Clustering
+
+    kg = load_golden("kmeans_small.npz")
+    for c in range(int(kg["n"])):
+        data, K, seed = kg[f"k{c}_data"], int(kg[f"k{c}_K"]), int(kg[f"k{c}_seed"])
+        random.seed(seed)
+        ci = Clustering.ClusterInitialization(list(data), K, data.shape[1])
+        mean, cov, alpha, clustered = ci.kmeans(algorithm=1, cov_matrix=True)
+        after = random.random()
+        assert np.abs(mean - kg[f"k{c}_mean"]).max() == 0
+        assert np.allclose(np.stack([np.diag(x) for x in cov]), kg[f"k{c}_var"], rtol=1e-14, atol=0)
+        assert alpha == list(kg[f"k{c}_alpha"])
+        assert [len(x) for x in clustered] == list(kg[f"k{c}_sizes"])
+        flat = np.concatenate([np.stack(cl) for cl in clustered])
+        assert np.array_equal(flat, data[kg[f"k{c}_members"]])
+        # the global RNG is left where the reference leaves it (one key draw per move)
+        from oracle import ref_port as rp
+        random.seed(seed)
+        rp.kmeans_pp(list(data), K)
+        assert random.random() == after
+    assert Clustering.ClusterInitialization.cal_distance([1, 5, 9], [3, 100, -7]) == 2.0  # Q2
+
+
+def test_gmm_point_and_dimension_error():
+    from oracle import ref_port as rp
+    from poccala_b200.Clustering import Clustering, DataDimensionError
+
+    g = load_golden("estep_small.npz")
+    gm = Clustering.GMM(None, dimension=39, mix_level=4, alpha=g["alpha"][0, 0], mean=g["mean"][0, 0],
+                        variance=g["var"][0, 0])
+    assert gm.covariance.shape == (4, 39, 39)
+    port = dict(mean=g["mean"][0, 0], var=g["var"][0, 0], alpha=g["alpha"][0, 0], record=[], dim=39, mix=4)
+    X = g["u0_X"]
+    ref = np.array([rp.gmm_point(port, x, record=False) for x in X[:8]])
+    got = np.array([gm.point(x, log=True) for x in X[:8]])
+    assert np.all(np.abs(got - ref) <= 2e-6 * np.abs(ref))
+    assert np.all(np.abs(gm.score_frames(X[:8]) - ref) <= 2e-6 * np.abs(ref))
+    with pytest.raises(DataDimensionError):
+        gm.point(np.zeros(38), log=True)
