@@ -260,7 +260,8 @@ class Clustering(object):
             tm = torch.zeros((1, 5, 5), dtype=torch.float64, device=dev)
             tmax = torch.full((1, _eng.SLOTS), float("-inf"), dtype=torch.float64, device=dev)
             tsum = torch.zeros((1, _eng.SLOTS), dtype=torch.float64, device=dev)
-            _eng.nat.call("pc_update_params", eng.h, 1, M, D, _eng._p(torch.as_tensor(acc).to(dev)), _eng._p(tmax),
+            acc_d = torch.as_tensor(acc).to(dev)  # referenced until the results are read back
+            _eng.nat.call("pc_update_params", eng.h, 1, M, D, _eng._p(acc_d), _eng._p(tmax),
                           _eng._p(tsum), None, None, float(c_covariance), 4, _eng._p(mean), _eng._p(var),
                           _eng._p(alpha), _eng._p(tm), _eng._stream())
             self.__mean = mean[0, 0].cpu().numpy()

@@ -292,11 +292,15 @@ class LHMM(object):
             M, D = 1, 1
             dummy = torch.zeros((1, 3, 1, _eng.KA), dtype=torch.float64, device=dev)
             one = torch.ones((1, 3, 1, 1), dtype=torch.float64, device=dev)
-            _eng.nat.call("pc_update_params", eng.h, 1, M, D, _eng._p(dummy), _eng._p(torch.as_tensor(tmax).to(dev)),
-                          _eng._p(torch.as_tensor(tsum).to(dev)), None, None, float(c_covariance), 2,
-                          _eng._p(one), _eng._p(one.clone()), _eng._p(one.clone().view(1, 3, 1)), _eng._p(tm),
-                          _eng._stream())
+            # every device buffer stays referenced until the result has been read back: a temporary
+            # freed right after _p() would hand its block to the next allocation of the same size
+            tmax_d, tsum_d = torch.as_tensor(tmax).to(dev), torch.as_tensor(tsum).to(dev)
+            one_v, one_a = one.clone(), one.clone().view(1, 3, 1)
+            _eng.nat.call("pc_update_params", eng.h, 1, M, D, _eng._p(dummy), _eng._p(tmax_d), _eng._p(tsum_d),
+                          None, None, float(c_covariance), 2, _eng._p(one), _eng._p(one_v), _eng._p(one_a),
+                          _eng._p(tm), _eng._stream())
             self.__transmat = tm[0].cpu().numpy()
+            del tmax_d, tsum_d, one_v, one_a
             if show_a:
                 self.log.note("transmat:\n%s" % self.__transmat, cls="i")
         if not self.__fix_list[1] and self.__profunction is not None:
