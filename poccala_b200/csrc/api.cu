@@ -58,6 +58,11 @@ int pc_destroy(pc_handle h) {
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->copy_stream) {
+        cudaStreamDestroy(h->copy_stream);
+        cudaEventDestroy(h->start_ev);
+        for (int k = 0; k < PC_MAX_CHUNKS; ++k) cudaEventDestroy(h->chunk_ev[k]);
+    }
     delete h;
     return PC_OK;
 }
@@ -66,6 +71,8 @@ int pc_set_option(pc_handle h, const char *key, int64_t value) {
     PC_REQUIRE(h && key, "pc_set_option: NULL argument");
     if (!strcmp(key, "tensor_core")) { h->use_tc = (int)value; return PC_OK; }
     if (!strcmp(key, "fb_variant")) { h->fb_variant = (int)value; return PC_OK; }
+    if (!strcmp(key, "fb_cfg")) { h->fb_cfg = (int)value; return PC_OK; }
+    if (!strcmp(key, "host_chunks")) { h->host_chunks = (int)value; return PC_OK; }
     if (!strcmp(key, "launches")) { h->launches = value; return PC_OK; }
     pc_set_error("pc_set_option: unknown key '%s'", key);
     return PC_ERR_INVALID;
@@ -75,6 +82,8 @@ int64_t pc_get_option(pc_handle h, const char *key) {
     if (!h || !key) return -1;
     if (!strcmp(key, "tensor_core")) return h->use_tc;
     if (!strcmp(key, "fb_variant")) return h->fb_variant;
+    if (!strcmp(key, "fb_cfg")) return h->fb_cfg;
+    if (!strcmp(key, "host_chunks")) return h->host_chunks;
     if (!strcmp(key, "launches")) return h->launches;
     if (!strcmp(key, "sm_count")) return h->sm_count;
     return -1;
@@ -173,8 +182,22 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     item_tile_lo.push_back(n_tiles);
     const int64_t n_items = (int64_t)item_unit.size();
     PC_REQUIRE(n_items < 2147483647LL, "pc_corpus_create: too many work items");
-    // utterance-major groups of <= 3 tiles for the scoring kernel, heaviest first
+    // transfer chunks for the host-buffer entry point: <= PC_MAX_CHUNKS runs of consecutive
+    // utterances with about the same number of frames each (>= 32k frames per chunk)
+    int n_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(PC_MAX_CHUNKS, frame_off[n_utt] / 32768));
+    std::vector<int32_t> chunk_utt(n_chunks + 1, n_utt);
+    chunk_utt[0] = 0;
+    for (int k = 1, u = 0; k < n_chunks; ++k) {
+        const int64_t want = frame_off[n_utt] * k / n_chunks;
+        while (u < n_utt && frame_off[u] < want) ++u;
+        chunk_utt[k] = u;
+    }
+    std::vector<int32_t> utt_chunk(n_utt, 0);
+    for (int k = 0; k < n_chunks; ++k)
+        for (int u = chunk_utt[k]; u < chunk_utt[k + 1]; ++u) utt_chunk[u] = k;
+    // utterance-major groups of <= 3 tiles for the scoring kernel: by chunk, heaviest first inside
     std::vector<int32_t> sitem_utt, sitem_t0, sitem_nt;
+    std::vector<int32_t> chunk_sitem(n_chunks + 1, 0);
     {
         std::vector<int32_t> su, st0, snt;
         for (int u = 0; u < n_utt; ++u) {
@@ -188,13 +211,16 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
         std::vector<int32_t> ord(su.size());
         std::iota(ord.begin(), ord.end(), 0);
         std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+            if (utt_chunk[su[a]] != utt_chunk[su[b]]) return utt_chunk[su[a]] < utt_chunk[su[b]];
             return (int64_t)snt[a] * n_labels[su[a]] > (int64_t)snt[b] * n_labels[su[b]];
         });
         for (int32_t i : ord) {
             sitem_utt.push_back(su[i]);
             sitem_t0.push_back(st0[i]);
             sitem_nt.push_back(snt[i]);
+            chunk_sitem[utt_chunk[su[i]] + 1]++;
         }
+        for (int k = 0; k < n_chunks; ++k) chunk_sitem[k + 1] += chunk_sitem[k];
     }
     const int64_t n_sitems = (int64_t)sitem_utt.size();
 
@@ -253,6 +279,13 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     c->emis_floats = emis_off[n_utt];
     c->total_states = state_off[n_utt];
     c->items_per_chunk = (int32_t)chunk;
+    c->n_chunks = n_chunks;
+    for (int k = 0; k <= n_chunks; ++k) {
+        const int u = chunk_utt[k];
+        c->chunk_frame[k] = frame_off[u];
+        c->chunk_xtile[k] = xtile_off[u];
+        c->chunk_sitem[k] = chunk_sitem[k];
+    }
     CorpusView &v = c->v;
     v.n_utt = n_utt;
     v.n_units = n_units;
@@ -368,7 +401,7 @@ int pc_prepare_frames_f64(pc_handle h, pc_corpus c, const double *x, int32_t dim
     PC_REQUIRE(c && (c->total_frames == 0 || (x && X)), "pc_prepare_frames_f64: bad arguments");
     int rc = check_dim_mix("pc_prepare_frames_f64", dim, 1);
     if (rc) return rc;
-    return launch_prepare_frames(h, c->v, x, 1, dim, shift, inv_scale, X, (cudaStream_t)stream);
+    return launch_prepare_frames(h, c->v, x, 1, dim, shift, inv_scale, X, 0, c->v.n_xtiles, (cudaStream_t)stream);
 }
 
 int pc_prepare_frames_f32(pc_handle h, pc_corpus c, const float *x, int32_t dim, const double *shift,
@@ -377,7 +410,7 @@ int pc_prepare_frames_f32(pc_handle h, pc_corpus c, const float *x, int32_t dim,
     PC_REQUIRE(c && (c->total_frames == 0 || (x && X)), "pc_prepare_frames_f32: bad arguments");
     int rc = check_dim_mix("pc_prepare_frames_f32", dim, 1);
     if (rc) return rc;
-    return launch_prepare_frames(h, c->v, x, 0, dim, shift, inv_scale, X, (cudaStream_t)stream);
+    return launch_prepare_frames(h, c->v, x, 0, dim, shift, inv_scale, X, 0, c->v.n_xtiles, (cudaStream_t)stream);
 }
 
 int pc_prepare_rows_f64(pc_handle h, const double *x, int64_t n, int32_t dim, const double *shift,
@@ -405,7 +438,7 @@ int pc_gmm_score(pc_handle h, pc_corpus c, const float *X, const float *W, int32
     int rc = check_dim_mix("pc_gmm_score", 1, mix);
     if (rc) return rc;
     if (h->use_tc && score_tc_supported(mix))
-        return launch_score_tc(h, c->v, X, W, mix, b, (cudaStream_t)stream);
+        return launch_score_tc(h, c->v, X, W, mix, b, 0, c->v.n_sitems, (cudaStream_t)stream);
     return launch_score_simt(h, c->v, X, W, mix, b, (cudaStream_t)stream);
 }
 
@@ -552,7 +585,27 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     double *tsum = (double *)(ws + o_tsum), *sum = (double *)(ws + o_sum);
     int32_t *iters = (int32_t *)(ws + o_it);
 
-    PC_CUDA_TRY(cudaMemcpyAsync(raw, host_frames, (size_t)F * dim * 4, cudaMemcpyHostToDevice, st));
+    // Frames travel on their own stream in <= PC_MAX_CHUNKS runs of utterances; the compute stream
+    // prepares and scores run k as soon as it has landed, under the copy of run k+1 (pinned host
+    // memory makes the copies asynchronous; pageable memory still works, without the overlap).
+    if (!h->copy_stream) {
+        PC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+        for (int k = 0; k < PC_MAX_CHUNKS; ++k)
+            PC_CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
+    }
+    PC_CUDA_TRY(cudaEventRecord(h->start_ev, st));  // whatever the caller queued before us
+    PC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->start_ev, 0));
+    // option "host_chunks" merges neighbouring runs (1 = one copy, no overlap)
+    const int cap = h->host_chunks > 0 ? h->host_chunks : PC_MAX_CHUNKS;
+    const int kstep = (c->n_chunks + cap - 1) / cap;
+    for (int k = 0; k < c->n_chunks; k += kstep) {
+        const int k1 = k + kstep < c->n_chunks ? k + kstep : c->n_chunks;
+        const int64_t f_lo = c->chunk_frame[k], f_hi = c->chunk_frame[k1];
+        PC_CUDA_TRY(cudaMemcpyAsync(raw + (size_t)f_lo * dim, host_frames + (size_t)f_lo * dim,
+                                    (size_t)(f_hi - f_lo) * dim * 4, cudaMemcpyHostToDevice, h->copy_stream));
+        PC_CUDA_TRY(cudaEventRecord(h->chunk_ev[k], h->copy_stream));
+    }
     PC_CUDA_TRY(cudaMemcpyAsync(mean, host_mean, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
     PC_CUDA_TRY(cudaMemcpyAsync(var, host_var, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
     PC_CUDA_TRY(cudaMemcpyAsync(alpha, host_alpha, (size_t)G * 8, cudaMemcpyHostToDevice, st));
@@ -566,13 +619,17 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
         PC_LAUNCH_CHECK();
         h->launches += 2;
     }
-    if ((rc = launch_prepare_frames(h, c->v, raw, 0, dim, nullptr, nullptr, X, st))) return rc;
     if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, mix, W, st))) return rc;
-    if (h->use_tc && score_tc_supported(mix)) {
-        if ((rc = launch_score_tc(h, c->v, X, W, mix, b, st))) return rc;
-    } else if ((rc = launch_score_simt(h, c->v, X, W, mix, b, st))) {
-        return rc;
+    const bool tc_score = h->use_tc && score_tc_supported(mix);
+    for (int k = 0; k < c->n_chunks; k += kstep) {
+        const int k1 = k + kstep < c->n_chunks ? k + kstep : c->n_chunks;
+        PC_CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_ev[k], 0));
+        if ((rc = launch_prepare_frames(h, c->v, raw, 0, dim, nullptr, nullptr, X, c->chunk_xtile[k],
+                                        c->chunk_xtile[k1], st))) return rc;
+        if (tc_score && (rc = launch_score_tc(h, c->v, X, W, mix, b, c->chunk_sitem[k], c->chunk_sitem[k1], st)))
+            return rc;
     }
+    if (!tc_score && (rc = launch_score_simt(h, c->v, X, W, mix, b, st))) return rc;
     if ((rc = launch_forward_backward(h, c->v, b, ls, ln, lg, c->v.scratch0, logp, iters, pt, st))) return rc;
     if (!(fix_code & 2))
     {

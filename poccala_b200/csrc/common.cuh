@@ -15,6 +15,7 @@
 __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 #define PC_NEG_INF (-INFINITY)
+#define PC_MAX_CHUNKS 8  // host-buffer entry point: transfer / prepare / score pipeline depth
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
 struct CorpusView {
@@ -119,12 +120,17 @@ struct pc_handle_s {
     int sm_count;
     int use_tc;          // option "tensor_core"
     int fb_variant;      // option "fb_variant"
+    int fb_cfg;          // option "fb_cfg": K2 launch shape experiments
+    int host_chunks;     // option "host_chunks": cap on the transfer pipeline depth (0 = PC_MAX_CHUNKS)
     int64_t launches;    // kernels launched through this handle (bench: gpu_launches)
     // workspace for the host-buffer entry point
     void *ws;
     size_t ws_bytes;
     void *pinned;
     size_t pinned_bytes;
+    cudaStream_t copy_stream;                 // host-buffer entry point: frames travel on their own stream
+    cudaEvent_t chunk_ev[PC_MAX_CHUNKS];
+    cudaEvent_t start_ev;
 };
 
 struct pc_corpus_s {
@@ -136,6 +142,11 @@ struct pc_corpus_s {
     void *dev_block;     // one allocation holding every table
     int64_t *host_frame_off, *host_emis_off, *host_pair_off, *host_state_off;
     int32_t items_per_chunk;
+    // runs of consecutive utterances the host-buffer entry point pipelines (copy k+1 under score k)
+    int32_t n_chunks;
+    int64_t chunk_frame[PC_MAX_CHUNKS + 1];  // first frame of each chunk
+    int64_t chunk_xtile[PC_MAX_CHUNKS + 1];  // first frame-tile image
+    int32_t chunk_sitem[PC_MAX_CHUNKS + 1];  // first K1 work item
 };
 
 // Kernel launchers implemented in the per-kernel translation units.
@@ -144,13 +155,16 @@ int launch_pack_gmm(pc_handle h, const double *mean, const double *var, const do
                     float *W, cudaStream_t st);
 int launch_prepare_rows(pc_handle h, const void *x, int is_f64, int64_t n, int dim,
                         const double *shift, const double *inv_scale, float *X, cudaStream_t st);
+// [xtile_lo, xtile_hi): range of frame-tile images (whole corpus: 0, cv.n_xtiles)
 int launch_prepare_frames(pc_handle h, const CorpusView &cv, const void *x, int is_f64, int dim,
-                          const double *shift, const double *inv_scale, float *X, cudaStream_t st);
+                          const double *shift, const double *inv_scale, float *X, int64_t xtile_lo,
+                          int64_t xtile_hi, cudaStream_t st);
 int launch_score_simt(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                       float *b, cudaStream_t st);
 bool score_tc_supported(int mix);
+// [item_lo, item_hi): range of utterance-major work items (whole corpus: 0, v.n_sitems)
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
-                    float *b, cudaStream_t st);
+                    float *b, int item_lo, int item_hi, cudaStream_t st);
 bool accumulate_tc_supported(int mix);
 int launch_accumulate_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                          const float *b, const float *lgam, double *acc, cudaStream_t st);

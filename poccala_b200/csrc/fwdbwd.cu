@@ -22,9 +22,7 @@
 // Emissions are time-major (b[t][s]), so a warp reads / writes one coalesced row per frame.
 #include "common.cuh"
 
-#define FB_WARPS 4
 #define FB_RENORM 8
-#define FB_CH 4  // frames per prefetch chunk
 
 namespace {
 
@@ -62,7 +60,8 @@ __device__ __forceinline__ double warp_max_d(double v) {
     return v;
 }
 
-template <int SPL>
+// FB_CH: frames per prefetch chunk (loads are issued one chunk ahead); FB_WARPS: warps per block
+template <int SPL, int FB_CH, int FB_WARPS>
 __global__ void __launch_bounds__(FB_WARPS * 32)
 fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restrict__ log_self,
               const double *__restrict__ log_next, float *__restrict__ lgam, float4 *scratch,
@@ -412,17 +411,34 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
     }
 }
 
+template <int SPL, int CH, int WARPS>
+int launch_fb_cfg(pc_handle h, const CorpusView &v, const float *b, const double *log_self,
+                  const double *log_next, float *lgam, float *scratch0, double *utt_logp,
+                  int32_t *utt_iters, float *pair_trans, cudaStream_t st) {
+    int blocks = (v.n_utt + WARPS - 1) / WARPS;
+    fwdbwd_kernel<SPL, CH, WARPS><<<blocks, WARPS * 32, 0, st>>>(v, b, log_self, log_next, lgam,
+                                                                reinterpret_cast<float4 *>(scratch0), utt_logp,
+                                                                utt_iters, pair_trans);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
 template <int SPL>
 int launch_fb(pc_handle h, const CorpusView &v, const float *b, const double *log_self,
               const double *log_next, float *lgam, float *scratch0, double *utt_logp,
               int32_t *utt_iters, float *pair_trans, cudaStream_t st) {
-    int blocks = (v.n_utt + FB_WARPS - 1) / FB_WARPS;
-    fwdbwd_kernel<SPL><<<blocks, FB_WARPS * 32, 0, st>>>(v, b, log_self, log_next, lgam,
-                                                        reinterpret_cast<float4 *>(scratch0), utt_logp,
-                                                        utt_iters, pair_trans);
-    PC_LAUNCH_CHECK();
-    h->launches++;
-    return PC_OK;
+    if constexpr (SPL == 1) {
+        switch (h->fb_cfg) {  // option "fb_cfg": tuning experiments (profiles/exp_k2.py)
+            case 1: return launch_fb_cfg<1, 4, 4>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+            case 2: return launch_fb_cfg<1, 16, 4>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+            case 3: return launch_fb_cfg<1, 8, 1>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+            case 4: return launch_fb_cfg<1, 16, 1>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+            case 5: return launch_fb_cfg<1, 4, 1>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+            default: return launch_fb_cfg<1, 8, 4>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+        }
+    }
+    return launch_fb_cfg<SPL, 4, 4>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
 }
 
 }  // namespace

@@ -155,11 +155,12 @@ __global__ void prepare_rows_kernel(const T *__restrict__ x, int64_t n, int dim,
 template <typename T>
 __global__ void prepare_frames_kernel(CorpusView cv, const T *__restrict__ x, int dim,
                                       const double *__restrict__ shift,
-                                      const double *__restrict__ inv_scale, float *__restrict__ X) {
+                                      const double *__restrict__ inv_scale, float *__restrict__ X,
+                                      int64_t xtile_lo, int64_t xtile_hi) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cv.n_xtiles * PC_TILE_ROWS * 5) return;
-    const int64_t blk = i / (PC_TILE_ROWS * 5);
-    const int rem = (int)(i - blk * (PC_TILE_ROWS * 5));
+    if (i >= (xtile_hi - xtile_lo) * PC_TILE_ROWS * 5) return;
+    const int64_t blk = xtile_lo + i / (PC_TILE_ROWS * 5);
+    const int rem = (int)(i % (PC_TILE_ROWS * 5));
     const int c = rem / PC_TILE_ROWS, r = rem - c * PC_TILE_ROWS;  // consecutive threads -> consecutive rows
     const int u = cv.xtile_utt[blk];
     const int64_t f0 = cv.frame_off[u];
@@ -239,18 +240,19 @@ int launch_prepare_rows(pc_handle h, const void *x, int is_f64, int64_t n, int d
 }
 
 int launch_prepare_frames(pc_handle h, const CorpusView &cv, const void *x, int is_f64, int dim,
-                          const double *shift, const double *inv_scale, float *X, cudaStream_t st) {
-    if (cv.n_xtiles == 0) return PC_OK;
+                          const double *shift, const double *inv_scale, float *X, int64_t xtile_lo,
+                          int64_t xtile_hi, cudaStream_t st) {
+    if (xtile_hi <= xtile_lo) return PC_OK;
     const int threads = 256;
-    const int64_t blocks = (cv.n_xtiles * PC_TILE_ROWS * 5 + threads - 1) / threads;
+    const int64_t blocks = ((xtile_hi - xtile_lo) * PC_TILE_ROWS * 5 + threads - 1) / threads;
     if (blocks > 2147483647LL) {
         pc_set_error("prepare_frames: too many frames for one launch");
         return PC_ERR_UNSUPPORTED;
     }
     if (is_f64)
-        prepare_frames_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(cv, (const double *)x, dim, shift, inv_scale, X);
+        prepare_frames_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(cv, (const double *)x, dim, shift, inv_scale, X, xtile_lo, xtile_hi);
     else
-        prepare_frames_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(cv, (const float *)x, dim, shift, inv_scale, X);
+        prepare_frames_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(cv, (const float *)x, dim, shift, inv_scale, X, xtile_lo, xtile_hi);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

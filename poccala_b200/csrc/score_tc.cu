@@ -126,7 +126,7 @@ __device__ __forceinline__ void epilogue_pair(uint32_t taddr, const float *__res
 template <int MIX>
 __global__ void __launch_bounds__(Cfg<MIX>::NTHREADS, 1)
 score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W, int n_gauss,
-                float *__restrict__ b, int dbg) {
+                float *__restrict__ b, int item_lo, int item_hi, int dbg) {
     using C = Cfg<MIX>;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars *bars = reinterpret_cast<Bars *>(smem);
@@ -155,7 +155,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
     const bool scaled_rows = reinterpret_cast<const int *>(wscale + n_gauss)[0] != 0;
 
     uint32_t n_a = 0, n_b = 0, n_pair = 0;  // running counters: frame tiles, B stages, (tile, position) pairs
-    for (int item = blockIdx.x; item < v.n_sitems; item += gridDim.x) {
+    for (int item = item_lo + blockIdx.x; item < item_hi; item += gridDim.x) {
         const int u = v.sitem_utt[item];
         const int64_t f0 = v.frame_off[u];
         const int T = (int)(v.frame_off[u + 1] - f0);
@@ -306,12 +306,14 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
 }
 
 template <int MIX>
-int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W, float *b,
-               cudaStream_t st) {
+int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W, float *b, int item_lo,
+               int item_hi, cudaStream_t st) {
     auto kern = score_tc_kernel<MIX>;
     PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MIX>::SMEM));
-    int grid = v.n_sitems < h->sm_count ? v.n_sitems : h->sm_count;
-    kern<<<grid, Cfg<MIX>::NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, h->fb_variant);
+    const int n = item_hi - item_lo;
+    int grid = n < h->sm_count ? n : h->sm_count;
+    kern<<<grid, Cfg<MIX>::NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, item_lo, item_hi,
+                                                          h->fb_variant);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -326,14 +328,14 @@ extern "C" int pc_debug_read(long long *host_out, int n) {
 bool score_tc_supported(int mix) { return mix == 4 || mix == 8 || mix == 16 || mix == 32 || mix == 64; }
 
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
-                    float *b, cudaStream_t st) {
-    if (v.n_sitems == 0) return PC_OK;
+                    float *b, int item_lo, int item_hi, cudaStream_t st) {
+    if (item_hi <= item_lo) return PC_OK;
     switch (mix) {
-        case 4: return launch_mix<4>(h, v, X, W, b, st);
-        case 8: return launch_mix<8>(h, v, X, W, b, st);
-        case 16: return launch_mix<16>(h, v, X, W, b, st);
-        case 32: return launch_mix<32>(h, v, X, W, b, st);
-        case 64: return launch_mix<64>(h, v, X, W, b, st);
+        case 4: return launch_mix<4>(h, v, X, W, b, item_lo, item_hi, st);
+        case 8: return launch_mix<8>(h, v, X, W, b, item_lo, item_hi, st);
+        case 16: return launch_mix<16>(h, v, X, W, b, item_lo, item_hi, st);
+        case 32: return launch_mix<32>(h, v, X, W, b, item_lo, item_hi, st);
+        case 64: return launch_mix<64>(h, v, X, W, b, item_lo, item_hi, st);
     }
     pc_set_error("launch_score_tc: mix=%d not covered", mix);
     return PC_ERR_UNSUPPORTED;

@@ -25,6 +25,30 @@ def _am(g, mix=4):
     return am
 
 
+OCC_MIN = 1e-4  # same floor as tests/test_gpu_parity.py (DESIGN.md "tolerances"): a component whose
+# occupancy over the corpus is below 1e-4 frames is compared on its weight only
+
+
+def _occupied(g):
+    """Mask [U,3,M] of the components the golden iteration gives more than OCC_MIN frames."""
+    from oracle import fast
+    from poccala_b200 import synth
+
+    n = int(g["n_utt"])
+    om = fast.Model(g["mean"], g["var"], g["alpha"], synth.default_transmat(len(UNITS3)))
+    stats, _ = fast.estep_corpus(om, [g[f"u{k}_label"] for k in range(n)], [g[f"u{k}_X"] for k in range(n)])
+    return stats.occ >= OCC_MIN
+
+
+def _params_close(g, mean, var, alpha, tm):
+    ok = _occupied(g)
+    assert _close(tm, g["it1_transmat"], floor=1e-2)
+    assert _close(alpha, g["it1_alpha"], floor=1e-3)
+    assert np.all(np.abs(mean - g["it1_mean"])[ok] <= (REL * np.maximum(np.abs(g["it1_mean"]), np.sqrt(g["it1_var"])))[ok])
+    gvar = np.concatenate([g[f"u{k}_X"] for k in range(int(g["n_utt"]))], axis=0).var(axis=0)
+    assert np.all((np.abs(var - g["it1_var"]) <= REL * np.maximum(g["it1_var"], 1e-2 * gvar))[ok])
+
+
 def _close(a, b, rel=REL, floor=1e-3):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     fin = np.isfinite(b)
@@ -45,11 +69,7 @@ def test_replay_reference_call_sequence_per_utterance():
         assert eh.iterations == [3]
     for i, u in enumerate(UNITS3):
         am.multi_embedded_training_2(u, True, False, False, 1e-6, i + 1, 3, 3, 0)
-    mean, var, alpha, tm = am.get_parameters()
-    assert _close(tm, g["it1_transmat"], floor=1e-6)
-    assert _close(alpha, g["it1_alpha"], floor=1e-3)
-    assert _close(mean, g["it1_mean"], floor=1.0)
-    assert np.all(np.abs(var - g["it1_var"]) <= REL * np.maximum(g["it1_var"], 1e-2))
+    _params_close(g, *am.get_parameters())
 
 
 def test_unit_accumulators_match_reference_log_domain():
@@ -97,12 +117,8 @@ def test_batched_training_equals_per_utterance_path_and_reference():
     data = [g[f"u{k}_X"] for k in range(n)]
     am.add_corpus(labels, data)
     ll = am.embedded_training(UNITS3, c_covariance=1e-6)
-    mean, var, alpha, tm = am.get_parameters()
     assert np.isfinite(ll)
-    assert _close(tm, g["it1_transmat"], floor=1e-6)
-    assert _close(alpha, g["it1_alpha"], floor=1e-3)
-    assert _close(mean, g["it1_mean"], floor=1.0)
-    assert np.all(np.abs(var - g["it1_var"]) <= REL * np.maximum(g["it1_var"], 1e-2))
+    _params_close(g, *am.get_parameters())
     # a second iteration runs from the updated parameters and increases the likelihood
     ll2 = am.embedded_training(UNITS3, c_covariance=1e-6)
     assert ll2 > ll
