@@ -44,7 +44,8 @@ struct CorpusView {
     const int64_t *tile_boff;    // [n_tiles] float offset of (frame t0, state 0 of the pair) in b / lgam
     const int64_t *item_tile_lo;  // [n_items+1] tile range of each work item (one unit per item)
     const int32_t *item_unit;     // [n_items]
-    float *scratch0;              // [total_frames] float4 per frame (K2 scratch: g, shift_b, entry beta)
+    float *scratch0;              // [total_frames] float4 per frame (K2 scratch: beta_hat of the entry state)
+    float *scratch1;              // [emission floats] K2 scratch: beta_hat rows, same layout as b / lgam
     // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
     int64_t total_frames;
     int32_t n_sitems;

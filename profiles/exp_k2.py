@@ -30,3 +30,10 @@ for cfg in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 5]:
     torch.cuda.synchronize()
     lp = es.utt_logp.sum().item()
     print("fb_cfg %d: %.1f us per call, sum logp %.6f" % (cfg, ev[0].elapsed_time(ev[1]) * 100, lp), flush=True)
+
+import ctypes as C
+buf = (C.c_longlong * 16)()
+lib = nat.lib(); lib.pc_debug_read_fb.argtypes = [C.c_void_p]; lib.pc_debug_read_fb(buf)
+a = list(buf)
+print("block 0 clocks: backward %d, pi %d, forward %d, helper tail after forward %d (T=%d: %.0f / %.0f clk per frame)" % (
+    a[1] - a[0], a[2] - a[1], a[3] - a[2], a[9] - a[3], T, (a[1] - a[0]) / (T - 1), (a[3] - a[2]) / (T - 1)))

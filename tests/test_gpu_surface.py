@@ -119,9 +119,21 @@ def test_batched_training_equals_per_utterance_path_and_reference():
     ll = am.embedded_training(UNITS3, c_covariance=1e-6)
     assert np.isfinite(ll)
     _params_close(g, *am.get_parameters())
-    # a second iteration runs from the updated parameters and increases the likelihood
+    # a second iteration runs from the updated parameters.  With the reference's arithmetic (Q1: the
+    # log-Gaussian normaliser uses sum(var), Q6, Q8) the likelihood is NOT monotone - the oracle
+    # itself drops from -8614.9 to -13825.7 here - so compare with the oracle's second iteration
+    # (collapsed variances at the 1e-6 floor make it sensitive to the 1e-4 parameter differences)
+    from oracle import fast
+    from poccala_b200 import synth
+
+    om = fast.Model(g["mean"], g["var"], g["alpha"], synth.default_transmat(len(UNITS3)))
+    lab = [g[f"u{k}_label"] for k in range(n)]
+    stats, info = fast.estep_corpus(om, lab, data)
+    assert abs(ll - float(np.sum(info["logp"]))) <= REL * abs(ll)
+    om = fast.mstep(om, stats, c_covariance=1e-6)
+    _, info2 = fast.estep_corpus(om, lab, data)
     ll2 = am.embedded_training(UNITS3, c_covariance=1e-6)
-    assert ll2 > ll
+    assert abs(ll2 - float(np.sum(info2["logp"]))) <= 2e-2 * abs(ll2)
 
 
 def test_lhmm_viterbi_golden_paths_and_ties():
