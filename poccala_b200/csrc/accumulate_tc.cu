@@ -33,6 +33,31 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float P_SHIFT = 15.f;
 constexpr float P_UNSHIFT = 1.f / 32768.f;
 
+// A (tile, unit) pair whose posteriors all vanish contributes exactly nothing: P = gamma_t(j,m) <=
+// gamma_t(j), and the P tile stores P * 2^15 as fp16 (hi, lo), which is exactly (0, 0) below 2^-25.
+// With every log gamma of the tile below log(2^-41) (one bit of margin for the rounding of S - b)
+// the kernel would multiply by an all-zero P tile; such tiles are dropped from the work list.  On
+// forced-alignment-like posteriors (a label position is occupied during a small part of its
+// utterance) that is more than half of the tiles.
+constexpr float ACTIVE_MIN_LGAM = -41.f * 0.6931471805599453f;
+
+// one warp per unit-major tile: active[tile] = any(log gamma > ACTIVE_MIN_LGAM)
+__global__ void tile_active_kernel(CorpusView v, const float *__restrict__ lgam, int32_t *__restrict__ active) {
+    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (tile >= v.n_tiles) return;
+    const int rows = v.tile_rows[tile], tp = v.tile_tp[tile];
+    const float *base = lgam + v.tile_boff[tile];
+    float m = PC_NEG_INF;
+    for (int r = lane; r < rows; r += 32) {
+        const float *p = base + (size_t)r * tp;
+#pragma unroll
+        for (int s = 0; s < PC_EMIT; ++s) m = fmaxf(m, __ldg(p + s));
+    }
+    const bool any = __any_sync(0xffffffffu, m > ACTIVE_MIN_LGAM);  // NaN rows: kept out, they poison nothing
+    if (lane == 0) active[tile] = any ? 1 : 0;
+}
+
 // NC = Gaussians handled per work item (a unit's 3*MIX Gaussians, or a slice of them)
 template <int MIX>
 struct Cfg {
@@ -104,7 +129,7 @@ template <int MIX>
 __global__ void __launch_bounds__(NTHREADS, 1)
 accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W, int n_gauss,
                      const float *__restrict__ b, const float *__restrict__ lgam,
-                     double *__restrict__ acc) {
+                     const int32_t *__restrict__ active, double *__restrict__ acc) {
     using C = Cfg<MIX>;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars *bars = reinterpret_cast<Bars *>(smem);
@@ -151,8 +176,17 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
         const int g0 = slice * C::NC;  // first Gaussian of the slice inside the unit
         const size_t gfirst = (size_t)unit * C::N_UNIT + g0;
         const int64_t lo = v.item_tile_lo[item], hi = v.item_tile_lo[item + 1];
-        const int n_tiles_ = (int)(hi - lo);
+        // the item's active tiles as a bit mask (an item has at most 16 tiles); every warp forms the
+        // same mask, so all roles skip the same tiles - and an item without any - consistently
+        const uint32_t amask = __ballot_sync(0xffffffffu, lane < (int)(hi - lo) && __ldg(active + lo + lane) != 0);
+        if (amask == 0u) {
+            --n_item;  // compensates the loop increment: barrier parities count non-empty items only
+            continue;
+        }
+        const int n_tiles_ = __popc(amask);
         const int n_tiles = n_tiles_;
+        // i-th active tile of the item -> tile index
+        auto nth_tile = [&](int i) { return lo + (int64_t)(__fns(amask, 0, i + 1)); };
 
         if (warp == W_PROD) {
             // ------------------------------------------------------------ TMA producer
@@ -166,7 +200,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
             for (int i = 0; i < n_tiles; ++i) {
                 const uint32_t n = n_tile + i;
                 const int slot = n % C::NA;
-                const int64_t tile = lo + i;
+                const int64_t tile = nth_tile(i);
                 tc::mbar_wait(&bars->a_empty[slot], ((n / C::NA) & 1) ^ 1);
                 if (lane == 0) {
                     tc::mbar_expect_tx(&bars->a_full[slot], PC_XTILE_BYTES);
@@ -257,7 +291,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                 const uint32_t n = n_tile + i;
                 if ((int)(n & 1) != grp) continue;
                 const int sb = n & 1, ps = n & 1;
-                const int64_t tile = lo + i;
+                const int64_t tile = nth_tile(i);
                 const int rows = v.tile_rows[tile];
                 const int tp = v.tile_tp[tile];
                 // d = (lgam - b) * log2(e) + 15 for the unit's three states; -inf kills the row
@@ -340,7 +374,15 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
     PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MIX>::SMEM));
     const int n_work = v.n_items * Cfg<MIX>::N_SLICES;
     const int grid = n_work < h->sm_count ? n_work : h->sm_count;
-    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, acc);
+    {
+        const int64_t warps = v.n_tiles;
+        const int threads = 256;
+        const int64_t blocks = (warps * 32 + threads - 1) / threads;
+        tile_active_kernel<<<(unsigned)blocks, threads, 0, st>>>(v, lgam, v.tile_active);
+        PC_LAUNCH_CHECK();
+        h->launches++;
+    }
+    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

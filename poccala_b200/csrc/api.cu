@@ -253,6 +253,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_iunit = add(item_unit.data(), (size_t)n_items * 4);
     size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 16);  // float4 per frame (K2)
     size_t o_scratch1 = add(nullptr, (size_t)emis_off[n_utt] * 4);    // beta_hat rows (K2)
+    size_t o_tact = add(nullptr, (size_t)n_tiles * 4);                 // active-tile flags (K3)
     size_t o_sutt = add(sitem_utt.data(), (size_t)n_sitems * 4);
     size_t o_st0 = add(sitem_t0.data(), (size_t)n_sitems * 4);
     size_t o_snt = add(sitem_nt.data(), (size_t)n_sitems * 4);
@@ -314,6 +315,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     v.item_unit = (const int32_t *)(dev + o_iunit);
     v.scratch0 = (float *)(dev + o_scratch);
     v.scratch1 = (float *)(dev + o_scratch1);
+    v.tile_active = (int32_t *)(dev + o_tact);
     v.total_frames = frame_off[n_utt];
     v.n_sitems = (int32_t)n_sitems;
     v.sitem_utt = (const int32_t *)(dev + o_sutt);

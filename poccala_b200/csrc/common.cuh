@@ -46,6 +46,7 @@ struct CorpusView {
     const int32_t *item_unit;     // [n_items]
     float *scratch0;              // [total_frames] float4 per frame (K2 scratch: beta_hat of the entry state)
     float *scratch1;              // [emission floats] K2 scratch: beta_hat rows, same layout as b / lgam
+    int32_t *tile_active;         // [n_tiles] K3 scratch: 1 = the tile carries posterior mass
     // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
     int64_t total_frames;
     int32_t n_sitems;
