@@ -227,7 +227,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     tc::mbar_wait(&bars->a_full[slot], (n / C::NA) & 1);
                     tc::mbar_wait(&bars->s_empty[sb], ((n >> 1) & 1) ^ 1);
                     tc::tc_fence_after();
-                    if (lane == 0) {
+                    if (tc::elect_one()) {
                         const uint32_t d = tmem_base + sb * C::S_STRIDE;
                         const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                         const uint32_t bh = b_base, bl = b_base + PC_WGROUP_BYTES / 2;
@@ -256,7 +256,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     tc::mbar_wait(&bars->p_full[ps], (n >> 1) & 1);
                     if (i == 1) tc::mbar_wait(&bars->d2_empty, (n_item & 1) ^ 1);  // previous flush done
                     tc::tc_fence_after();
-                    if (lane == 0) {
+                    if (tc::elect_one()) {
                         const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                         const uint32_t ph = p_base + ps * 2 * C::P_PIECE, pl = ph + C::P_PIECE;
                         uint32_t accum = (i == 1) ? 0u : 1u;  // first tile of the item resets D2

@@ -41,11 +41,22 @@ struct Cfg {
     static constexpr int B_PIECE = T_KCH * NPAD * 16;
     static constexpr int B_STAGE = 2 * B_PIECE;  // hi, lo
     static constexpr int G = MIX <= 16 ? 3 : 2;                                // tiles per group
-    static constexpr int NA = MIX <= 16 ? 4 : (MIX <= 32 ? 3 : 2);             // frame-tile slots
-    static constexpr int NB = MIX <= 16 ? 3 : 2;                               // B stages
+    // frame-tile slots / B stages.  Up to 16 mixtures the tiles move on to tensor memory at once
+    // (A_TMEM below), so 3 slots suffice and the shared memory goes to a deep ring of unit images:
+    // a 15 KiB bulk copy has ~2 us of latency, 3 stages of ~1 us of contractions each starved the
+    // MMA warp (profiles/README.md)
+    static constexpr int NA = MIX <= 16 ? 3 : (MIX <= 32 ? 3 : 2);
+    static constexpr int NB = MIX <= 16 ? 6 : 2;
     static constexpr int TM_STRIDE = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256));
     static constexpr int TM_BUFS = TM_STRIDE >= 256 ? 2 : 4;
-    static constexpr int TM_COLS = TM_STRIDE * TM_BUFS;
+    // frame tiles as the TMEM A operand (tcgen05.cp once per tile, reused by every label position):
+    // 40 columns hi + 40 columns lo per tile.  Fits beside the accumulators up to 16 mixtures;
+    // wider units (N >= 96 per MMA) amortise the shared-memory A read well enough already.
+    static constexpr bool A_TMEM = (TM_STRIDE * TM_BUFS + G * T_KCH * 8) <= 512 && NPAD <= 64;
+    static constexpr int A_COL0 = TM_STRIDE * TM_BUFS;
+    static constexpr int A_TILE_COLS = T_KCH * 8;  // 2 pieces x 5 K-steps x 8 columns
+    static constexpr int TM_NEED = A_TMEM ? A_COL0 + G * A_TILE_COLS : TM_STRIDE * TM_BUFS;
+    static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : (TM_NEED <= 64 ? 64 : (TM_NEED <= 128 ? 128 : (TM_NEED <= 256 ? 256 : 512)));
     static constexpr int EPI_GROUPS = TM_BUFS;                // one epilogue warpgroup per TMEM buffer
     static constexpr int W_PROD = 4 * EPI_GROUPS, W_MMA = W_PROD + 1;
     static constexpr int NTHREADS = (W_MMA + 1) * 32;
@@ -55,7 +66,7 @@ struct Cfg {
 
 struct Bars {
     uint64_t a_full[4], a_empty[4];
-    uint64_t b_full[3], b_empty[3];
+    uint64_t b_full[8], b_empty[8];
     uint64_t tm_full[4], tm_empty[4];
     uint32_t tmem_base;
 };
@@ -139,7 +150,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
             tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1);
             tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], 4);
         }
-        for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars->b_full[i], 1); tc::mbar_init(&bars->b_empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { tc::mbar_init(&bars->b_full[i], 1); tc::mbar_init(&bars->b_empty[i], 1); }
         tc::mbar_fence_init();
     }
     if (warp == C::W_MMA) tc::tmem_alloc(&bars->tmem_base, C::TM_COLS);
@@ -216,6 +227,28 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                 n_b = __reduce_max_sync(0xffffffffu, n_b);
                 n_pair = __reduce_max_sync(0xffffffffu, n_pair);
                 const uint32_t na0 = n_a;
+                if constexpr (C::A_TMEM) {
+                    // stage the group's frame tiles in tensor memory: 10 copies of 128 rows x 32 bytes
+                    // per tile; the shared-memory slot is free again as soon as they have run, so the
+                    // producer streams the next group's tiles under this group's contractions
+                    for (int j = 0; j < nt; ++j) {
+                        const uint32_t na = na0 + j;
+                        const int slot = na % C::NA;
+                        tc::mbar_wait(&bars->a_full[slot], (na / C::NA) & 1);
+                        tc::tc_fence_after();
+                        if (tc::elect_one()) {
+                            const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
+                            const uint32_t ta = tmem_base + C::A_COL0 + j * C::A_TILE_COLS;
+#pragma unroll
+                            for (int k = 0; k < T_KCH / 2; ++k) {
+                                tc::tmem_cp_128x256b(ta + 8 * k, tc::umma_desc(ah + 2 * k * T_ROWS * 16, T_ROWS * 16, 128));
+                                tc::tmem_cp_128x256b(ta + T_KCH * 4 + 8 * k, tc::umma_desc(al + 2 * k * T_ROWS * 16, T_ROWS * 16, 128));
+                            }
+                            tc::tc_commit(&bars->a_empty[slot]);
+                        }
+                        __syncwarp();
+                    }
+                }
                 for (int p = 0; p < L; ++p, ++n_b) {
                     const int stage = n_b % C::NB;
                     tc::mbar_wait(&bars->b_full[stage], (n_b / C::NB) & 1);
@@ -224,31 +257,37 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         const int slot = na % C::NA, tb = n_pair % C::TM_BUFS;
                         const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n_pair < 1000;
                         if (rec) g_pc_dbg[n_pair * 8 + 0] = clock64();
-                        if (p == 0) tc::mbar_wait(&bars->a_full[slot], (na / C::NA) & 1);
+                        if (!C::A_TMEM && p == 0) tc::mbar_wait(&bars->a_full[slot], (na / C::NA) & 1);
                         if (rec) g_pc_dbg[n_pair * 8 + 1] = clock64();
                         tc::mbar_wait(&bars->tm_empty[tb], ((n_pair / C::TM_BUFS) & 1) ^ 1);
                         if (rec) g_pc_dbg[n_pair * 8 + 2] = clock64();
                         tc::tc_fence_after();
-                        if (lane == 0) {
+                        if (tc::elect_one()) {
                             const uint32_t d = tmem_base + tb * C::TM_STRIDE;
                             const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                             const uint32_t bh = b_base + stage * C::B_STAGE, bl = bh + PC_WGROUP_BYTES / 2;
+                            const uint32_t tah = tmem_base + C::A_COL0 + j * C::A_TILE_COLS, tal = tah + T_KCH * 4;
                             uint32_t accum = 0;
 #pragma unroll
                             for (int q = 0; q < 3; ++q) {
                                 const uint32_t ap = (q == 2) ? al : ah;
+                                const uint32_t tap = (q == 2) ? tal : tah;
                                 const uint32_t bp = (q == 1) ? bl : bh;
                                 if (dbg & 2) break;
 #pragma unroll
                                 for (int k = 0; k < T_KCH / 2; ++k) {
-                                    const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
                                     const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
-                                    tc::mma_f16_ss(d, ad, bd, idesc, accum);
+                                    if constexpr (C::A_TMEM) {
+                                        tc::mma_f16_ts(d, tap + 8 * k, bd, idesc, accum);
+                                    } else {
+                                        const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
+                                        tc::mma_f16_ss(d, ad, bd, idesc, accum);
+                                    }
                                     accum = 1;
                                 }
                             }
                             tc::tc_commit(&bars->tm_full[tb]);
-                            if (p == L - 1) tc::tc_commit(&bars->a_empty[slot]);
+                            if (!C::A_TMEM && p == L - 1) tc::tc_commit(&bars->a_empty[slot]);
                             if (j == nt - 1) tc::tc_commit(&bars->b_empty[stage]);
                         }
                         if (rec) g_pc_dbg[n_pair * 8 + 3] = clock64();

@@ -65,6 +65,19 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
         : "memory");
 }
 
+// One lane of the (converged) warp, chosen by the hardware: code under `if (elect_one())` is known to
+// the compiler to run in a single thread, so tcgen05 instructions issue back to back instead of
+// inside the per-active-lane loop that a `lane == 0` branch gets.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_out, uint32_t cols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -98,6 +111,22 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows = lanes, 8 columns of packed fp16
+// pairs per K = 16 step) staged in tensor memory by tcgen05.cp
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory (matrix descriptor: 128 rows x 32 bytes as 8x16-byte core matrices) -> 128 lanes x
+// 8 columns of tensor memory; ordered with the tcgen05.mma stream of the issuing thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t smem_desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(smem_desc) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
