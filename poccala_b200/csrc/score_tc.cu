@@ -181,38 +181,64 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
             const int t_first = t_item + jg * T_ROWS;
             if (warp == C::W_PROD) {
                 // -------------------------------------------------------- TMA producer
-                // order = consumption order of the MMA warp: A_0, B_0, A_1 .. A_{nt-1}, B_1 .. B_{L-1}
-                for (int step = 0; step < nt + L; ++step) {
-                    const bool is_a = (step == 0) || (step >= 2 && step <= nt);
-                    if (is_a) {
-                        const int j = (step == 0) ? 0 : step - 1;
-                        const int slot = n_a % C::NA;
-                        const int t0 = t_first + j * T_ROWS;
-                        tc::mbar_wait(&bars->a_empty[slot], ((n_a / C::NA) & 1) ^ 1);
-                        if (lane == 0 && (dbg & 8)) {
-                            tc::mbar_arrive(&bars->a_full[slot]);
-                        } else if (lane == 0) {
-                            tc::mbar_expect_tx(&bars->a_full[slot], PC_XTILE_BYTES);
-                            tc::tma_load_1d(a_s + slot * 2 * T_PIECE,
-                                            x16 + (size_t)(v.xtile_off[u] + t0 / T_ROWS) * PC_XTILE_BYTES,
-                                            PC_XTILE_BYTES, &bars->a_full[slot]);
-                        }
-                        ++n_a;
-                    } else {
-                        const int p = (step == 1) ? 0 : step - nt;
-                        const int stage = n_b % C::NB;
-                        const int unit = v.labels[p0 + p];
-                        uint8_t *dst = b_s + stage * C::B_STAGE;
-                        tc::mbar_wait(&bars->b_empty[stage], ((n_b / C::NB) & 1) ^ 1);
-                        if (lane == 0 && (dbg & 4)) {
-                            tc::mbar_arrive(&bars->b_full[stage]);
-                        } else if (lane == 0) {
-                            tc::mbar_expect_tx(&bars->b_full[stage], C::B_STAGE);
-                            tc::tma_load_1d(dst, w16 + (size_t)unit * C::B_STAGE, C::B_STAGE, &bars->b_full[stage]);
-                        }
-                        ++n_b;
+                auto load_a = [&](int uu, int t0) {   // one frame tile of utterance uu
+                    const int slot = n_a % C::NA;
+                    tc::mbar_wait(&bars->a_empty[slot], ((n_a / C::NA) & 1) ^ 1);
+                    if (lane == 0 && (dbg & 8)) {
+                        tc::mbar_arrive(&bars->a_full[slot]);
+                    } else if (lane == 0) {
+                        tc::mbar_expect_tx(&bars->a_full[slot], PC_XTILE_BYTES);
+                        tc::tma_load_1d(a_s + slot * 2 * T_PIECE,
+                                        x16 + (size_t)(v.xtile_off[uu] + t0 / T_ROWS) * PC_XTILE_BYTES,
+                                        PC_XTILE_BYTES, &bars->a_full[slot]);
                     }
+                    ++n_a;
                     __syncwarp();
+                };
+                auto load_b = [&](int p) {            // the unit image of label position p
+                    const int stage = n_b % C::NB;
+                    const int unit = v.labels[p0 + p];
+                    uint8_t *dst = b_s + stage * C::B_STAGE;
+                    tc::mbar_wait(&bars->b_empty[stage], ((n_b / C::NB) & 1) ^ 1);
+                    if (lane == 0 && (dbg & 4)) {
+                        tc::mbar_arrive(&bars->b_full[stage]);
+                    } else if (lane == 0) {
+                        tc::mbar_expect_tx(&bars->b_full[stage], C::B_STAGE);
+                        tc::tma_load_1d(dst, w16 + (size_t)unit * C::B_STAGE, C::B_STAGE, &bars->b_full[stage]);
+                    }
+                    ++n_b;
+                    __syncwarp();
+                };
+                if constexpr (C::A_TMEM) {
+                    // The MMA warp moves a group's tiles to tensor memory at once, which frees their
+                    // slots: the NEXT group's tiles are requested right after this group's first unit
+                    // images, a whole group of contractions before they are needed (HBM latency and
+                    // the tcgen05.cp staging stay off the critical path).
+                    if (item == item_lo + (int)blockIdx.x && jg == 0)
+                        for (int j = 0; j < nt; ++j) load_a(u, t_first + j * T_ROWS);
+                    const int lead = min(L, 3);  // unit images issued ahead of the next group's tiles
+                    for (int p = 0; p < lead; ++p) load_b(p);
+                    {
+                        int nu = u, nt0 = t_first + C::G * T_ROWS, nn = nt_item - jg - C::G;  // next group
+                        if (nn <= 0) {
+                            const int nitem = item + (int)gridDim.x;
+                            nn = 0;
+                            if (nitem < item_hi) {
+                                nu = v.sitem_utt[nitem];
+                                nt0 = v.sitem_t0[nitem];
+                                nn = v.sitem_nt[nitem];
+                            }
+                        }
+                        nn = min(nn, C::G);
+                        for (int j = 0; j < nn; ++j) load_a(nu, nt0 + j * T_ROWS);
+                    }
+                    for (int p = lead; p < L; ++p) load_b(p);
+                } else {
+                    // order = consumption order of the MMA warp: A_0, B_0, A_1 .. A_{nt-1}, B_1 .. B_{L-1}
+                    load_a(u, t_first);
+                    load_b(0);
+                    for (int j = 1; j < nt; ++j) load_a(u, t_first + j * T_ROWS);
+                    for (int p = 1; p < L; ++p) load_b(p);
                 }
             } else if (warp == C::W_MMA) {
                 // -------------------------------------------------------- MMA issuer
