@@ -216,10 +216,7 @@ def run_gpu(args):
             return
         ev[0].record(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
         es.accumulate(); ev[3].record()
-        es.reduce_transitions(group)
-        if group is not None:
-            dist.all_reduce(es.acc, group=group)
-            dist.all_reduce(es.tsum, group=group)
+        es.reduce_statistics(group)  # transition log-sum-exp + the two NCCL collectives
         es.mstep(c_covariance=1e-6)
         ev[4].record()
 

@@ -77,6 +77,11 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *host_n_frames,
                      pc_corpus *out);
 int pc_corpus_destroy(pc_corpus c);
 int64_t pc_corpus_total_frames(pc_corpus c);
+int64_t pc_corpus_total_tiles(pc_corpus c);
+/* (tile, unit) pairs the last pc_accumulate on this corpus actually contracted: pairs whose
+ * posteriors all vanish below the resolution of the kernel's fp16 P tile contribute exactly zero
+ * and are skipped (synchronises the device; diagnostics / bench accounting). */
+int64_t pc_corpus_active_tiles(pc_corpus c);
 int64_t pc_corpus_emission_floats(pc_corpus c); /* length of the b / lgam buffers */
 int64_t pc_corpus_total_pairs(pc_corpus c);     /* number of (utterance, label position) pairs */
 int64_t pc_corpus_total_states(pc_corpus c);    /* sum over utterances of 3L+2 */

@@ -54,6 +54,8 @@ _SIGS = {
                                    C.POINTER(C.c_void_p)]),
     "pc_corpus_destroy": (C.c_int, [C.c_void_p]),
     "pc_corpus_total_frames": (C.c_int64, [C.c_void_p]),
+    "pc_corpus_total_tiles": (C.c_int64, [C.c_void_p]),
+    "pc_corpus_active_tiles": (C.c_int64, [C.c_void_p]),
     "pc_corpus_emission_floats": (C.c_int64, [C.c_void_p]),
     "pc_corpus_total_pairs": (C.c_int64, [C.c_void_p]),
     "pc_corpus_total_states": (C.c_int64, [C.c_void_p]),

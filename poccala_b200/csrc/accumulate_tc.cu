@@ -12,7 +12,7 @@
 // K-major A operand of MMA1 (K = feature) and, through an MN-major descriptor over the same bytes,
 // as the A operand of MMA2 (M = feature, K = frame).  P (scaled by 2^15 to sit in the fp16 range)
 // is written by the softmax warps as the MN-major B operand of MMA2.  Work is UNIT-major so that
-// D2 stays in TMEM for a whole work item (<= 16 tiles of one unit) before one fp64-atomic flush.
+// D2 stays in TMEM for a whole work item (<= 32 tiles of one unit) before one fp64-atomic flush.
 //
 //   warp 19     TMA producer : per item the unit's Gaussian rows (B), per tile 20 x 2 KiB of frames
 //   warp 20     MMA issuer   : MMA1(i), then MMA2(i-1) (software pipelined), commits
@@ -20,6 +20,8 @@
 //                              exp2, hi/lo split, P tile
 //   warps 16-18 flush        : D2 (lane = feature) -> atomicAdd(double) into acc, once per item
 #include "tc_common.cuh"
+
+__device__ long long g_acc_dbg[8192];
 
 namespace {
 
@@ -129,7 +131,7 @@ template <int MIX>
 __global__ void __launch_bounds__(NTHREADS, 1)
 accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restrict__ W, int n_gauss,
                      const float *__restrict__ b, const float *__restrict__ lgam,
-                     const int32_t *__restrict__ active, double *__restrict__ acc) {
+                     const int32_t *__restrict__ active, double *__restrict__ acc, int dbg) {
     using C = Cfg<MIX>;
     extern __shared__ __align__(1024) uint8_t smem[];
     Bars *bars = reinterpret_cast<Bars *>(smem);
@@ -176,7 +178,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
         const int g0 = slice * C::NC;  // first Gaussian of the slice inside the unit
         const size_t gfirst = (size_t)unit * C::N_UNIT + g0;
         const int64_t lo = v.item_tile_lo[item], hi = v.item_tile_lo[item + 1];
-        // the item's active tiles as a bit mask (an item has at most 16 tiles); every warp forms the
+        // the item's active tiles as a bit mask (an item has at most 32 tiles); every warp forms the
         // same mask, so all roles skip the same tiles - and an item without any - consistently
         const uint32_t amask = __ballot_sync(0xffffffffu, lane < (int)(hi - lo) && __ldg(active + lo + lane) != 0);
         if (amask == 0u) {
@@ -224,8 +226,12 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                 if (i < n_tiles) {
                     const uint32_t n = n_tile_u + i;
                     const int slot = n % C::NA, sb = n & 1;
+                    const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n < 1000;
+                    if (rec) g_acc_dbg[n * 8 + 0] = clock64();
                     tc::mbar_wait(&bars->a_full[slot], (n / C::NA) & 1);
+                    if (rec) g_acc_dbg[n * 8 + 1] = clock64();
                     tc::mbar_wait(&bars->s_empty[sb], ((n >> 1) & 1) ^ 1);
+                    if (rec) g_acc_dbg[n * 8 + 2] = clock64();
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
                         const uint32_t d = tmem_base + sb * C::S_STRIDE;
@@ -253,7 +259,10 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     // MMA2 of tile i-1: D2[f, g] += sum_t A[t, f] * P[t, g]
                     const uint32_t n = n_tile_u + i - 1;
                     const int slot = n % C::NA, ps = n & 1;
+                    const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n < 1000;
+                    if (rec) g_acc_dbg[n * 8 + 3] = clock64();
                     tc::mbar_wait(&bars->p_full[ps], (n >> 1) & 1);
+                    if (rec) g_acc_dbg[n * 8 + 4] = clock64();
                     if (i == 1) tc::mbar_wait(&bars->d2_empty, (n_item & 1) ^ 1);  // previous flush done
                     tc::tc_fence_after();
                     if (tc::elect_one()) {
@@ -308,9 +317,12 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                         dl[s] = d;
                     }
                 }
+                const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && (warp & 7) == 0 && n < 1000;
+                if (rec) g_acc_dbg[n * 8 + 5] = clock64();
                 tc::mbar_wait(&bars->s_full[sb], (n >> 1) & 1);
                 tc::tc_fence_after();
                 tc::mbar_wait(&bars->p_empty[ps], ((n >> 1) & 1) ^ 1);
+                if (rec) g_acc_dbg[n * 8 + 6] = clock64();
                 const uint32_t taddr = tmem_base + sb * C::S_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
                 uint8_t *ph = p_s + ps * 2 * C::P_PIECE, *pl = ph + C::P_PIECE;
 #define PC_SOFTMAX(G0_, SC_)                                                              \
@@ -333,6 +345,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     tc::mbar_arrive(&bars->s_empty[sb]);
                     tc::mbar_arrive(&bars->p_full[ps]);
                 }
+                if (rec) g_acc_dbg[n * 8 + 7] = clock64();
             }
         } else if (warp < W_PROD) {
             // ------------------------------------------------------------ flush D2 (lane = feature)
@@ -382,13 +395,20 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
         PC_LAUNCH_CHECK();
         h->launches++;
     }
-    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc);
+    kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc,
+                                                 h->fb_variant);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
 }
 
 }  // namespace
+
+// block 0's per-tile clocks (option fb_variant & 32): MMA warp [0] start, [1] tile landed, [2] S buffer
+// free, [3] MMA1 issued / waiting for P, [4] P ready; softmax group [5] start, [6] S ready, [7] P written
+extern "C" int pc_debug_read_acc(long long *host_out, int n) {
+    return cudaMemcpyFromSymbol(host_out, g_acc_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
 
 bool accumulate_tc_supported(int mix) { return mix == 4 || mix == 8 || mix == 16 || mix == 32 || mix == 64; }
 

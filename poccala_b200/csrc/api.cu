@@ -145,39 +145,65 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
         std::vector<int64_t> cur(unit_pair_off.begin(), unit_pair_off.end() - 1);
         for (int64_t p = 0; p < n_pairs; ++p) sorted_pair[cur[labels[p]]++] = p;
     }
+    // K3 walks (tile, unit) pairs unit-major so that a unit's statistics stay in tensor memory, but
+    // every frame tile is then fetched once per label position.  The walk is therefore split into
+    // runs of consecutive utterances whose frame-tile images (40 KiB each) fit in a quarter of the
+    // L2 (PC_L2_RUN_BYTES): inside a run the re-reads hit L2 instead of HBM.
     std::vector<int64_t> tile_pair, tile_xrow, tile_boff, tile_xblk;
     std::vector<int32_t> tile_t0, tile_rows, tile_tp;
-    std::vector<int64_t> unit_tile_off(n_units + 1, 0);
-    for (int k = 0; k < n_units; ++k) {
-        for (int64_t i = unit_pair_off[k]; i < unit_pair_off[k + 1]; ++i) {
-            const int64_t p = sorted_pair[i];
-            const int u = pair_utt[p];
-            const int T = n_frames[u];
-            const int tp = pc_spad(n_labels[u]);
-            const int64_t pos = p - pair_off[u];
-            for (int t0 = 0; t0 < T; t0 += PC_TILE_ROWS) {
-                tile_pair.push_back(p);
-                tile_t0.push_back(t0);
-                tile_rows.push_back(std::min(PC_TILE_ROWS, T - t0));
-                tile_tp.push_back(tp);
-                tile_xrow.push_back(frame_off[u] + t0);
-                tile_xblk.push_back(xtile_off[u] + t0 / PC_TILE_ROWS);
-                tile_boff.push_back(emis_off[u] + (int64_t)t0 * tp + PC_EMIT * pos);
+    std::vector<int64_t> run_tile_off;  // first tile of each (run, unit) block, then n_tiles
+    {
+        std::vector<int> run_utt(1, 0);
+        int64_t bytes = 0;
+        for (int u = 0; u < n_utt; ++u) {
+            const int64_t add_b = (xtile_off[u + 1] - xtile_off[u]) * (int64_t)PC_XTILE_BYTES;
+            if (bytes > 0 && bytes + add_b > PC_L2_RUN_BYTES) {
+                run_utt.push_back(u);
+                bytes = 0;
+            }
+            bytes += add_b;
+        }
+        run_utt.push_back(n_utt);
+        const int n_runs = (int)run_utt.size() - 1;
+        // sorted_pair is stable: inside a unit the pairs are in utterance order, so each run is a
+        // contiguous slice of the unit's pair list
+        std::vector<int64_t> cur(unit_pair_off.begin(), unit_pair_off.end() - 1);
+        for (int r = 0; r < n_runs; ++r) {
+            for (int k = 0; k < n_units; ++k) {
+                run_tile_off.push_back((int64_t)tile_pair.size());
+                int64_t &i = cur[k];
+                for (; i < unit_pair_off[k + 1] && pair_utt[sorted_pair[i]] < run_utt[r + 1]; ++i) {
+                    const int64_t p = sorted_pair[i];
+                    const int u = pair_utt[p];
+                    const int T = n_frames[u];
+                    const int tp = pc_spad(n_labels[u]);
+                    const int64_t pos = p - pair_off[u];
+                    for (int t0 = 0; t0 < T; t0 += PC_TILE_ROWS) {
+                        tile_pair.push_back(p);
+                        tile_t0.push_back(t0);
+                        tile_rows.push_back(std::min(PC_TILE_ROWS, T - t0));
+                        tile_tp.push_back(tp);
+                        tile_xrow.push_back(frame_off[u] + t0);
+                        tile_xblk.push_back(xtile_off[u] + t0 / PC_TILE_ROWS);
+                        tile_boff.push_back(emis_off[u] + (int64_t)t0 * tp + PC_EMIT * pos);
+                    }
+                }
             }
         }
-        unit_tile_off[k + 1] = (int64_t)tile_pair.size();
+        run_tile_off.push_back((int64_t)tile_pair.size());
     }
     const int64_t n_tiles = (int64_t)tile_pair.size();
     // work items: runs of <= chunk tiles inside one unit; aim at >= 8 items per SM
     int64_t chunk = n_tiles / ((int64_t)h->sm_count * 8);
-    // <= 16 tiles: the accumulation kernel keeps an item's sums in fp32 (TMEM) before the fp64 flush
-    chunk = std::max<int64_t>(4, std::min<int64_t>(16, chunk));
+    // <= 32 tiles: the accumulation kernel keeps an item's sums in fp32 (TMEM) before the fp64 flush
+    // and addresses an item's tiles through a 32-bit activity mask (typically under half are active)
+    chunk = std::max<int64_t>(4, std::min<int64_t>(32, chunk));
     std::vector<int64_t> item_tile_lo;
     std::vector<int32_t> item_unit;
-    for (int k = 0; k < n_units; ++k)
-        for (int64_t lo = unit_tile_off[k]; lo < unit_tile_off[k + 1]; lo += chunk) {
+    for (size_t blk = 0; blk + 1 < run_tile_off.size(); ++blk)
+        for (int64_t lo = run_tile_off[blk]; lo < run_tile_off[blk + 1]; lo += chunk) {
             item_tile_lo.push_back(lo);
-            item_unit.push_back(k);
+            item_unit.push_back((int32_t)(blk % (size_t)n_units));
         }
     item_tile_lo.push_back(n_tiles);
     const int64_t n_items = (int64_t)item_unit.size();
@@ -347,6 +373,18 @@ int pc_corpus_destroy(pc_corpus c) {
     return PC_OK;
 }
 
+int64_t pc_corpus_active_tiles(pc_corpus c) {
+    if (!c) return -1;
+    std::vector<int32_t> a((size_t)c->v.n_tiles);
+    if (cudaSetDevice(c->h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(a.data(), c->v.tile_active, a.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    int64_t n = 0;
+    for (int32_t x : a) n += x != 0;
+    return n;
+}
+
+int64_t pc_corpus_total_tiles(pc_corpus c) { return c ? c->v.n_tiles : -1; }
 int64_t pc_corpus_total_frames(pc_corpus c) { return c ? c->total_frames : -1; }
 int64_t pc_corpus_emission_floats(pc_corpus c) { return c ? c->emis_floats : -1; }
 int64_t pc_corpus_total_pairs(pc_corpus c) { return c ? c->v.n_pairs : -1; }

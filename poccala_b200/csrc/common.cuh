@@ -15,6 +15,7 @@
 __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 #define PC_NEG_INF (-INFINITY)
+#define PC_L2_RUN_BYTES (32ll << 20)  // frame-tile images one K3 run of utterances may span (L2 = 126 MB)
 #define PC_MAX_CHUNKS 8  // host-buffer entry point: transfer / prepare / score pipeline depth
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).

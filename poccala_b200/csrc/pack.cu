@@ -32,65 +32,71 @@ __device__ __forceinline__ void split_h(float a, __half &hi, __half &lo) {
     lo = __float2half_rn(a - __half2float(hi));
 }
 
+// One warp per (unit, padded row); lane l owns elements l, l+32, l+64 of the 80-element row.
 __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *__restrict__ var,
                                 const double *__restrict__ alpha, const double *__restrict__ shift,
                                 const double *__restrict__ inv_scale, int n_gauss, int dim, int n_unit,
                                 float *__restrict__ W) {
     const int npad = (n_unit + 15) & ~15;
     const int n_units = n_gauss / n_unit;
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // (unit, padded row)
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);  // (unit, padded row)
     if (slot >= n_units * npad) return;
     const int unit = slot / npad, row = slot - unit * npad;
     uint8_t *img = reinterpret_cast<uint8_t *>(W) + pc_w16_offset(n_gauss) + (size_t)unit * 2 * (PC_KA / 8) * npad * 16;
+    uint8_t *grp = img + (size_t)(row >> 3) * PC_WGROUP_BYTES + (row & 7) * 16;
     if (row >= n_unit) {  // padding row of the operand image
-        for (int c = 0; c < 2 * (PC_KA / 8); ++c)
-            *reinterpret_cast<uint4 *>(img + (size_t)(row >> 3) * PC_WGROUP_BYTES + c * 128 + (row & 7) * 16) =
+        if (lane < 2 * (PC_KA / 8))
+            *reinterpret_cast<uint4 *>(grp + (lane / (PC_KA / 8)) * (PC_WGROUP_BYTES / 2) + (lane % (PC_KA / 8)) * 128) =
                 make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const int g = unit * n_unit + row;
     const double LOG_2PI = 1.8378770664093453;  // np.log(2*pi), util.py:14
-    float w[PC_KA];
-    double sum_var = 0.0, quad = 0.0;
-    for (int d = 0; d < PC_DIM_MAX; ++d) {
+    // per-dimension terms: lane handles d = lane and d = lane + 32
+    double wx[2] = {0.0, 0.0}, wq[2] = {0.0, 0.0}, sum_var = 0.0, quad = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int d = lane + 32 * h;
         if (d < dim) {
-            double mu = mean[(size_t)g * dim + d];
-            double v = var[(size_t)g * dim + d];
-            double sh = shift ? shift[d] : 0.0;
-            double is = inv_scale ? inv_scale[d] : 1.0;
-            double mu_s = (mu - sh) * is;
-            double v_s = v * is * is;
+            const double mu = mean[(size_t)g * dim + d];
+            const double v = var[(size_t)g * dim + d];
+            const double sh = shift ? shift[d] : 0.0;
+            const double is = inv_scale ? inv_scale[d] : 1.0;
+            const double mu_s = (mu - sh) * is;
+            const double v_s = v * is * is;
             sum_var += v;
             quad += mu_s * mu_s / v_s;
-            w[d] = (float)(mu_s / v_s);
-            w[PC_XS + d] = (float)(-0.5 / v_s);
-        } else {
-            w[d] = 0.f;
-            w[PC_XS + d] = 0.f;
+            wx[h] = (double)(float)(mu_s / v_s);
+            wq[h] = (double)(float)(-0.5 / v_s);
         }
     }
+    sum_var = warp_sum_d(sum_var);
+    quad = warp_sum_d(quad);
     const double k = log(alpha[g]) - 0.5 * dim * LOG_2PI - 0.5 * sum_var - 0.5 * quad;
     const float k_hi = (float)k;
     const float k_lo = isfinite(k) ? (float)(k - (double)k_hi) : 0.f;
-    w[PC_XS - 1] = k_hi;
-    w[PC_KA - 1] = k_lo;
-    float *wrow = W + (size_t)g * PC_KA;
-    for (int i = 0; i < PC_KA; ++i) wrow[i] = w[i];
-
-    // ---- fp16 operand image
-    float *scale = W + (size_t)n_gauss * PC_KA;
-    int *flags = reinterpret_cast<int *>(scale + n_gauss);
     const bool dead = !isfinite(k);
+    // the row's largest finite magnitude decides the power-of-two scale that fits it into fp16
     float mx = 0.f;
-    for (int i = 0; i < PC_KA; ++i) {
-        float a = fabsf(w[i]);
-        if (a <= 3.0e38f) mx = fmaxf(mx, a);
+    {
+        const float cand[6] = {(float)wx[0], (float)wx[1], (float)wq[0], (float)wq[1], k_hi, k_lo};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float a = fabsf(cand[i]);
+            if (a <= 3.0e38f) mx = fmaxf(mx, a);
+        }
+        mx = warp_max(mx);
     }
     int e = 0;
     if (mx > 16384.f) e = (int)((__float_as_uint(mx) >> 23) & 0xff) - 127 - 13;
     const double inv = ldexp(1.0, -e);
-    scale[g] = dead ? 1.f : (float)ldexp(1.0, e);
-    if (!dead && e != 0) atomicOr(flags, 1);
+    float *scale = W + (size_t)n_gauss * PC_KA;
+    int *flags = reinterpret_cast<int *>(scale + n_gauss);
+    if (lane == 0) {
+        scale[g] = dead ? 1.f : (float)ldexp(1.0, e);
+        if (!dead && e != 0) atomicOr(flags, 1);
+    }
     // the constant keeps 4 fp16 pieces: (hi, lo) of k in column 39, (hi, lo) of the rest in column 79
     __half k1h = __float2half_rn(-60000.f), k1l = __float2half_rn(0.f), k2h = k1l, k2l = k1l;
     if (!dead) {
@@ -103,23 +109,29 @@ __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *_
         r -= (double)__half2float(k2h);
         k2l = __float2half_rn((float)r);
     }
-    for (int c = 0; c < PC_KA / 8; ++c) {
-        __half hi[8], lo[8];
-        for (int j = 0; j < 8; ++j) {
-            const int i = 8 * c + j;
-            if (i == PC_XS - 1) {
-                hi[j] = k1h; lo[j] = k1l;
-            } else if (i == PC_KA - 1) {
-                hi[j] = k2h; lo[j] = k2l;
-            } else if (dead) {
-                hi[j] = lo[j] = __float2half_rn(0.f);
-            } else {
-                split_h((float)((double)w[i] * inv), hi[j], lo[j]);
-            }
+    float *wrow = W + (size_t)g * PC_KA;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int i = lane + 32 * t;  // element of the 80-element row
+        const bool valid = i < PC_KA;
+        const int ii = valid ? i : 0;
+        const int d = (ii < PC_XS) ? ii : ii - PC_XS;  // 39 for the two constant columns: a zero lane
+        // element d lives in lane d % 32, half d / 32 (all lanes take part in the shuffles)
+        const double vx0 = __shfl_sync(0xffffffffu, wx[0], d & 31), vx1 = __shfl_sync(0xffffffffu, wx[1], d & 31);
+        const double vq0 = __shfl_sync(0xffffffffu, wq[0], d & 31), vq1 = __shfl_sync(0xffffffffu, wq[1], d & 31);
+        const double vx = (d < 32) ? vx0 : vx1, vq = (d < 32) ? vq0 : vq1;
+        float wf = (d < dim) ? (float)((ii < PC_XS) ? vx : vq) : 0.f;  // fp32 row (CUDA-core kernels)
+        __half hi, lo;
+        if (dead) hi = lo = __float2half_rn(0.f);
+        else split_h((float)((double)wf * inv), hi, lo);
+        if (ii == PC_XS - 1) { wf = k_hi; hi = k1h; lo = k1l; }
+        if (ii == PC_KA - 1) { wf = k_lo; hi = k2h; lo = k2l; }
+        if (valid) {
+            wrow[i] = wf;
+            const int c = i >> 3, j = i & 7;
+            reinterpret_cast<__half *>(grp + c * 128)[j] = hi;
+            reinterpret_cast<__half *>(grp + PC_WGROUP_BYTES / 2 + c * 128)[j] = lo;
         }
-        uint8_t *grp = img + (size_t)(row >> 3) * PC_WGROUP_BYTES + (row & 7) * 16;
-        *reinterpret_cast<uint4 *>(grp + c * 128) = *reinterpret_cast<uint4 *>(hi);
-        *reinterpret_cast<uint4 *>(grp + PC_WGROUP_BYTES / 2 + c * 128) = *reinterpret_cast<uint4 *>(lo);
     }
 }
 
@@ -212,8 +224,8 @@ int launch_pack_gmm(pc_handle h, const double *mean, const double *var, const do
     const int n_unit = mix > 0 ? PC_EMIT * mix : n_gauss;  // mix = 0: flat list = one pseudo unit
     const int npad = (n_unit + 15) & ~15;
     const int slots = (n_gauss / n_unit) * npad;
-    const int threads = 64;
-    const int blocks = (slots + threads - 1) / threads;
+    const int threads = 128;  // one warp per slot
+    const int blocks = (int)(((int64_t)slots * 32 + threads - 1) / threads);
     PC_CUDA_TRY(cudaMemsetAsync(reinterpret_cast<char *>(W) + (size_t)n_gauss * 324, 0, sizeof(int), st));
     pack_gmm_kernel<<<blocks, threads, 0, st>>>(mean, var, alpha, shift, inv_scale, n_gauss, dim, n_unit, W);
     PC_LAUNCH_CHECK();

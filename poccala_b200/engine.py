@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
+from . import distributed as _dist
 from ._native import _p
 
 EMIT, STATES, XS, KA, SLOTS = nat.EMIT, nat.STATES, nat.XS, nat.KA, nat.TRANS_SLOTS
@@ -208,9 +209,12 @@ class EStep:
         self.utt_logp = e.empty((corpus.n_utt,), torch.float64)
         self.utt_iters = e.empty((corpus.n_utt,), torch.int32)
         self.pair_trans = e.empty((max(corpus.n_pairs, 1), SLOTS), torch.float32)
-        self.acc = e.empty((model.n_gauss, KA), torch.float64)
+        # linear GMM statistics and transition sums share one flat buffer: one allreduce(SUM)
+        n_acc = model.n_gauss * KA
+        self.flat = e.empty((n_acc + model.n_units * SLOTS,), torch.float64)
+        self.acc = self.flat[:n_acc].view(model.n_gauss, KA)
+        self.tsum = self.flat[n_acc:].view(model.n_units, SLOTS)
         self.tmax = e.empty((model.n_units, SLOTS), torch.float64)
-        self.tsum = e.empty((model.n_units, SLOTS), torch.float64)
         self.shift = None
         self.inv_scale = None
         self.standardise = standardise
@@ -247,28 +251,31 @@ class EStep:
         nat.call("pc_accumulate", self.engine.h, self.corpus.c, _p(self.corpus.X), _p(m.W), m.mix, _p(self.b),
                  _p(self.lgam), _p(self.acc), _stream())
 
-    def reduce_transitions(self, group=None):
+    def reduce_statistics(self, group=None):
+        """Per-unit log-sum-exp of the transition counts (pc_transitions_max / _sum) and, with a
+        process group, the two collectives of poccala_b200.distributed."""
         self.tmax.fill_(float("-inf"))
-        self.tsum.zero_()
         nat.call("pc_transitions_max", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
                  _p(self.tmax), _stream())
-        if group is not None:
-            torch.distributed.all_reduce(self.tmax, op=torch.distributed.ReduceOp.MAX, group=group)
-        nat.call("pc_transitions_sum", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
-                 _p(self.tmax), _p(self.tsum), _stream())
+
+        def local_sums():
+            self.tsum.zero_()
+            nat.call("pc_transitions_sum", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
+                     _p(self.tmax), _p(self.tsum), _stream())
+
+        _dist.allreduce_em_statistics(self.flat, self.tmax, local_sums, group)
+
+    reduce_transitions = reduce_statistics
 
     def estep(self, fix_code=0, group=None):
-        """K1 -> K2 -> K3 -> transition reduction (+ allreduce when `group` is a process group)."""
+        """K1 -> K2 -> K3 -> accumulator reduction (+ allreduce when `group` is a process group)."""
         self.score()
         self.forward_backward()
         if not (fix_code & 2):
             self.accumulate()
         else:
             self.acc.zero_()
-        self.reduce_transitions(group)
-        if group is not None:
-            torch.distributed.all_reduce(self.acc, group=group)
-            torch.distributed.all_reduce(self.tsum, group=group)
+        self.reduce_statistics(group)
 
     def mstep(self, c_covariance=1e-3, fix_code=0):
         m = self.model

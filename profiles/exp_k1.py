@@ -33,3 +33,4 @@ for flags in [int(a) for a in sys.argv[1:]] or [0]:
     eng.set_option("fb_variant", flags)
     print("flags", flags, "K1 us %.1f" % t_kernel(k1), "K3 us %.1f" % t_kernel(k3), flush=True)
 eng.set_option("fb_variant", 0)
+print("K3 active (tile, unit) pairs: %d of %d" % (nat.lib().pc_corpus_active_tiles(corpus.c), nat.lib().pc_corpus_total_tiles(corpus.c)))

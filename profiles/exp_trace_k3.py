@@ -1,0 +1,26 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, ctypes as C
+from poccala_b200 import synth, _native as nat
+from poccala_b200.engine import Corpus, Engine, EStep, Model
+N_UNITS, MIX, N_UTT, T, L = 57, 16, 1000, 300, 10
+eng = Engine(0)
+truth, init, labels, x = synth.torch_corpus(N_UTT, T, L, N_UNITS, MIX, 2, eng.device, 22)
+corpus = Corpus(eng, labels, np.full(N_UTT, T, dtype=np.int32), N_UNITS)
+model = Model(eng, *init, synth.default_transmat(N_UNITS))
+es = EStep(eng, corpus, model); es.load_frames(x); es.score(); es.forward_backward(); torch.cuda.synchronize()
+eng.set_option("fb_variant", 32)
+for _ in range(2): es.accumulate()
+torch.cuda.synchronize()
+buf = (C.c_longlong * 8000)()
+lib = nat.lib(); lib.pc_debug_read_acc.argtypes = [C.c_void_p, C.c_int]; lib.pc_debug_read_acc(buf, 8000)
+a = np.array(buf[:]).reshape(1000, 8)
+n = 80
+a = a[:n] - a[0, 0]
+np.set_printoptions(linewidth=220)
+print("cols: mma_start, tile_landed, S_free, MMA1_issued(wait P), P_ready | smx_start, S_ready, P_written")
+for i in range(0, 40): print(i, a[i])
+d = np.diff(a[:, 0])
+print("mean clk per tile (mma start to start): %.0f median %.0f" % (d.mean(), np.median(d)))
+print("mma: wait tile %.0f, wait S free %.0f, MMA1 issue+loop %.0f, wait P %.0f" % ((a[:,1]-a[:,0]).mean(), (a[:,2]-a[:,1]).mean(), (a[:,3]-a[:,2]).mean(), (a[:,4]-a[:,3]).mean()))
+print("softmax: wait S %.0f, work %.0f" % ((a[:,6]-a[:,5]).mean(), (a[:,7]-a[:,6]).mean()))
