@@ -43,21 +43,32 @@ constexpr float P_UNSHIFT = 1.f / 32768.f;
 // utterance) that is more than half of the tiles.
 constexpr float ACTIVE_MIN_LGAM = -41.f * 0.6931471805599453f;
 
-// one warp per unit-major tile: active[tile] = any(log gamma > ACTIVE_MIN_LGAM)
+// One warp per 128-frame tile of an utterance: coalesced rows of log gamma (lane = state column),
+// running maximum per column, then active[(tile, position)] = 1 where any of the position's states
+// exceeds ACTIVE_MIN_LGAM (the flags are zeroed by the launcher; NaN columns stay inactive).
 __global__ void tile_active_kernel(CorpusView v, const float *__restrict__ lgam, int32_t *__restrict__ active) {
-    const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t xt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (tile >= v.n_tiles) return;
-    const int rows = v.tile_rows[tile], tp = v.tile_tp[tile];
-    const float *base = lgam + v.tile_boff[tile];
-    float m = PC_NEG_INF;
-    for (int r = lane; r < rows; r += 32) {
-        const float *p = base + (size_t)r * tp;
-#pragma unroll
-        for (int s = 0; s < PC_EMIT; ++s) m = fmaxf(m, __ldg(p + s));
+    if (xt >= v.n_xtiles) return;
+    const int u = v.xtile_utt[xt], t0 = v.xtile_t0[xt];
+    const int T = (int)(v.frame_off[u + 1] - v.frame_off[u]);
+    const int64_t p0 = v.pair_off[u];
+    const int L = (int)(v.pair_off[u + 1] - p0);
+    const int sp = pc_spad(L), rows = min(PC_TILE_ROWS, T - t0);
+    const float *base = lgam + v.emis_off[u] + (size_t)t0 * sp;
+    for (int c = lane; c < PC_EMIT * L; c += 32) {
+        float m0 = PC_NEG_INF, m1 = PC_NEG_INF, m2 = PC_NEG_INF, m3 = PC_NEG_INF;
+        int r = 0;
+        for (; r + 3 < rows; r += 4) {
+            m0 = fmaxf(m0, __ldg(base + (size_t)r * sp + c));
+            m1 = fmaxf(m1, __ldg(base + (size_t)(r + 1) * sp + c));
+            m2 = fmaxf(m2, __ldg(base + (size_t)(r + 2) * sp + c));
+            m3 = fmaxf(m3, __ldg(base + (size_t)(r + 3) * sp + c));
+        }
+        for (; r < rows; ++r) m0 = fmaxf(m0, __ldg(base + (size_t)r * sp + c));
+        if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > ACTIVE_MIN_LGAM)
+            active[v.pair_tile0[p0 + c / PC_EMIT] + t0 / PC_TILE_ROWS] = 1;
     }
-    const bool any = __any_sync(0xffffffffu, m > ACTIVE_MIN_LGAM);  // NaN rows: kept out, they poison nothing
-    if (lane == 0) active[tile] = any ? 1 : 0;
 }
 
 // NC = Gaussians handled per work item (a unit's 3*MIX Gaussians, or a slice of them)
@@ -388,9 +399,10 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
     const int n_work = v.n_items * Cfg<MIX>::N_SLICES;
     const int grid = n_work < h->sm_count ? n_work : h->sm_count;
     {
-        const int64_t warps = v.n_tiles;
-        const int threads = 256;
+        const int64_t warps = v.n_xtiles;
+        const int threads = 128;
         const int64_t blocks = (warps * 32 + threads - 1) / threads;
+        PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)v.n_tiles * sizeof(int32_t), st));
         tile_active_kernel<<<(unsigned)blocks, threads, 0, st>>>(v, lgam, v.tile_active);
         PC_LAUNCH_CHECK();
         h->launches++;

@@ -152,6 +152,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     std::vector<int64_t> tile_pair, tile_xrow, tile_boff, tile_xblk;
     std::vector<int32_t> tile_t0, tile_rows, tile_tp;
     std::vector<int64_t> run_tile_off;  // first tile of each (run, unit) block, then n_tiles
+    std::vector<int64_t> pair_tile0(n_pairs, 0);
     {
         std::vector<int> run_utt(1, 0);
         int64_t bytes = 0;
@@ -178,6 +179,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
                     const int T = n_frames[u];
                     const int tp = pc_spad(n_labels[u]);
                     const int64_t pos = p - pair_off[u];
+                    pair_tile0[p] = (int64_t)tile_pair.size();
                     for (int t0 = 0; t0 < T; t0 += PC_TILE_ROWS) {
                         tile_pair.push_back(p);
                         tile_t0.push_back(t0);
@@ -275,6 +277,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_ttp = add(tile_tp.data(), (size_t)n_tiles * 4);
     size_t o_txrow = add(tile_xrow.data(), (size_t)n_tiles * 8);
     size_t o_tboff = add(tile_boff.data(), (size_t)n_tiles * 8);
+    size_t o_pt0 = add(pair_tile0.data(), (size_t)n_pairs * 8);
     size_t o_ilo = add(item_tile_lo.data(), item_tile_lo.size() * 8);
     size_t o_iunit = add(item_unit.data(), (size_t)n_items * 4);
     size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 16);  // float4 per frame (K2)
@@ -337,6 +340,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     v.tile_tp = (const int32_t *)(dev + o_ttp);
     v.tile_xrow = (const int64_t *)(dev + o_txrow);
     v.tile_boff = (const int64_t *)(dev + o_tboff);
+    v.pair_tile0 = (const int64_t *)(dev + o_pt0);
     v.item_tile_lo = (const int64_t *)(dev + o_ilo);
     v.item_unit = (const int32_t *)(dev + o_iunit);
     v.scratch0 = (float *)(dev + o_scratch);

@@ -43,6 +43,7 @@ struct CorpusView {
     const int32_t *tile_tp;      // [n_tiles] frame stride SP (floats) of the utterance's b / lgam block
     const int64_t *tile_xrow;    // [n_tiles] first row of the tile in X
     const int64_t *tile_boff;    // [n_tiles] float offset of (frame t0, state 0 of the pair) in b / lgam
+    const int64_t *pair_tile0;   // [n_pairs] first unit-major tile of the pair (its tiles are consecutive)
     const int64_t *item_tile_lo;  // [n_items+1] tile range of each work item (one unit per item)
     const int32_t *item_unit;     // [n_items]
     float *scratch0;              // [total_frames] float4 per frame (K2 scratch: beta_hat of the entry state)
