@@ -195,7 +195,7 @@ def run_gpu(args):
     tm0 = synth.default_transmat(N_UNITS)
     model = Model(eng, init0[0], init0[1], init0[2], tm0)
     es = EStep(eng, corpus, model)
-    es.load_frames(x)
+    es.load_frames(x, group=group)  # corpus-wide standardisation: identical on every rank
     frames = corpus.total_frames
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 

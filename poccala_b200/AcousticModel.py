@@ -253,7 +253,7 @@ class AcousticModel(object):
         self.__estep = None
         return self.__corpus
 
-    def _ensure_estep(self):
+    def _ensure_estep(self, group=None):
         if self.__corpus is None:
             raise RuntimeError("add_corpus(labels, data) first")
         if self.__model is None:
@@ -261,7 +261,7 @@ class AcousticModel(object):
             self.__estep = None
         if self.__estep is None:
             self.__estep = _eng.EStep(self.engine, self.__corpus, self.__model)
-            self.__estep.load_frames(self.__frames)
+            self.__estep.load_frames(self.__frames, group=group)
         return self.__estep
 
     def embedded_training(self, wwt_units=None, init=True, load_line=0, fix_code=0, show_q=False, show_a=False,
@@ -270,7 +270,7 @@ class AcousticModel(object):
         `group`: torch.distributed process group - every rank holds its own shard of the
         utterances and the accumulators are allreduced (the reference merges accumulator files
         from all machines, LHMM.py:256-290)."""
-        es = self._ensure_estep()
+        es = self._ensure_estep(group)
         es.em_iteration(c_covariance=c_covariance, fix_code=fix_code, group=group)
         mean, var, alpha, tm = self.__model.numpy()
         keep = None if wwt_units is None else set(wwt_units)

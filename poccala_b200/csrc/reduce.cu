@@ -64,6 +64,10 @@ __global__ void update_gmm_kernel(int n_units, int mix, int dim, const double *_
     if (!(socc > 0.0)) return;  // unseen state: parameters stay (deviation D1)
     const double *a = acc + (size_t)g * PC_KA;
     double occ = a[PC_XS - 1];
+    if (!(occ > 0.0)) {  // component without any posterior mass: weight 0, mean / variance stay (D1)
+        if (d == 0) alpha[g] = 0.0;
+        return;
+    }
     double sx = a[d], sxx = a[PC_XS + d];
     double sh = shift ? shift[d] : 0.0;
     double is = inv_scale ? inv_scale[d] : 1.0;

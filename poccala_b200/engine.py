@@ -220,14 +220,26 @@ class EStep:
         self.standardise = standardise
 
     # frames -------------------------------------------------------------------------------
-    def load_frames(self, x):
-        """x: [F,D] float tensor on the device (utterances concatenated in corpus order)."""
+    def load_frames(self, x, group=None, shift=None, inv_scale=None):
+        """x: [F,D] float tensor on the device (utterances concatenated in corpus order).
+        Standardisation uses the per-dimension mean / std of the WHOLE corpus: with a process group
+        the moments are allreduced first, so every rank maps its frames (and therefore its
+        accumulators, which live in the standardised space) the same way.  `shift` / `inv_scale`
+        override the statistics (fp64 device tensors [D])."""
         if x.shape[0] != self.corpus.total_frames:
             raise ValueError("expected %d frames, got %d" % (self.corpus.total_frames, x.shape[0]))
-        if self.standardise:
+        if shift is not None:
+            self.shift, self.inv_scale = shift.contiguous(), inv_scale.contiguous()
+        elif self.standardise:
             xd = x.to(torch.float64)
-            mu = xd.mean(dim=0)
-            sd = xd.std(dim=0, unbiased=False).clamp_min(1e-12)
+            mom = torch.cat([xd.sum(dim=0), (xd * xd).sum(dim=0),
+                             torch.full((1,), float(x.shape[0]), dtype=torch.float64, device=x.device)])
+            if group is not None:
+                torch.distributed.all_reduce(mom, group=group)
+            D = x.shape[1]
+            n = mom[-1]
+            mu = mom[:D] / n
+            sd = (mom[D:2 * D] / n - mu * mu).clamp_min(0.0).sqrt().clamp_min(1e-12)
             self.shift = mu.contiguous()
             self.inv_scale = (1.0 / sd).contiguous()
         self.corpus.X = self.engine.prepare_frames(self.corpus, x, self.shift, self.inv_scale, out=self.corpus.X)
