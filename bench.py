@@ -277,6 +277,7 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     pk, pk_src = peaks()
+    vit = viterbi_leg(eng, pk)
     # dominant kernel and its roofline: K1/K3 are contractions, 158 flops per
     # (frame, Gaussian) pair; K2 moves 8 B per (emitting state, frame)
     pairs = frames * 3 * L * MIX
@@ -313,12 +314,70 @@ def run_gpu(args):
                 "steps": e2e_steps, "api": "pc_em_iteration_host"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "viterbi": vit,
         "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d utterances x %d frames of the same workload (E-step), %.1f s" % (n_sample, T, cpu_wall)},
     }
     print(json.dumps(line), flush=True)
     if group is not None:
         dist.destroy_process_group()
+
+
+def viterbi_leg(eng, pk, n_utt=2000, T_v=1000, L_v=20, reps=5):
+    """Second half of BASELINE.json's metric: Viterbi forced alignment frames/s on the configs[3]
+    shape (1000-frame utterances against 20 concatenated IF unit HMMs, N = 62 states, 16-mix
+    emissions scored by K1), 2 000 utterances per GPU, emissions resident in HBM.  HBM roofline:
+    4 B per (emitting state, frame) read + 4 B per frame written."""
+    import torch
+
+    from poccala_b200 import synth
+    from poccala_b200.engine import Corpus, EStep, Model, host_log_bands, viterbi
+
+    dev = eng.device
+    truth, init0, labels, x = synth.torch_corpus(n_utt, T_v, L_v, N_UNITS, MIX, 4, dev, N_INITIALS)
+    corpus = Corpus(eng, labels, np.full(n_utt, T_v, dtype=np.int32), N_UNITS)
+    tm0 = synth.default_transmat(N_UNITS)
+    model = Model(eng, init0[0], init0[1], init0[2], tm0)
+    es = EStep(eng, corpus, model)
+    es.load_frames(x)
+    es.score()
+    ls, ln = host_log_bands(tm0, dev)
+    n_states = 3 * L_v + 2
+    logpi = torch.full((n_utt,), float(np.log(np.ones(n_states) / n_states)[0]), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        viterbi(eng, corpus, es.b, ls, ln, utt_logpi=logpi)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        score, path, units = viterbi(eng, corpus, es.b, ls, ln, utt_logpi=logpi)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = statistics.mean(ms) * 1e-3
+    frames = n_utt * T_v
+    bytes_alg = 4.0 * frames * 3 * L_v + 4.0 * frames
+    ach = bytes_alg / t / 1e9
+    if os.environ.get("PC_TRACE"):
+        import ctypes as C
+        from poccala_b200 import _native as nat
+        buf = (C.c_longlong * 8)()
+        nat.lib().pc_debug_read_vit.argtypes = [C.c_void_p]
+        nat.lib().pc_debug_read_vit(buf)
+        print("viterbi block 0: recurrence %d clk, traceback %d clk" % (buf[1] - buf[0], buf[2] - buf[1]), file=sys.stderr)
+    # sanity: every path is a monotone walk
+    p = path.view(n_utt, T_v)
+    d = p[:, 1:] - p[:, :-1]
+    ok = bool(((d == 0) | (d == 1)).all().item())
+    return {"value": frames / t, "unit": "frames/s", "ms": t * 1e3,
+            "workload": "cfg4 shape: %d utt x %d frames x %d units (N=%d), 16-mix emissions, bit-exact fp64 recurrence"
+                        % (n_utt, T_v, L_v, n_states),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
+                         "frac": ach / float(pk["hbm_gbs"])},
+            "paths_monotone": ok}
 
 
 def main():

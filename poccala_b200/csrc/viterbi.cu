@@ -11,6 +11,8 @@
 // implementations trace state 0, so one bit per cell is enough.
 #include "common.cuh"
 
+__device__ long long g_vit_dbg[8];
+
 template <int SPL, typename E>
 __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
                                const double *__restrict__ log_self,
@@ -64,33 +66,62 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
         double e0 = kind[q] == 1 ? (double)bu[row[q]] : (kind[q] == 0 ? 0.0 : NINF);  // frame 0
         p[q] = (kind[q] == 2) ? NINF : lpi + e0;
     }
+    const bool trace = blockIdx.x == 0 && threadIdx.x == 0;
+    if (trace) g_vit_dbg[0] = clock64();
     uint32_t bits[SPL];
 #pragma unroll
     for (int q = 0; q < SPL; ++q) bits[q] = 0u;
-    for (int t = 1; t < T; ++t) {
-        double left = __shfl_up_sync(0xffffffffu, p[SPL - 1] + ln[SPL - 1], 1);
-        if (lane == 0) left = NINF;
-        double np_[SPL];
+    // emission rows are fetched VT_CH frames ahead of the recurrence (they do not depend on it):
+    // without the prefetch every step waited for its own global load (~1 350 clk per frame)
+    constexpr int VT_CH = (SPL <= 2) ? 16 : 8;
+    auto load_rows = [&](int t0, E (&e)[VT_CH][SPL]) {
 #pragma unroll
-        for (int q = 0; q < SPL; ++q) {
-            const double move = (q > 0) ? p[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
-            const double stay = p[q] + ls[q];
-            const bool take = move >= stay;  // tie -> lower index (j-1)
-            const double best = take ? move : stay;
-            const double e = kind[q] == 1 ? (double)bu[(int64_t)t * sp + row[q]] : (kind[q] == 0 ? 0.0 : NINF);
-            np_[q] = (kind[q] == 2) ? NINF : best + e;
-            bits[q] |= (take ? 1u : 0u) << (t & 31);
+        for (int k = 0; k < VT_CH; ++k) {
+            const int t = min(t0 + k, T - 1);
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) e[k][q] = (kind[q] == 1) ? bu[(int64_t)t * sp + row[q]] : (E)0;
         }
+    };
+    E e_nxt[VT_CH][SPL];
+    load_rows(1, e_nxt);
+    for (int t0 = 1; t0 < T; t0 += VT_CH) {
+        E e_cur[VT_CH][SPL];
 #pragma unroll
-        for (int q = 0; q < SPL; ++q) p[q] = np_[q];
-        if ((t & 31) == 31 || t == T - 1) {
+        for (int k = 0; k < VT_CH; ++k) {
 #pragma unroll
-            for (int q = 0; q < SPL; ++q) {
-                bp[((t >> 5) * SPL + q) * 32 + lane] = bits[q];
-                bits[q] = 0u;
+            for (int q = 0; q < SPL; ++q) e_cur[k][q] = e_nxt[k][q];
+        }
+        load_rows(t0 + VT_CH, e_nxt);
+#pragma unroll
+        for (int k = 0; k < VT_CH; ++k) {
+            const int t = t0 + k;
+            if (t < T) {
+                double left = __shfl_up_sync(0xffffffffu, p[SPL - 1] + ln[SPL - 1], 1);
+                if (lane == 0) left = NINF;
+                double np_[SPL];
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) {
+                    const double move = (q > 0) ? p[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
+                    const double stay = p[q] + ls[q];
+                    const bool take = move >= stay;  // tie -> lower index (j-1)
+                    const double best = take ? move : stay;
+                    const double e = kind[q] == 1 ? (double)e_cur[k][q] : (kind[q] == 0 ? 0.0 : NINF);
+                    np_[q] = (kind[q] == 2) ? NINF : best + e;
+                    bits[q] |= (take ? 1u : 0u) << (t & 31);
+                }
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) p[q] = np_[q];
+                if ((t & 31) == 31 || t == T - 1) {
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) {
+                        bp[((t >> 5) * SPL + q) * 32 + lane] = bits[q];
+                        bits[q] = 0u;
+                    }
+                }
             }
         }
     }
+    if (trace) g_vit_dbg[1] = clock64();
     if (T == 1) {
 #pragma unroll
         for (int q = 0; q < SPL; ++q) bp[q * 32 + lane] = 0u;
@@ -113,26 +144,45 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
     }
     if (best_s == 0x7fffffff) best_s = 0;  // every score -inf: np.where(p == max)[0][0] == 0
     if (lane == 0) score[u] = best;
-    // traceback (every lane follows the same chain; lane t%32 keeps state t, stores are coalesced)
+    // traceback, 32 frames at a time: every lane follows the same chain; the block's backpointer words
+    // sit in registers (lane l holds the words of its own states) and the one for the current state
+    // comes by shuffle; lane k keeps the state of frame 32*blk + k, so the stores are coalesced
     int cur = best_s;
-    int keep = 0;
-    for (int t = T - 1; t >= 0; --t) {
-        if ((t & 31) == lane) keep = cur;
-        if ((t & 31) == 0) {
-            const int tt = t + lane;
-            if (tt < T) {
-                path[f0 + tt] = keep;
-                if (unit_path) {
-                    const int pos = keep == 0 ? 0 : (keep > NE ? L - 1 : (keep - 1) / PC_EMIT);
-                    unit_path[f0 + tt] = v.labels[p0 + pos];
+    for (int blk = (T - 1) >> 5; blk >= 0; --blk) {
+        uint32_t w[SPL];
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) w[q] = bp[(blk * SPL + q) * 32 + lane];
+        const int t_lo = blk * 32, t_hi = min(T - 1, t_lo + 31);
+        int keep = 0;
+#pragma unroll
+        for (int k = 31; k >= 0; --k) {
+            const int t = t_lo + k;
+            if (t <= t_hi) {  // warp-uniform
+                if (k == lane) keep = cur;
+                if (t > 0) {
+                    uint32_t wsel = w[0];
+#pragma unroll
+                    for (int q = 1; q < SPL; ++q) wsel = ((cur % SPL) == q) ? w[q] : wsel;
+                    const uint32_t wb = __shfl_sync(0xffffffffu, wsel, cur / SPL);
+                    cur -= (int)((wb >> k) & 1u);
                 }
             }
         }
-        if (t > 0) {
-            const uint32_t wbits = bp[((t >> 5) * SPL + (cur % SPL)) * 32 + (cur / SPL)];
-            cur -= (int)((wbits >> (t & 31)) & 1u);
+        const int tt = t_lo + lane;
+        if (tt <= t_hi) {
+            path[f0 + tt] = keep;
+            if (unit_path) {
+                const int pos = keep == 0 ? 0 : (keep > NE ? L - 1 : (keep - 1) / PC_EMIT);
+                unit_path[f0 + tt] = v.labels[p0 + pos];
+            }
         }
     }
+    if (trace) g_vit_dbg[2] = clock64();
+}
+
+// block 0 clocks: [0] start, [1] recurrence done, [2] traceback done (tuning aid)
+extern "C" int pc_debug_read_vit(long long *host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_vit_dbg, sizeof(long long) * 8) == cudaSuccess ? 0 : -2;
 }
 
 template <int SPL, typename E>
