@@ -142,6 +142,12 @@ int pc_forward_backward(pc_handle h, pc_corpus c, const float *dev_b, const doub
                         const double *dev_log_next, float *dev_lgam, double *dev_utt_logp,
                         int32_t *dev_utt_iters, float *dev_pair_trans, void *stream);
 
+/* log of the diagonal / super-diagonal of every unit transmat [n_units][5][5] -> [n_units][5] each
+ * (np.log(transmat) of LHMM.py:340,358 restricted to the two bands; the bit-exact Viterbi path takes
+ * host-computed logs instead). */
+int pc_log_bands(pc_handle h, const double *dev_transmat, int32_t n_units, double *dev_log_self,
+                 double *dev_log_next, void *stream);
+
 /* ---- K3: Baum-Welch accumulation -----------------------------------------------------------
  * LHMM.update_acc -> Clustering.GMM.update_acc (LHMM.py:473-507, Clustering.py:653-680) in the
  * linear-equivalent form of SURVEY A.4: acc[g] += sum_t gamma_t(j,m) * [x, x^2, 1, 1].

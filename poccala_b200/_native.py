@@ -70,6 +70,7 @@ _SIGS = {
     "pc_gmm_score_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p]),
     "pc_forward_backward": (C.c_int, [C.c_void_p] * 10),
+    "pc_log_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pc_accumulate": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 4),
     "pc_transitions_max": (C.c_int, [C.c_void_p] * 6),
     "pc_transitions_sum": (C.c_int, [C.c_void_p] * 7),

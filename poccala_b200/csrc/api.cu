@@ -585,6 +585,18 @@ __global__ void log_bands_kernel(const double *transmat, int n_units, double *lo
     log_next[i] = (s + 1 < PC_STATES) ? log(row[s + 1]) : -INFINITY;
 }
 
+int pc_log_bands(pc_handle h, const double *transmat, int32_t n_units, double *log_self, double *log_next,
+                 void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n_units >= 0 && (n_units == 0 || (transmat && log_self && log_next)), "pc_log_bands: bad arguments");
+    if (n_units == 0) return PC_OK;
+    log_bands_kernel<<<(n_units * PC_STATES + 127) / 128, 128, 0, (cudaStream_t)stream>>>(transmat, n_units, log_self,
+                                                                                         log_next);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
 __global__ void sum_double_kernel(const double *p, int n, double *out) {
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += 32) s += p[i];
@@ -657,13 +669,10 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     PC_CUDA_TRY(cudaMemcpyAsync(alpha, host_alpha, (size_t)G * 8, cudaMemcpyHostToDevice, st));
     PC_CUDA_TRY(cudaMemcpyAsync(tm, host_transmat, (size_t)n_units * 25 * 8, cudaMemcpyHostToDevice, st));
     PC_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)G * PC_KA * 8, st));
-    PC_CUDA_TRY(cudaMemsetAsync(tsum, 0, (size_t)n_units * PC_TRANS_SLOTS * 8, st));
     {
-        int n = n_units * PC_TRANS_SLOTS;
-        fill_double_kernel<<<(n + 255) / 256, 256, 0, st>>>(tmax, n, -INFINITY);
         log_bands_kernel<<<(n_units * PC_STATES + 127) / 128, 128, 0, st>>>(tm, n_units, ls, ln);
         PC_LAUNCH_CHECK();
-        h->launches += 2;
+        h->launches += 1;
     }
     if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, mix, W, st))) return rc;
     const bool tc_score = h->use_tc && score_tc_supported(mix);

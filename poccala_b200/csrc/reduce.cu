@@ -10,42 +10,81 @@
 // from the linear statistics.
 #include "common.cuh"
 
-__device__ __forceinline__ void atomic_max_double(double *addr, double val) {
-    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
-    unsigned long long old = *a;
-    while (true) {
-        double cur = __longlong_as_double((long long)old);
-        if (!(val > cur)) return;
-        unsigned long long prev = atomicCAS(a, old, (unsigned long long)__double_as_longlong(val));
-        if (prev == old) return;
-        old = prev;
+// One block per unit: the unit's (utterance, position) pairs are contiguous in the unit-major pair
+// list, so the per-slot maximum and the per-slot sum of exp(value - max) are plain block
+// reductions - no atomics, and a fixed summation order (replicas of a rank's partial sums are
+// reproducible run to run).
+#define TR_THREADS 128
+
+__device__ __forceinline__ double block_reduce(double v, bool is_max, double *sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmax(v, other) : v + other;
+    }
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double r = sh[0];
+    for (int w = 1; w < TR_THREADS / 32; ++w) r = is_max ? fmax(r, sh[w]) : r + sh[w];
+    return r;
+}
+
+__global__ void __launch_bounds__(TR_THREADS)
+transitions_max_kernel(CorpusView v, const double *__restrict__ utt_logp,
+                       const float *__restrict__ pair_trans, double *tmax) {
+    __shared__ double sh[TR_THREADS / 32];
+    const int unit = blockIdx.x;
+    const int64_t lo = v.unit_pair_off[unit], hi = v.unit_pair_off[unit + 1];
+    double m[PC_TRANS_SLOTS];
+#pragma unroll
+    for (int s = 0; s < PC_TRANS_SLOTS; ++s) m[s] = -INFINITY;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += TR_THREADS) {
+        const int64_t pair = v.sorted_pair[i];
+        const double lp = utt_logp[v.pair_utt[pair]];
+#pragma unroll
+        for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
+            const double val = lp + (double)pair_trans[pair * PC_TRANS_SLOTS + s];
+            if (val > m[s]) m[s] = val;  // NaN and -inf never win
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
+        const double r = block_reduce(m[s], true, sh);
+        if (threadIdx.x == 0) tmax[(size_t)unit * PC_TRANS_SLOTS + s] = r;
     }
 }
 
-__global__ void transitions_max_kernel(CorpusView v, const double *__restrict__ utt_logp,
-                                       const float *__restrict__ pair_trans, double *tmax) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (pair, slot)
-    if (i >= v.n_pairs * PC_TRANS_SLOTS) return;
-    int64_t pair = i / PC_TRANS_SLOTS;
-    int slot = (int)(i - pair * PC_TRANS_SLOTS);
-    double val = utt_logp[v.pair_utt[pair]] + (double)pair_trans[i];
-    if (val == -INFINITY || isnan(val)) return;
-    atomic_max_double(tmax + (size_t)v.labels[pair] * PC_TRANS_SLOTS + slot, val);
-}
-
-__global__ void transitions_sum_kernel(CorpusView v, const double *__restrict__ utt_logp,
-                                       const float *__restrict__ pair_trans,
-                                       const double *__restrict__ tmax, double *tsum) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= v.n_pairs * PC_TRANS_SLOTS) return;
-    int64_t pair = i / PC_TRANS_SLOTS;
-    int slot = (int)(i - pair * PC_TRANS_SLOTS);
-    double val = utt_logp[v.pair_utt[pair]] + (double)pair_trans[i];
-    if (val == -INFINITY || isnan(val)) return;
-    size_t o = (size_t)v.labels[pair] * PC_TRANS_SLOTS + slot;
-    double m = tmax[o];
-    double e = exp(val - m);
-    if (e > 0.0) atomicAdd(tsum + o, e);
+__global__ void __launch_bounds__(TR_THREADS)
+transitions_sum_kernel(CorpusView v, const double *__restrict__ utt_logp,
+                       const float *__restrict__ pair_trans, const double *__restrict__ tmax,
+                       double *tsum) {
+    __shared__ double sh[TR_THREADS / 32];
+    const int unit = blockIdx.x;
+    const int64_t lo = v.unit_pair_off[unit], hi = v.unit_pair_off[unit + 1];
+    double acc[PC_TRANS_SLOTS], mx[PC_TRANS_SLOTS];
+#pragma unroll
+    for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
+        acc[s] = 0.0;
+        mx[s] = tmax[(size_t)unit * PC_TRANS_SLOTS + s];
+    }
+    for (int64_t i = lo + threadIdx.x; i < hi; i += TR_THREADS) {
+        const int64_t pair = v.sorted_pair[i];
+        const double lp = utt_logp[v.pair_utt[pair]];
+#pragma unroll
+        for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
+            const double val = lp + (double)pair_trans[pair * PC_TRANS_SLOTS + s];
+            if (val == -INFINITY || isnan(val)) continue;
+            const double e = exp(val - mx[s]);
+            if (e > 0.0) acc[s] += e;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
+        const double r = block_reduce(acc[s], false, sh);
+        if (threadIdx.x == 0) tsum[(size_t)unit * PC_TRANS_SLOTS + s] = r;
+    }
 }
 
 // One thread per (gaussian, dimension); GMM part of the M-step.
@@ -100,9 +139,8 @@ __global__ void update_transmat_kernel(int n_units, const double *__restrict__ t
 
 int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_logp,
                            const float *pair_trans, double *tmax, cudaStream_t st) {
-    int64_t n = v.n_pairs * PC_TRANS_SLOTS;
-    if (n == 0) return PC_OK;
-    transitions_max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, utt_logp, pair_trans, tmax);
+    if (v.n_units == 0) return PC_OK;
+    transitions_max_kernel<<<v.n_units, TR_THREADS, 0, st>>>(v, utt_logp, pair_trans, tmax);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -111,10 +149,8 @@ int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_l
 int launch_transitions_sum(pc_handle h, const CorpusView &v, const double *utt_logp,
                            const float *pair_trans, const double *tmax, double *tsum,
                            cudaStream_t st) {
-    int64_t n = v.n_pairs * PC_TRANS_SLOTS;
-    if (n == 0) return PC_OK;
-    transitions_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, utt_logp, pair_trans, tmax,
-                                                                        tsum);
+    if (v.n_units == 0) return PC_OK;
+    transitions_sum_kernel<<<v.n_units, TR_THREADS, 0, st>>>(v, utt_logp, pair_trans, tmax, tsum);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

@@ -187,11 +187,11 @@ class Model:
 
     def log_bands(self):
         """log of the diagonal / super-diagonal of every unit transmat, [U,5] each (device, fp64)."""
-        with np.errstate(divide="ignore"):
-            ls = torch.log(torch.diagonal(self.transmat, dim1=1, dim2=2)).contiguous()
-            ln = torch.full_like(ls, float("-inf"))
-            ln[:, :-1] = torch.log(torch.diagonal(self.transmat, offset=1, dim1=1, dim2=2))
-        return ls, ln.contiguous()
+        if not hasattr(self, "_ls"):
+            self._ls = self.engine.empty((self.n_units, STATES), torch.float64)
+            self._ln = self.engine.empty((self.n_units, STATES), torch.float64)
+        nat.call("pc_log_bands", self.engine.h, _p(self.transmat), self.n_units, _p(self._ls), _p(self._ln), _stream())
+        return self._ls, self._ln
 
     def numpy(self):
         return (self.mean.cpu().numpy(), self.var.cpu().numpy(), self.alpha.cpu().numpy(),
@@ -266,12 +266,10 @@ class EStep:
     def reduce_statistics(self, group=None):
         """Per-unit log-sum-exp of the transition counts (pc_transitions_max / _sum) and, with a
         process group, the two collectives of poccala_b200.distributed."""
-        self.tmax.fill_(float("-inf"))
         nat.call("pc_transitions_max", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
-                 _p(self.tmax), _stream())
+                 _p(self.tmax), _stream())  # writes every (unit, slot): -inf where the unit has no pair
 
         def local_sums():
-            self.tsum.zero_()
             nat.call("pc_transitions_sum", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
                      _p(self.tmax), _p(self.tsum), _stream())
 
