@@ -97,6 +97,8 @@ struct Bars {
     uint64_t p_full[2], p_empty[2];
     uint64_t d2_full, d2_empty;
     uint32_t tmem_base;
+    // per P buffer and lane quarter: which of the quarter's two 16-frame K-steps carry posterior mass
+    uint8_t kact[2][4];
 };
 
 // S (TMEM, one frame per thread) -> P = 2^15 * exp(S*scale + lgam - b) -> fp16 hi / lo rows of the
@@ -276,6 +278,13 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     if (rec) g_acc_dbg[n * 8 + 4] = clock64();
                     if (i == 1) tc::mbar_wait(&bars->d2_empty, (n_item & 1) ^ 1);  // previous flush done
                     tc::tc_fence_after();
+                    // active 16-frame K-steps of this tile (2 bits per lane quarter)
+                    uint32_t kmask;
+                    {
+                        const uint32_t w = *reinterpret_cast<const volatile uint32_t *>(&bars->kact[ps][0]);
+                        kmask = (w & 3u) | (((w >> 8) & 3u) << 2) | (((w >> 16) & 3u) << 4) | (((w >> 24) & 3u) << 6);
+                        kmask = __reduce_or_sync(0xffffffffu, kmask);
+                    }
                     if (tc::elect_one()) {
                         const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                         const uint32_t ph = p_base + ps * 2 * C::P_PIECE, pl = ph + C::P_PIECE;
@@ -286,6 +295,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                             const uint32_t pp = (q == 2) ? pl : ph;
 #pragma unroll
                             for (int k = 0; k < T_ROWS / 16; ++k) {
+                                if (!((kmask >> k) & 1u)) continue;
                                 // MN-major views: 8 frames x 16 B core matrices; LBO = 128 B between
                                 // 8-frame groups, SBO = 2048 B between 8-feature / 8-Gaussian blocks
                                 const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
@@ -316,6 +326,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                 const int tp = v.tile_tp[tile];
                 // d = (lgam - b) * log2(e) + 15 for the unit's three states; -inf kills the row
                 float dl[PC_EMIT];
+                bool row_act = false;
                 {
                     const size_t o = (size_t)v.tile_boff[tile] + (size_t)r * tp;
 #pragma unroll
@@ -324,10 +335,15 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                         if (r < rows) {
                             const float lg = __ldg(lgam + o + s), bb = __ldg(b + o + s);
                             d = (lg == PC_NEG_INF) ? PC_NEG_INF : fmaf(lg - bb, LOG2E, P_SHIFT);
+                            row_act = row_act || lg > ACTIVE_MIN_LGAM;
                         }
                         dl[s] = d;
                     }
                 }
+                // 16-frame K-steps of MMA2 whose frames all lack posterior mass have an exactly zero P
+                // block (same argument as for whole tiles): the MMA warp skips them, and a warp whose
+                // 32 frames are all dead does not form its part of P at all
+                const uint32_t ract = __ballot_sync(0xffffffffu, row_act);
                 const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && (warp & 7) == 0 && n < 1000;
                 if (rec) g_acc_dbg[n * 8 + 5] = clock64();
                 tc::mbar_wait(&bars->s_full[sb], (n >> 1) & 1);
@@ -341,7 +357,8 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
         if (half == 0) softmax_blocks<MIX, G0_, SC_, 0>(taddr, dl, scale_g, ph, pl, r);   \
         else softmax_blocks<MIX, G0_, SC_, 1>(taddr, dl, scale_g, ph, pl, r);             \
     } while (0)
-                if (C::N_SLICES == 1 || slice == 0) {
+                if (ract == 0u) {
+                } else if (C::N_SLICES == 1 || slice == 0) {
                     if (scaled_rows) PC_SOFTMAX(0, true);
                     else PC_SOFTMAX(0, false);
                 } else {
@@ -349,6 +366,8 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     else PC_SOFTMAX(C::NC, false);
                 }
 #undef PC_SOFTMAX
+                if (half == 0 && lane == 0)
+                    bars->kact[ps][warp & 3] = (uint8_t)(((ract & 0xffffu) ? 1u : 0u) | ((ract >> 16) ? 2u : 0u));
                 tc::tc_fence_before();
                 tc::fence_proxy_async();
                 __syncwarp();
