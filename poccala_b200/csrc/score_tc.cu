@@ -46,21 +46,28 @@ struct Cfg {
     // a 15 KiB bulk copy has ~2 us of latency, 3 stages of ~1 us of contractions each starved the
     // MMA warp (profiles/README.md)
     static constexpr int NA = MIX <= 16 ? 3 : (MIX <= 32 ? 3 : 2);
-    static constexpr int NB = MIX <= 16 ? 6 : 2;
-    static constexpr int TM_STRIDE = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : (NPAD <= 128 ? 128 : 256));
-    static constexpr int TM_BUFS = TM_STRIDE >= 256 ? 2 : 4;
+    // PG label positions share one accumulator (one MMA of N = PG * NPAD columns, one hand-off to the
+    // epilogue): with the frame tile in tensor memory an N = 48 MMA still costs ~32 clk of a 24 clk
+    // floor and every accumulator costs a commit / wait round trip, so narrow units go in pairs
+    static constexpr int PG = NPAD <= 64 ? 2 : 1;
+    static constexpr int NB = PG == 2 ? 3 : 2;  // B slots (PG unit images each)
+    static constexpr int N_ACC = PG * NPAD;
+    static constexpr int TM_STRIDE = N_ACC <= 32 ? 32 : (N_ACC <= 64 ? 64 : (N_ACC <= 128 ? 128 : 256));
+    static constexpr int TM_BUFS = PG == 2 ? 2 : (TM_STRIDE >= 256 ? 2 : 4);
     // frame tiles as the TMEM A operand (tcgen05.cp once per tile, reused by every label position):
     // 40 columns hi + 40 columns lo per tile.  Fits beside the accumulators up to 16 mixtures;
     // wider units (N >= 96 per MMA) amortise the shared-memory A read well enough already.
-    static constexpr bool A_TMEM = (TM_STRIDE * TM_BUFS + G * T_KCH * 8) <= 512 && NPAD <= 64;
+    static constexpr bool A_TMEM = PG == 2;
     static constexpr int A_COL0 = TM_STRIDE * TM_BUFS;
     static constexpr int A_TILE_COLS = T_KCH * 8;  // 2 pieces x 5 K-steps x 8 columns
     static constexpr int TM_NEED = A_TMEM ? A_COL0 + G * A_TILE_COLS : TM_STRIDE * TM_BUFS;
+    static_assert(TM_NEED <= 512, "tensor memory budget");
     static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : (TM_NEED <= 64 ? 64 : (TM_NEED <= 128 ? 128 : (TM_NEED <= 256 ? 256 : 512)));
-    static constexpr int EPI_GROUPS = TM_BUFS;                // one epilogue warpgroup per TMEM buffer
+    static constexpr int EPI_GROUPS = PG * TM_BUFS;           // one epilogue warpgroup per (TMEM buffer, position)
     static constexpr int W_PROD = 4 * EPI_GROUPS, W_MMA = W_PROD + 1;
     static constexpr int NTHREADS = (W_MMA + 1) * 32;
-    static constexpr int SMEM = 1024 + NA * 2 * T_PIECE + NB * B_STAGE;
+    static constexpr int B_SLOT = PG * B_STAGE;
+    static constexpr int SMEM = 1024 + NA * 2 * T_PIECE + NB * B_SLOT;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -148,7 +155,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) {
             tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1);
-            tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], 4);
+            tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], 4 * C::PG);
         }
         for (int i = 0; i < 8; ++i) { tc::mbar_init(&bars->b_full[i], 1); tc::mbar_init(&bars->b_empty[i], 1); }
         tc::mbar_fence_init();
@@ -195,20 +202,23 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                     ++n_a;
                     __syncwarp();
                 };
-                auto load_b = [&](int p) {            // the unit image of label position p
-                    const int stage = n_b % C::NB;
-                    const int unit = v.labels[p0 + p];
-                    uint8_t *dst = b_s + stage * C::B_STAGE;
-                    tc::mbar_wait(&bars->b_empty[stage], ((n_b / C::NB) & 1) ^ 1);
+                auto load_b = [&](int pp) {           // the unit images of label positions pp*PG ..
+                    const int slot = n_b % C::NB;
+                    const int n_img = min(C::PG, L - pp * C::PG);
+                    uint8_t *dst = b_s + slot * C::B_SLOT;
+                    tc::mbar_wait(&bars->b_empty[slot], ((n_b / C::NB) & 1) ^ 1);
                     if (lane == 0 && (dbg & 4)) {
-                        tc::mbar_arrive(&bars->b_full[stage]);
+                        tc::mbar_arrive(&bars->b_full[slot]);
                     } else if (lane == 0) {
-                        tc::mbar_expect_tx(&bars->b_full[stage], C::B_STAGE);
-                        tc::tma_load_1d(dst, w16 + (size_t)unit * C::B_STAGE, C::B_STAGE, &bars->b_full[stage]);
+                        tc::mbar_expect_tx(&bars->b_full[slot], n_img * C::B_STAGE);
+                        for (int i = 0; i < n_img; ++i)
+                            tc::tma_load_1d(dst + i * C::B_STAGE, w16 + (size_t)v.labels[p0 + pp * C::PG + i] * C::B_STAGE,
+                                            C::B_STAGE, &bars->b_full[slot]);
                     }
                     ++n_b;
                     __syncwarp();
                 };
+                const int NPG = (L + C::PG - 1) / C::PG;  // position groups of this utterance
                 if constexpr (C::A_TMEM) {
                     // The MMA warp moves a group's tiles to tensor memory at once, which frees their
                     // slots: the NEXT group's tiles are requested right after this group's first unit
@@ -216,7 +226,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                     // the tcgen05.cp staging stay off the critical path).
                     if (item == item_lo + (int)blockIdx.x && jg == 0)
                         for (int j = 0; j < nt; ++j) load_a(u, t_first + j * T_ROWS);
-                    const int lead = min(L, 3);  // unit images issued ahead of the next group's tiles
+                    const int lead = min(NPG, 2);  // B slots issued ahead of the next group's tiles
                     for (int p = 0; p < lead; ++p) load_b(p);
                     {
                         int nu = u, nt0 = t_first + C::G * T_ROWS, nn = nt_item - jg - C::G;  // next group
@@ -232,19 +242,20 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         nn = min(nn, C::G);
                         for (int j = 0; j < nn; ++j) load_a(nu, nt0 + j * T_ROWS);
                     }
-                    for (int p = lead; p < L; ++p) load_b(p);
+                    for (int p = lead; p < NPG; ++p) load_b(p);
                 } else {
                     // order = consumption order of the MMA warp: A_0, B_0, A_1 .. A_{nt-1}, B_1 .. B_{L-1}
                     load_a(u, t_first);
                     load_b(0);
                     for (int j = 1; j < nt; ++j) load_a(u, t_first + j * T_ROWS);
-                    for (int p = 1; p < L; ++p) load_b(p);
+                    for (int p = 1; p < NPG; ++p) load_b(p);
                 }
             } else if (warp == C::W_MMA) {
                 // -------------------------------------------------------- MMA issuer
                 // loop bounds and ring counters go through redux.sync so that the compiler can keep
                 // them (and the UMMA descriptors derived from them) in uniform registers
-                constexpr uint32_t idesc = tc::umma_idesc_f16(T_ROWS, C::NPAD, 0, 0);
+                constexpr uint32_t idesc_full = tc::umma_idesc_f16(T_ROWS, C::N_ACC, 0, 0);
+                constexpr uint32_t idesc_tail = tc::umma_idesc_f16(T_ROWS, C::NPAD, 0, 0);  // odd position left over
                 const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s);
                 const int L = __reduce_max_sync(0xffffffffu, L_);
                 const int nt = __reduce_max_sync(0xffffffffu, nt_);
@@ -275,8 +286,10 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         __syncwarp();
                     }
                 }
-                for (int p = 0; p < L; ++p, ++n_b) {
+                const int NPG = (L + C::PG - 1) / C::PG;
+                for (int p = 0; p < NPG; ++p, ++n_b) {
                     const int stage = n_b % C::NB;
+                    const uint32_t idesc = (L - p * C::PG >= C::PG) ? idesc_full : idesc_tail;
                     tc::mbar_wait(&bars->b_full[stage], (n_b / C::NB) & 1);
                     for (int j = 0; j < nt; ++j, ++n_pair) {
                         const uint32_t na = na0 + j;
@@ -291,7 +304,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         if (tc::elect_one()) {
                             const uint32_t d = tmem_base + tb * C::TM_STRIDE;
                             const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
-                            const uint32_t bh = b_base + stage * C::B_STAGE, bl = bh + PC_WGROUP_BYTES / 2;
+                            const uint32_t bh = b_base + stage * C::B_SLOT, bl = bh + PC_WGROUP_BYTES / 2;
                             const uint32_t tah = tmem_base + C::A_COL0 + j * C::A_TILE_COLS, tal = tah + T_KCH * 4;
                             uint32_t accum = 0;
 #pragma unroll
@@ -313,7 +326,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                                 }
                             }
                             tc::tc_commit(&bars->tm_full[tb]);
-                            if (!C::A_TMEM && p == L - 1) tc::tc_commit(&bars->a_empty[slot]);
+                            if (!C::A_TMEM && p == NPG - 1) tc::tc_commit(&bars->a_empty[slot]);
                             if (j == nt - 1) tc::tc_commit(&bars->b_empty[stage]);
                         }
                         if (rec) g_pc_dbg[n_pair * 8 + 3] = clock64();
@@ -324,12 +337,16 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
             } else {
                 // -------------------------------------------------------- epilogue warpgroups
                 const int grp = warp >> 2;
+                const int tbsel = grp / C::PG, sub = grp % C::PG;  // accumulator buffer, position inside it
                 const int r = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane
                 const int sp = pc_spad(L);
-                for (int p = 0; p < L; ++p) {
-                    const float *scale_g = wscale + (size_t)v.labels[p0 + p] * C::N_REAL;
+                const int NPG = (L + C::PG - 1) / C::PG;
+                for (int pp = 0; pp < NPG; ++pp) {
+                    const int p = pp * C::PG + sub;
+                    const bool have = p < L;  // an odd tail leaves the second warpgroup without a position
+                    const float *scale_g = wscale + (size_t)v.labels[p0 + (have ? p : 0)] * C::N_REAL;
                     for (int j = 0; j < nt; ++j, ++n_pair) {
-                        if ((int)(n_pair % C::EPI_GROUPS) != grp) continue;
+                        if ((int)(n_pair % C::TM_BUFS) != tbsel) continue;
                         const int tb = n_pair % C::TM_BUFS;
                         const int t0 = t_first + j * T_ROWS;
                         const int rows = min(T_ROWS, T - t0);
@@ -339,7 +356,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         tc::mbar_wait(&bars->tm_full[tb], (n_pair / C::TM_BUFS) & 1);
                         if (rec) g_pc_dbg[n_pair * 8 + 5] = clock64();
                         tc::tc_fence_after();
-                        const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
+                        const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + sub * C::NPAD + ((uint32_t)((warp & 3) * 32) << 16);
                         float res[PC_EMIT] = {0.f, 0.f, 0.f};
                         if (dbg & 16) {
                             tc::tc_fence_before();
@@ -347,7 +364,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                             if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
                             continue;
                         }
-                        if (dbg & 1) {
+                        if ((dbg & 1) || !have) {
                         } else if (scaled_rows)
                             epilogue_pair<MIX, true>(taddr, scale_g, res);
                         else
@@ -355,7 +372,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                         tc::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
-                        if (r < rows) {
+                        if (have && r < rows) {
 #pragma unroll
                             for (int s = 0; s < PC_EMIT; ++s) out[s] = res[s];
                         }
