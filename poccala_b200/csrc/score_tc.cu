@@ -41,30 +41,34 @@ struct Cfg {
     static constexpr int B_PIECE = T_KCH * NPAD * 16;
     static constexpr int B_STAGE = 2 * B_PIECE;  // hi, lo
     static constexpr int G = MIX <= 16 ? 3 : 2;                                // tiles per group
-    // frame-tile slots / B stages.  Up to 16 mixtures the tiles move on to tensor memory at once
-    // (A_TMEM below), so 3 slots suffice and the shared memory goes to a deep ring of unit images:
-    // a 15 KiB bulk copy has ~2 us of latency, 3 stages of ~1 us of contractions each starved the
-    // MMA warp (profiles/README.md)
-    static constexpr int NA = MIX <= 16 ? 3 : (MIX <= 32 ? 3 : 2);
+    // frame-tile slots: the group's tiles stay in shared memory for all label positions; one more
+    // slot lets the producer start on the next group
+    static constexpr int NA = MIX <= 16 ? 4 : (MIX <= 32 ? 3 : 2);
     // PG label positions share one accumulator (one MMA of N = PG * NPAD columns, one hand-off to the
     // epilogue): with the frame tile in tensor memory an N = 48 MMA still costs ~32 clk of a 24 clk
     // floor and every accumulator costs a commit / wait round trip, so narrow units go in pairs
     static constexpr int PG = NPAD <= 64 ? 2 : 1;
-    static constexpr int NB = PG == 2 ? 3 : 2;  // B slots (PG unit images each)
+    static constexpr int NB = 2;  // B slots (PG unit images each)
     static constexpr int N_ACC = PG * NPAD;
     static constexpr int TM_STRIDE = N_ACC <= 32 ? 32 : (N_ACC <= 64 ? 64 : (N_ACC <= 128 ? 128 : 256));
-    static constexpr int TM_BUFS = PG == 2 ? 2 : (TM_STRIDE >= 256 ? 2 : 4);
-    // frame tiles as the TMEM A operand (tcgen05.cp once per tile, reused by every label position):
-    // 40 columns hi + 40 columns lo per tile.  Fits beside the accumulators up to 16 mixtures;
-    // wider units (N >= 96 per MMA) amortise the shared-memory A read well enough already.
-    static constexpr bool A_TMEM = PG == 2;
+    static constexpr int TM_BUFS = TM_STRIDE >= 256 ? 2 : 4;
+    // A_TMEM: frame tiles staged in tensor memory (tcgen05.cp once per tile, 40 columns hi + 40 lo)
+    // as the A operand of every label position.  Measured (profiles/README.md): an N = 48 MMA drops
+    // from ~70 to ~32 clk, but every tcgen05.cp of 128 rows x 32 B takes ~190 clk, i.e. ~5 600 clk
+    // per group of three tiles; with two positions per MMA (N = 96) the shared-memory A read is
+    // amortised just as well (~55 clk per MMA) without the staging, so the path is switched off.
+    static constexpr bool A_TMEM = false;  // see profiles/README.md: staging cost ~190 clk per tcgen05.cp
     static constexpr int A_COL0 = TM_STRIDE * TM_BUFS;
     static constexpr int A_TILE_COLS = T_KCH * 8;  // 2 pieces x 5 K-steps x 8 columns
     static constexpr int TM_NEED = A_TMEM ? A_COL0 + G * A_TILE_COLS : TM_STRIDE * TM_BUFS;
     static_assert(TM_NEED <= 512, "tensor memory budget");
     static constexpr int TM_COLS = TM_NEED <= 32 ? 32 : (TM_NEED <= 64 ? 64 : (TM_NEED <= 128 ? 128 : (TM_NEED <= 256 ? 256 : 512)));
-    static constexpr int EPI_GROUPS = PG * TM_BUFS;           // one epilogue warpgroup per (TMEM buffer, position)
-    static constexpr int W_PROD = 4 * EPI_GROUPS, W_MMA = W_PROD + 1;
+    // epilogue warps.  PG == 2: one warp per (lane quarter, position, state) - 24 warps that take every
+    // accumulator, each thread reducing ONE state's mixtures (a thread that reduced a whole 48-column
+    // block needed ~1 300 clk per block, more than the 800 clk the tensor pipe needs for the pair).
+    // PG == 1 (wide units): one warpgroup per TMEM buffer, a thread reduces its frame's three states.
+    static constexpr int EPI_WARPS = PG == 2 ? 4 * PG * PC_EMIT : 4 * TM_BUFS;
+    static constexpr int W_PROD = EPI_WARPS, W_MMA = W_PROD + 1;
     static constexpr int NTHREADS = (W_MMA + 1) * 32;
     static constexpr int B_SLOT = PG * B_STAGE;
     static constexpr int SMEM = 1024 + NA * 2 * T_PIECE + NB * B_SLOT;
@@ -155,7 +159,7 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) {
             tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1);
-            tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], 4 * C::PG);
+            tc::mbar_init(&bars->tm_full[i], 1); tc::mbar_init(&bars->tm_empty[i], C::PG == 2 ? C::EPI_WARPS : 4);
         }
         for (int i = 0; i < 8; ++i) { tc::mbar_init(&bars->b_full[i], 1); tc::mbar_init(&bars->b_empty[i], 1); }
         tc::mbar_fence_init();
@@ -334,49 +338,75 @@ score_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__restri
                     }
                 }
                 n_a = na0 + nt;
-            } else {
-                // -------------------------------------------------------- epilogue warpgroups
-                const int grp = warp >> 2;
-                const int tbsel = grp / C::PG, sub = grp % C::PG;  // accumulator buffer, position inside it
-                const int r = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane
+            } else if constexpr (C::PG == 2) {
+                // -------------------------------------------------------- epilogue, narrow units
+                // warp = (lane quarter, position inside the pair, state); every warp takes every
+                // accumulator: tcgen05.ld of the state's MIX columns (one frame per thread), LSE, store
+                const int quarter = warp & 3, role = warp >> 2;
+                const int sub = role / PC_EMIT, st = role - sub * PC_EMIT;
+                const int r = quarter * 32 + lane;  // row of the tile == TMEM lane
                 const int sp = pc_spad(L);
                 const int NPG = (L + C::PG - 1) / C::PG;
                 for (int pp = 0; pp < NPG; ++pp) {
                     const int p = pp * C::PG + sub;
-                    const bool have = p < L;  // an odd tail leaves the second warpgroup without a position
-                    const float *scale_g = wscale + (size_t)v.labels[p0 + (have ? p : 0)] * C::N_REAL;
+                    const bool have = p < L;  // an odd tail leaves the second position's warps idle
+                    const float *scale_g = wscale + (size_t)v.labels[p0 + (have ? p : 0)] * C::N_REAL + st * MIX;
                     for (int j = 0; j < nt; ++j, ++n_pair) {
-                        if ((int)(n_pair % C::TM_BUFS) != tbsel) continue;
+                        const int tb = n_pair % C::TM_BUFS;
+                        const int t0 = t_first + j * T_ROWS;
+                        const int rows = min(T_ROWS, T - t0);
+                        tc::mbar_wait(&bars->tm_full[tb], (n_pair / C::TM_BUFS) & 1);
+                        tc::tc_fence_after();
+                        float res = 0.f;
+                        if (have && !(dbg & 17)) {
+                            const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + sub * C::NPAD + st * MIX +
+                                                   ((uint32_t)(quarter * 32) << 16);
+                            float vv[MIX];
+                            if constexpr (MIX == 16) {
+                                tc::tmem_ld16(taddr, vv);
+                            } else {
+                                float t8[8];
+                                tc::tmem_ld8(taddr, t8);
+#pragma unroll
+                                for (int e = 0; e < MIX; ++e) vv[e] = t8[e];
+                            }
+                            tc::tmem_ld_wait();
+                            res = scaled_rows ? state_lse<MIX, true>(vv, scale_g) : state_lse<MIX, false>(vv, scale_g);
+                        }
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
+                        if (have && r < rows) b[v.emis_off[u] + (size_t)(t0 + r) * sp + PC_EMIT * p + st] = res;
+                    }
+                }
+            } else {
+                // -------------------------------------------------------- epilogue warpgroups, wide units
+                const int grp = warp >> 2;
+                const int r = (warp & 3) * 32 + lane;  // row of the tile == TMEM lane
+                const int sp = pc_spad(L);
+                for (int p = 0; p < L; ++p) {
+                    const float *scale_g = wscale + (size_t)v.labels[p0 + p] * C::N_REAL;
+                    for (int j = 0; j < nt; ++j, ++n_pair) {
+                        if ((int)(n_pair % C::TM_BUFS) != grp) continue;
                         const int tb = n_pair % C::TM_BUFS;
                         const int t0 = t_first + j * T_ROWS;
                         const int rows = min(T_ROWS, T - t0);
                         float *out = b + v.emis_off[u] + (size_t)(t0 + r) * sp + PC_EMIT * p;
-                        const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && (warp & 3) == 0 && n_pair < 1000;
-                        if (rec) g_pc_dbg[n_pair * 8 + 4] = clock64();
                         tc::mbar_wait(&bars->tm_full[tb], (n_pair / C::TM_BUFS) & 1);
-                        if (rec) g_pc_dbg[n_pair * 8 + 5] = clock64();
                         tc::tc_fence_after();
-                        const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + sub * C::NPAD + ((uint32_t)((warp & 3) * 32) << 16);
+                        const uint32_t taddr = tmem_base + tb * C::TM_STRIDE + ((uint32_t)((warp & 3) * 32) << 16);
                         float res[PC_EMIT] = {0.f, 0.f, 0.f};
-                        if (dbg & 16) {
-                            tc::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
-                            continue;
+                        if (!(dbg & 17)) {
+                            if (scaled_rows) epilogue_pair<MIX, true>(taddr, scale_g, res);
+                            else epilogue_pair<MIX, false>(taddr, scale_g, res);
                         }
-                        if ((dbg & 1) || !have) {
-                        } else if (scaled_rows)
-                            epilogue_pair<MIX, true>(taddr, scale_g, res);
-                        else
-                            epilogue_pair<MIX, false>(taddr, scale_g, res);
                         tc::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) tc::mbar_arrive(&bars->tm_empty[tb]);
-                        if (have && r < rows) {
+                        if (r < rows) {
 #pragma unroll
                             for (int s = 0; s < PC_EMIT; ++s) out[s] = res[s];
                         }
-                        if (rec) g_pc_dbg[n_pair * 8 + 6] = clock64();
                     }
                 }
             }
