@@ -107,6 +107,34 @@ class AcousticModel(object):
         return (np.stack([self.__params[u]["mean"] for u in us]), np.stack([self.__params[u]["var"] for u in us]),
                 np.stack([self.__params[u]["alpha"] for u in us]), np.stack([self.__params[u]["transmat"] for u in us]))
 
+    def flat_start(self, data, proportion=0.25, step=1, differentiation=True, coefficient=1.):
+        """AcousticModel.py:479-517 (`__flat_start`) on in-memory utterances: the frames of the first
+        int(len(data) * proportion) utterances, every `step`-th frame, go through
+        ClusterInitialization(k=1).kmeans(algorithm=1, cov_matrix=True) - i.e. the global mean and
+        variance, by the device k-means with the reference's insertion-order sums - and every GMM
+        of every unit starts from mean + diff * variance (diff drawn from numpy's global RNG exactly
+        like the reference, one [mix, 1] draw shared by all units) and the global variance."""
+        n = int(len(data) * proportion)
+        p_data = np.asarray(data[0], dtype=np.float64)[::step]
+        for index in range(1, n):
+            p_data = np.append(p_data, np.asarray(data[index], dtype=np.float64)[::step], axis=0)
+        cluster = Clustering.ClusterInitialization(p_data, 1, self.__vector_size, self.log)
+        mean, covariance, alpha, clustered = cluster.kmeans(algorithm=1, cov_matrix=True)
+        covariance_diagonal = covariance[0].diagonal()
+        M = self.__mix_level
+        diff = np.zeros((M, 1))
+        if differentiation:
+            assert 0 <= coefficient <= 1, "coefficient must lie in [0, 1]"
+            diff = (np.random.random((M, 1)) - np.random.random((M, 1))) * coefficient
+        g_mean = mean.repeat(M, axis=0) + diff * covariance_diagonal
+        g_var = np.repeat(covariance_diagonal[None], M, axis=0)
+        tm = _synth.default_transmat(1)[0]
+        for unit in self.__loaded_units:
+            self.__params[unit] = dict(mean=np.stack([g_mean] * EMIT), var=np.stack([g_var] * EMIT),
+                                       alpha=np.ones((EMIT, M)) / M, transmat=tm.copy())
+        self.__model = None
+        self.delete_trainInfo()
+
     def init_unit(self, unit=None, new_log=True, fix_code=0):
         """AcousticModel.py:164-226: a 5-state left-to-right unit HMM: entry VirtualState(1.), three
         GMM states, exit VirtualState(0.); transmat [0,1] = 1, emitting rows (0.5, 0.5)."""

@@ -118,8 +118,45 @@ def kmeans_golden():
     print("kmeans_small.npz written")
 
 
+def flat_start_golden():
+    """AcousticModel.__flat_start (AcousticModel.py:479-517) executed as is: only the audio loader is
+    replaced by in-memory feature arrays and the parameter writer by a capture."""
+    import random
+
+    H = rh.Harness(UNITS, MIX)
+    am = H.am
+    rng = np.random.default_rng(2024)
+    utts = [rng.normal(0.5, 2.0, size=(int(n), 39)) for n in rng.integers(15, 30, size=8)]
+    paths = [["utt%d" % i, "lab%d" % i] for i in range(len(utts))]
+    am._AcousticModel__load_audio = lambda path: utts[int(path[3:])]
+    captured = {}
+
+    def save(unit, hmm):
+        gm = hmm.profunction[1:-1]
+        captured[unit] = (np.stack([np.array(g.mean) for g in gm]),
+                          np.stack([np.stack([np.diag(c) for c in g.covariance]) for g in gm]))
+
+    am._AcousticModel__save_parameter = save
+    am.delete_trainInfo = lambda: None
+    am._AcousticModel__loaded_units = list(UNITS)
+    random.seed(31)
+    np.random.seed(32)
+    am._AcousticModel__flat_start(paths, len(paths), proportion=0.5, step=2, differentiation=True, coefficient=0.7)
+    out = dict(n_utt=len(utts), proportion=0.5, step=2, coefficient=0.7, py_seed=31, np_seed=32)
+    for i, x in enumerate(utts):
+        out[f"x{i}"] = x
+    out["mean"] = np.stack([captured[u][0] for u in UNITS])
+    out["var"] = np.stack([captured[u][1] for u in UNITS])
+    np.savez_compressed(os.path.join(OUT, "flat_start.npz"), **out)
+    print("flat_start.npz written", out["mean"].shape, out["var"].shape)
+
+
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
+    if "--flat-start-only" in sys.argv:
+        flat_start_golden()
+        sys.exit(0)
     estep_golden()
     viterbi_ties_golden()
     kmeans_golden()
+    flat_start_golden()

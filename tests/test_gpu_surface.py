@@ -212,3 +212,25 @@ def test_gmm_point_and_dimension_error():
     assert np.all(np.abs(gm.score_frames(X[:8]) - ref) <= 2e-6 * np.abs(ref))
     with pytest.raises(DataDimensionError):
         gm.point(np.zeros(38), log=True)
+
+
+def test_flat_start_matches_executed_reference():
+    """§8 f4: AcousticModel.__flat_start (AcousticModel.py:479-517), golden from the executed
+    reference method (tests/golden/make_golden.py: only its audio loader was replaced).  The global
+    mean comes from the device k-means (k = 1) with the reference's insertion-order sums."""
+    from poccala_b200.AcousticModel import AcousticModel
+
+    g = load_golden("flat_start.npz")
+    data = [g[f"x{i}"] for i in range(int(g["n_utt"]))]
+    am = AcousticModel(None, "T", state_num=5, mix_level=4)
+    am.set_units(UNITS3)
+    random.seed(int(g["py_seed"]))
+    np.random.seed(int(g["np_seed"]))
+    am.flat_start(data, proportion=float(g["proportion"]), step=int(g["step"]), differentiation=True,
+                  coefficient=float(g["coefficient"]))
+    mean, var, alpha, tm = am.get_parameters()
+    assert np.allclose(var, g["var"], rtol=1e-14, atol=0)
+    assert np.allclose(mean, g["mean"], rtol=1e-14, atol=1e-15)
+    assert np.all(alpha == 0.25)
+    assert np.array_equal(tm[0], np.array([[0, 1, 0, 0, 0], [0, .5, .5, 0, 0], [0, 0, .5, .5, 0], [0, 0, 0, .5, .5],
+                                           [0, 0, 0, 0, 0]], dtype=np.float64))
