@@ -27,6 +27,10 @@ class DataDimensionError(Exception):
     """Exceptions.DataDimensionError (Exceptions.py:76): raised by GMM.point on a wrong-length frame."""
 
 
+class ParameterFileExistsError(Exception):
+    """Exceptions.ParameterFileExistsError: the GMM_<id> parameter directory is missing (Clustering.py:295)."""
+
+
 def _diag_stack(var):
     var = np.asarray(var, dtype=np.float64)
     M, D = var.shape
@@ -64,6 +68,39 @@ class Clustering(object):
             self.__gmm_id = gmm_id
             self.__record = []
             self._clear_acc()
+
+        # ---- parameter files (Clustering.py:234-255, 288-312): same directory layout and array
+        # shapes as the reference, so models trained by either side load in the other.  (The
+        # accumulator files of save_acc / init_acc are replaced by device reductions.)
+        def save_parameter(self, path):
+            import configparser
+            import os
+
+            path = path + '/GMM_%d' % self.__gmm_id
+            if not os.path.exists(path):
+                os.mkdir(path)
+            np.save(path + '/GMM_means.npy', self.__mean)              # [M, D]
+            np.save(path + '/GMM_covariance.npy', self.__covariance)   # [M, D, D]
+            np.save(path + '/GMM_weight.npy', self.__alpha)            # [M]
+            with open(path + '/GMM_config.ini', 'w+') as f:
+                cfg = configparser.ConfigParser()
+                cfg.add_section('Configuration')
+                cfg.set('Configuration', 'MIXTURE', value=str(self.__mix_level))
+                cfg.set('Configuration', 'DIMENSION', value=str(self.__dimension))
+                cfg.set('Configuration', 'BIAS', value=str(self.__bias))
+                cfg.write(f)
+
+        def init_parameter(self, path):
+            import os
+
+            path = path + '/GMM_%d' % self.__gmm_id
+            if not os.path.exists(path):
+                raise ParameterFileExistsError(path)
+            self.__mean = np.load(path + '/GMM_means.npy')
+            self.__covariance = np.load(path + '/GMM_covariance.npy')
+            self.__alpha = np.load(path + '/GMM_weight.npy')
+            # the reference hands ConfigParser.read() an open file object, so the .ini never parses
+            # and mixture / dimension / bias keep their constructor values (Q15); same here
 
         # ---- parameters (Clustering.py:122-229) -------------------------------------------
         @property

@@ -161,6 +161,28 @@ class LHMM(object):
     def clear_result_buffer(self):
         self.__result_p = None
 
+    # ---- parameter files (LHMM.py:192-209, 233-254): same layout as the reference ---------------
+    def save_parameter(self, path):
+        import configparser
+        import os
+
+        path = path + '/HMM'
+        if not os.path.exists(path):
+            os.mkdir(path)
+        np.save(path + '/transmat.npy', self.__transmat)
+        np.save(path + '/pi.npy', self.__pi)
+        with open(path + '/HMM_config.ini', 'w+') as f:
+            cfg = configparser.ConfigParser()
+            cfg.add_section('Configuration')
+            cfg.set('Configuration', 'FIX_CODE', value=str(self.__fix_code))
+            cfg.write(f)
+
+    def init_parameter(self, path):
+        path = path + '/HMM'
+        self.__transmat = np.load(path + '/transmat.npy')
+        self.__pi = np.load(path + '/pi.npy')
+        # HMM_config.ini is written but never parsed by the reference (Q15): fix_code keeps its value
+
     # ---- accumulators (LHMM.py:149-161) ----------------------------------------------------------
     def add_acc(self, ksai_value, gamma_value):
         """Element-wise log-add into the log-domain transition accumulators."""
