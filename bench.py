@@ -184,7 +184,9 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     group = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout (one JSON line)
+        # the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout: rank 0 must print ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         group = dist.group.WORLD
     eng = Engine(local)
