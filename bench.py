@@ -187,8 +187,21 @@ def run_gpu(args):
         # the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout: rank 0 must print ONE JSON line
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        group = dist.group.WORLD
+        # ... and whatever NCCL still writes while the communicator comes up goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            group = dist.group.WORLD
+            warm = torch.zeros(1, device=torch.device("cuda", local))
+            dist.all_reduce(warm, group=group)
+            dist.all_reduce(warm, op=dist.ReduceOp.MAX, group=group)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     eng = Engine(local)
     dev = eng.device
     # every rank starts from the SAME model (replicated parameters) and owns its own utterances
