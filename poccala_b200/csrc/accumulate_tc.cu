@@ -81,12 +81,21 @@ struct Cfg {
     static constexpr int B_PIECE = T_KCH * NPAD * 16;
     static constexpr int P_PIECE = (NPAD / 8) * T_ROWS * 16;
     static constexpr int NA = NPAD <= 48 ? 3 : 2;
-    static constexpr int S_STRIDE = NPAD <= 32 ? 32 : (NPAD <= 64 ? 64 : 128);
+    // STACK: the (hi, lo) halves of the B operands are stacked along N, so one MMA of N = 2*NPAD
+    // columns forms A*B_hi and A*B_lo at once and the A operand - whose 4 KB shared-memory read paces
+    // an N = 48 MMA at ~65 clk - is fetched twice per K-step instead of three times:
+    //   MMA1: S = (A_hi + A_lo) * [W_hi | W_lo]  (the unit image interleaves hi / lo row groups: SBO 1280)
+    //   MMA2: D2 = (A_hi + A_lo)^T * [P_hi | P_lo]  (the lo piece of the P tile follows the hi piece)
+    // The extra lo*lo products only add accuracy; the consumer adds the two column halves.
+    static constexpr bool STACK = NPAD <= 64;
+    static constexpr int S_COLS = STACK ? 2 * NPAD : NPAD;
+    static constexpr int S_STRIDE = S_COLS <= 32 ? 32 : (S_COLS <= 64 ? 64 : 128);
     static constexpr int D2_COL = S_STRIDE * 2;
+    static constexpr int D2_COLS = STACK ? 2 * NPAD : NPAD;
     static constexpr int TM_COLS = 512;
     static constexpr int SMEM = 1024 + NA * 2 * T_PIECE + 2 * B_PIECE + 2 * 2 * P_PIECE;
     static_assert(N_UNIT % NC == 0, "slices must tile the unit");
-    static_assert(D2_COL + NPAD <= 512, "TMEM budget");
+    static_assert(D2_COL + D2_COLS <= 512, "TMEM budget");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -117,8 +126,16 @@ __device__ __forceinline__ void softmax_blocks(uint32_t taddr, const float (&dl)
         const int blk = blk0 + bb;
         if (blk >= NBLK) break;
         float t8[8];
-        tc::tmem_ld8(taddr + blk * 8, t8);
-        tc::tmem_ld_wait();
+        if constexpr (C::STACK) {  // columns 16*blk + [0,8): A*W_hi, + [8,16): A*W_lo
+            float t16[16];
+            tc::tmem_ld16(taddr + blk * 16, t16);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t8[e] = t16[e] + t16[8 + e];
+        } else {
+            tc::tmem_ld8(taddr + blk * 8, t8);
+            tc::tmem_ld_wait();
+        }
         uint32_t h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -228,6 +245,8 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc1 = tc::umma_idesc_f16(T_ROWS, C::NPAD, 0, 0);
             constexpr uint32_t idesc2 = tc::umma_idesc_f16(128, C::NPAD, 1, 1);
+            constexpr uint32_t idesc1s = tc::umma_idesc_f16(T_ROWS, 2 * C::NPAD, 0, 0);
+            constexpr uint32_t idesc2s = tc::umma_idesc_f16(128, 2 * C::NPAD, 1, 1);
             const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s), p_base = tc::smem_u32(p_s);
             // loop bounds / ring counters through redux.sync: uniform registers for the descriptors
             const int n_tiles = __reduce_max_sync(0xffffffffu, n_tiles_);
@@ -251,16 +270,30 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                         const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                         const uint32_t bh = b_base, bl = b_base + PC_WGROUP_BYTES / 2;
                         uint32_t accum = 0;
+                        if constexpr (C::STACK) {
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const uint32_t ap = (q == 2) ? al : ah;
-                            const uint32_t bp = (q == 1) ? bl : bh;
+                            for (int q = 0; q < 2; ++q) {
+                                const uint32_t ap = q ? al : ah;
 #pragma unroll
-                            for (int k = 0; k < T_KCH / 2; ++k) {
-                                const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
-                                const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
-                                tc::mma_f16_ss(d, ad, bd, idesc1, accum);
-                                accum = 1;
+                                for (int k = 0; k < T_KCH / 2; ++k) {
+                                    const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
+                                    const uint64_t bd = tc::umma_desc(bh + 2 * k * 128, 128, PC_WGROUP_BYTES / 2);
+                                    tc::mma_f16_ss(d, ad, bd, idesc1s, accum);
+                                    accum = 1;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const uint32_t ap = (q == 2) ? al : ah;
+                                const uint32_t bp = (q == 1) ? bl : bh;
+#pragma unroll
+                                for (int k = 0; k < T_KCH / 2; ++k) {
+                                    const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
+                                    const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
+                                    tc::mma_f16_ss(d, ad, bd, idesc1, accum);
+                                    accum = 1;
+                                }
                             }
                         }
                         tc::tc_commit(&bars->s_full[sb]);
@@ -289,19 +322,34 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                         const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
                         const uint32_t ph = p_base + ps * 2 * C::P_PIECE, pl = ph + C::P_PIECE;
                         uint32_t accum = (i == 1) ? 0u : 1u;  // first tile of the item resets D2
+                        if constexpr (C::STACK) {
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const uint32_t ap = (q == 1) ? al : ah;
-                            const uint32_t pp = (q == 2) ? pl : ph;
+                            for (int q = 0; q < 2; ++q) {
+                                const uint32_t ap = q ? al : ah;
 #pragma unroll
-                            for (int k = 0; k < T_ROWS / 16; ++k) {
-                                if (!((kmask >> k) & 1u)) continue;
-                                // MN-major views: 8 frames x 16 B core matrices; LBO = 128 B between
-                                // 8-frame groups, SBO = 2048 B between 8-feature / 8-Gaussian blocks
-                                const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
-                                const uint64_t bd = tc::umma_desc(pp + k * 256, 128, T_ROWS * 16);
-                                tc::mma_f16_ss(d2, ad, bd, idesc2, accum);
-                                accum = 1;
+                                for (int k = 0; k < T_ROWS / 16; ++k) {
+                                    if (!((kmask >> k) & 1u)) continue;
+                                    const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
+                                    const uint64_t bd = tc::umma_desc(ph + k * 256, 128, T_ROWS * 16);  // hi then lo blocks
+                                    tc::mma_f16_ss(d2, ad, bd, idesc2s, accum);
+                                    accum = 1;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const uint32_t ap = (q == 1) ? al : ah;
+                                const uint32_t pp = (q == 2) ? pl : ph;
+#pragma unroll
+                                for (int k = 0; k < T_ROWS / 16; ++k) {
+                                    if (!((kmask >> k) & 1u)) continue;
+                                    // MN-major views: 8 frames x 16 B core matrices; LBO = 128 B between
+                                    // 8-frame groups, SBO = 2048 B between 8-feature / 8-Gaussian blocks
+                                    const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
+                                    const uint64_t bd = tc::umma_desc(pp + k * 256, 128, T_ROWS * 16);
+                                    tc::mma_f16_ss(d2, ad, bd, idesc2, accum);
+                                    accum = 1;
+                                }
                             }
                         }
                         tc::tc_commit(&bars->a_empty[slot]);
@@ -389,7 +437,15 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
             for (int j = 0; j < C::NPAD / 16; ++j) {
                 float t16[16];
                 tc::tmem_ld16(taddr + j * 16, t16);
-                tc::tmem_ld_wait();
+                if constexpr (C::STACK) {  // + the columns fed by P_lo
+                    float u16[16];
+                    tc::tmem_ld16(taddr + C::NPAD + j * 16, u16);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) t16[e] += u16[e];
+                } else {
+                    tc::tmem_ld_wait();
+                }
                 if (f < PC_KA) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {

@@ -305,6 +305,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     pc_corpus c = new pc_corpus_s();
     memset(c, 0, sizeof(*c));
     c->h = h;
+    c->device = h->device;
     c->dev_block = dev;
     c->total_frames = frame_off[n_utt];
     c->emis_floats = emis_off[n_utt];
@@ -370,7 +371,7 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
 
 int pc_corpus_destroy(pc_corpus c) {
     if (!c) return PC_OK;
-    cudaSetDevice(c->h->device);
+    cudaSetDevice(c->device);  // not c->h: the handle may already be gone
     if (c->dev_block) cudaFree(c->dev_block);
     delete[] c->host_frame_off;
     delete c;
@@ -380,7 +381,7 @@ int pc_corpus_destroy(pc_corpus c) {
 int64_t pc_corpus_active_tiles(pc_corpus c) {
     if (!c) return -1;
     std::vector<int32_t> a((size_t)c->v.n_tiles);
-    if (cudaSetDevice(c->h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
         cudaMemcpy(a.data(), c->v.tile_active, a.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
         return -1;
     int64_t n = 0;
@@ -409,9 +410,11 @@ int pc_corpus_offsets(pc_corpus c, int64_t *frame_off, int64_t *emis_off, int64_
 }
 
 // --------------------------------------------------------------------------------- kernels
+// (a stale error left behind by an unrelated runtime call must not be blamed on this call's launches)
 #define PC_ENTER(h)                                           \
     PC_REQUIRE((h) != nullptr, "%s: NULL handle", __func__);  \
-    PC_CUDA_TRY(cudaSetDevice((h)->device))
+    PC_CUDA_TRY(cudaSetDevice((h)->device));                  \
+    (void)cudaGetLastError()
 
 static int check_dim_mix(const char *fn, int dim, int mix) {
     if (dim < 1 || dim > PC_DIM_MAX) {

@@ -139,6 +139,7 @@ struct pc_handle_s {
 
 struct pc_corpus_s {
     pc_handle h;
+    int device;
     CorpusView v;
     int64_t total_frames;
     int64_t emis_floats;

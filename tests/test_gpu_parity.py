@@ -189,7 +189,7 @@ def test_accumulators_and_mstep_match_oracle(eng):
     assert np.all(np.abs(tm - new.transmat) <= REL * np.maximum(new.transmat, 1e-2))
 
 
-@pytest.mark.parametrize("mix", [4, 16, 64])
+@pytest.mark.parametrize("mix", [4, 8, 16, 32, 64])
 def test_accumulate_tensor_core_vs_cuda_core_and_oracle(eng, mix):
     """K3 on tcgen05 (two chained contractions, posteriors kept on chip) against the CUDA-core
     kernel and the oracle's sufficient statistics; several tiles per utterance, ragged tails."""
