@@ -43,6 +43,24 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) of the stage's kernel from the
+    committed `ncu --set full` excerpt of this workload (profiles/current/, see profiles/README.md);
+    None when the excerpt is missing."""
+    name = {"K1_score": "score_tc_kernel", "K2_forward_backward": "fwdbwd_kernel",
+            "K3_accumulate": "accumulate_tc_kernel"}.get(stage)
+    path = os.path.join(ROOT, "profiles", "current", "%s.csv" % name)
+    if not name or not os.path.exists(path):
+        return None
+    total, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    with open(path) as f:
+        for line in f:
+            parts = line.strip().split(",")
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(parts[1]) * scale.get(parts[2], 1.0)
+    return total or None
+
+
 # ------------------------------------------------------------------------------------ CPU arm
 _CPU = {}
 
@@ -306,7 +324,7 @@ def run_gpu(args):
     else:
         ach, peak, unit = work / (ms * 1e-3) / 1e9, float(pk["hbm_gbs"]), "GB/s"
     roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                "traffic": None, "peak_source": pk_src + (" (bf16 sustained)" if bound == "tensor" else ""),
+                "traffic": ncu_traffic(dom), "peak_source": pk_src + (" (bf16 sustained)" if bound == "tensor" else ""),
                 "ms_per_launch": ms,
                 "all_ms": {k: v[0] for k, v in kern.items()},
                 "note": ("achieved = 158 flop per (frame, Gaussian) pair of the corpus / event time of the stage "
