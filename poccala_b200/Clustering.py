@@ -27,6 +27,10 @@ class DataDimensionError(Exception):
     """Exceptions.DataDimensionError (Exceptions.py:76): raised by GMM.point on a wrong-length frame."""
 
 
+class DataUnLoadError(Exception):
+    """Exceptions.DataUnLoadError: em() without data (Clustering.py:698-699)."""
+
+
 class ParameterFileExistsError(Exception):
     """Exceptions.ParameterFileExistsError: the GMM_<id> parameter directory is missing (Clustering.py:295)."""
 
@@ -155,9 +159,11 @@ class Clustering(object):
         def add_data(self, data):
             d = np.array(data)
             self.__data = d if self.__data is None else np.append(self.__data, d, axis=0)
+            self._em_es = None
 
         def clear_data(self):
             self.__data = None
+            self._em_es = None
 
         # ---- accumulators: log-domain views of the linear statistics (Clustering.py:98-101) ----
         def _clear_acc(self):
@@ -308,12 +314,95 @@ class Clustering(object):
                 self.log.note("GMM %s re-estimated" % self.__gmm_id, cls="i")
             self._clear_acc()
 
-        # ---- outside the hot path --------------------------------------------------------------
-        def em(self, *a, **k):
-            raise NotImplementedError("stand-alone GMM.em() / SMEM (Clustering.py:483-651,695-719) is outside the "
-                                      "E-step hot path (SURVEY §8 f2)")
+        # ---- stand-alone EM of one GMM (mode 1, Clustering.py:583-651, 695-719) ----------
+        # The data set is laid out as a corpus of one pseudo unit whose first state carries this GMM and
+        # whose posterior is 1 for every frame, so expectation() is K1 (scoring) + K3 (accumulation):
+        # the component posteriors gamma_ik never leave the SM, what comes back are the sufficient
+        # statistics occ_k = sum_i gamma_ik, sx_k = sum_i gamma_ik x_i, sxx_k = sum_i gamma_ik x_i^2.
+        # maximization() and q_function() are closed forms of those (fp64, host: M x D numbers).
+        def _em_setup(self):
+            if getattr(self, "_em_es", None) is not None:
+                return
+            data = None if self.__data is None else np.asarray(self.__data, dtype=np.float64)
+            if data is None or len(data) == 0:
+                raise DataUnLoadError("GMM.em: no data loaded (Exceptions.DataUnLoadError)")
+            if data.ndim != 2 or data.shape[1] != self.__dimension:
+                raise DataDimensionError("expected [n, %d] data" % self.__dimension)
+            eng = get_engine()
+            n, chunk = len(data), 384
+            n_frames = np.array([min(chunk, n - o) for o in range(0, n, chunk)], dtype=np.int32)
+            corpus = _eng.Corpus(eng, [np.zeros(1, dtype=np.int32)] * len(n_frames), n_frames, 1)
+            M, D = self.__mix_level, self.__dimension
+            model = _eng.Model(eng, np.zeros((1, 3, M, D)), np.ones((1, 3, M, D)), np.ones((1, 3, M)) / M,
+                               np.zeros((1, 5, 5)))
+            es = _eng.EStep(eng, corpus, model)
+            es.load_frames(torch.as_tensor(data).to(eng.device))
+            # every frame belongs to state 0 with posterior 1; states 1, 2 of the pseudo unit are unused
+            es.lgam.fill_(float("-inf"))
+            es.lgam.view(-1, 8)[:, 0] = 0.0
+            self._em_es, self._em_n = es, n
 
-        expectation = maximization = q_function = theta = em
+        def expectation(self):
+            """Clustering.py:583-600: gamma_ik = alpha_k N(x_i; k) / sum_k' (...), reduced on the device
+            to (occ, sx, sxx)."""
+            self._em_setup()
+            es, m = self._em_es, self._em_es.model
+            dev = es.engine.device
+            for r in range(3):
+                m.mean[0, r].copy_(torch.as_tensor(self.__mean).to(dev))
+                m.var[0, r].copy_(torch.as_tensor(self.variance).to(dev))
+                m.alpha[0, r].copy_(torch.as_tensor(self.__alpha).to(dev))
+            es.score()
+            es.accumulate()
+            occ, sx, sxx = es.linear_stats()
+            self._em_stats = (occ[0, 0], sx[0, 0], sxx[0, 0])
+
+        def maximization(self, c_covariance=1e-3):
+            """Clustering.py:619-651: mean_k = sum gamma x / sum gamma (the reference goes through
+            log(x + 100)), covariance around the NEW mean with the floor c_covariance, alpha_k = occ_k / n."""
+            occ, sx, sxx = self._em_stats
+            new_mean = sx / occ[:, None]
+            var = (sxx - 2.0 * new_mean * sx + new_mean * new_mean * occ[:, None]) / occ[:, None]
+            var = np.where(var < c_covariance, c_covariance, var)
+            new_alpha = occ / self._em_n
+            return new_mean, [np.diag(v) for v in var], new_alpha
+
+        def q_function(self):
+            """Clustering.py:602-613 with the posteriors of the last expectation() and the CURRENT
+            parameters: sum_k occ_k log alpha_k + sum_ik gamma_ik log N(x_i; k), the second term written
+            out on the sufficient statistics (log N is the reference's: -1/2 sum(var), Q1)."""
+            occ, sx, sxx = self._em_stats
+            mu, var = self.__mean, self.variance
+            with np.errstate(divide="ignore"):
+                value_1 = np.sum(occ * np.log(self.__alpha))
+            const = -0.5 * self.__dimension * np.log(2 * np.pi) - 0.5 * var.sum(axis=1)
+            quad = ((sxx - 2.0 * mu * sx + mu * mu * occ[:, None]) / var).sum(axis=1)
+            return float(value_1 + np.sum(occ * const - 0.5 * quad))
+
+        def em(self, show_q=False, smem=False, c_covariance=1e-3):
+            """Clustering.py:695-719: iterate while Q grows by more than 1.28."""
+            if smem:
+                raise NotImplementedError("the SMEM split / merge search (Clustering.py:483-577) is host-side model "
+                                          "selection outside this path; em(smem=False) is covered")
+            self._em_setup()
+            self.iterations = 0
+            q_value = -float("inf")
+            while True:
+                self.log.note("GMM Q: %f" % q_value, cls="i", show_console=show_q)
+                self.expectation()
+                self.iterations += 1
+                mean, cov, alpha = self.maximization(c_covariance=c_covariance)
+                self.__mean, self.__covariance, self.__alpha = mean, np.stack(cov), alpha
+                _q = self.q_function()
+                if _q - q_value > 1.28:
+                    q_value = _q
+                else:
+                    break
+            self.q_value = q_value
+
+        def theta(self):
+            """Clustering.py:721-726: {'theta_k': [mean_k, diag(covariance_k)]}."""
+            return {"theta_%d" % i: [self.__mean[i], self.__covariance[i].diagonal()] for i in range(self.__mix_level)}
 
     class ClusterInitialization(object):
         def __init__(self, data, k, dimension, log=None):

@@ -151,12 +151,51 @@ def flat_start_golden():
     print("flat_start.npz written", out["mean"].shape, out["var"].shape)
 
 
+def gmm_em_golden():
+    """Clustering.GMM.em(smem=False) (Clustering.py:583-651,695-719) executed on two small problems."""
+    H = rh.Harness(UNITS, MIX)
+    out = {}
+    for c, (n, M, seed) in enumerate([(160, 3, 5), (240, 4, 6)]):
+        rng = np.random.default_rng(seed)
+        centres = rng.normal(0, 0.35, size=(M, 39))
+        data = centres[rng.integers(0, M, size=n)] + rng.normal(size=(n, 39)) * rng.uniform(0.6, 1.2, size=(1, 39))
+        mean0 = centres + rng.normal(0, 0.25, size=centres.shape)
+        var0 = rng.uniform(0.8, 1.6, size=(M, 39))
+        alpha0 = np.ones(M) / M
+        g = H.Clustering.GMM(H.log, dimension=39, mix_level=M, data=list(data), alpha=alpha0.copy(), mean=mean0.copy(),
+                             covariance=np.stack([np.diag(v) for v in var0]))
+        iters = {"n": 0}
+        orig = g.expectation
+
+        def counted(orig=orig, iters=iters):
+            iters["n"] += 1
+            return orig()
+
+        g.expectation = counted
+        g.em(show_q=False, smem=False, c_covariance=1e-3)
+        out[f"e{c}_data"] = data
+        out[f"e{c}_mean0"] = mean0
+        out[f"e{c}_var0"] = var0
+        out[f"e{c}_alpha0"] = alpha0
+        out[f"e{c}_mean"] = np.array(g.mean)
+        out[f"e{c}_var"] = np.stack([np.diag(x) for x in g.covariance])
+        out[f"e{c}_alpha"] = np.array(g.alpha)
+        out[f"e{c}_iters"] = iters["n"]
+    out["n"] = 2
+    np.savez_compressed(os.path.join(OUT, "gmm_em.npz"), **out)
+    print("gmm_em.npz written", [int(out[f"e{c}_iters"]) for c in range(2)])
+
+
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
     if "--flat-start-only" in sys.argv:
         flat_start_golden()
         sys.exit(0)
+    if "--gmm-em-only" in sys.argv:
+        gmm_em_golden()
+        sys.exit(0)
     estep_golden()
     viterbi_ties_golden()
     kmeans_golden()
     flat_start_golden()
+    gmm_em_golden()

@@ -234,3 +234,28 @@ def test_flat_start_matches_executed_reference():
     assert np.all(alpha == 0.25)
     assert np.array_equal(tm[0], np.array([[0, 1, 0, 0, 0], [0, .5, .5, 0, 0], [0, 0, .5, .5, 0], [0, 0, 0, .5, .5],
                                            [0, 0, 0, 0, 0]], dtype=np.float64))
+
+
+def test_gmm_em_matches_executed_reference():
+    """§8 f2: Clustering.GMM.em(smem=False) (Clustering.py:583-651,695-719): expectation on the device
+    (K1 + K3 on a one-state pseudo unit), maximisation and Q in closed form on the sufficient
+    statistics.  Golden: the reference's own em() on two overlapping-cluster problems (5 iterations
+    each).  The fp32 statistics of one iteration feed the next, so the final parameters are held to
+    1e-3 (1e-4 per iteration)."""
+    from poccala_b200.Clustering import Clustering, DataUnLoadError
+
+    g = load_golden("gmm_em.npz")
+    for c in range(int(g["n"])):
+        data = g[f"e{c}_data"]
+        M = len(g[f"e{c}_alpha0"])
+        gm = Clustering.GMM(None, dimension=39, mix_level=M, data=list(data), alpha=g[f"e{c}_alpha0"].copy(),
+                            mean=g[f"e{c}_mean0"].copy(), variance=g[f"e{c}_var0"].copy())
+        gm.em(show_q=False, smem=False, c_covariance=1e-3)
+        assert gm.iterations == int(g[f"e{c}_iters"])
+        var = np.stack([np.diag(x) for x in gm.covariance])
+        assert np.all(np.abs(gm.alpha - g[f"e{c}_alpha"]) <= 1e-3 * np.maximum(g[f"e{c}_alpha"], 1e-2))
+        assert np.all(np.abs(gm.mean - g[f"e{c}_mean"]) <= 1e-3 * np.maximum(np.abs(g[f"e{c}_mean"]), np.sqrt(g[f"e{c}_var"])))
+        assert np.all(np.abs(var - g[f"e{c}_var"]) <= 1e-3 * g[f"e{c}_var"])
+        assert sorted(gm.theta()) == ["theta_%d" % i for i in range(M)]
+    with pytest.raises(DataUnLoadError):
+        Clustering.GMM(None, dimension=39, mix_level=2).em()
