@@ -63,8 +63,10 @@ const char *pc_last_error(void);
 /* One handle per device.  Fails (PC_ERR_CUDA) when the device is absent or not sm_100. */
 int pc_create(int device, pc_handle *out);
 int pc_destroy(pc_handle h);
-/* Select the kernel generation: 0 = CUDA-core kernels, 1 = tcgen05/TMA kernels (default when the
- * shape is covered).  Used by the tests to cross-check both on the same inputs. */
+/* Options: "tensor_core" 0 = CUDA-core kernels, 1 = tcgen05/TMA kernels (default when the shape is
+ * covered; the tests cross-check both on the same inputs); "host_chunks" caps the transfer pipeline
+ * depth of pc_em_iteration_host (0 = 8); "debug_flags" is a tuning aid for the tcgen05 kernels (skip
+ * stages, record block 0's phase clocks); read-only: "launches" (kernels launched), "sm_count". */
 int pc_set_option(pc_handle h, const char *key, int64_t value);
 int64_t pc_get_option(pc_handle h, const char *key);
 

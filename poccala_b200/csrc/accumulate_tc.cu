@@ -483,7 +483,7 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
         h->launches++;
     }
     kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc,
-                                                 h->fb_variant);
+                                                 h->debug_flags);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -491,7 +491,7 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
 
 }  // namespace
 
-// block 0's per-tile clocks (option fb_variant & 32): MMA warp [0] start, [1] tile landed, [2] S buffer
+// block 0's per-tile clocks (option debug_flags & 32): MMA warp [0] start, [1] tile landed, [2] S buffer
 // free, [3] MMA1 issued / waiting for P, [4] P ready; softmax group [5] start, [6] S ready, [7] P written
 extern "C" int pc_debug_read_acc(long long *host_out, int n) {
     return cudaMemcpyFromSymbol(host_out, g_acc_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -2;

@@ -70,8 +70,7 @@ int pc_destroy(pc_handle h) {
 int pc_set_option(pc_handle h, const char *key, int64_t value) {
     PC_REQUIRE(h && key, "pc_set_option: NULL argument");
     if (!strcmp(key, "tensor_core")) { h->use_tc = (int)value; return PC_OK; }
-    if (!strcmp(key, "fb_variant")) { h->fb_variant = (int)value; return PC_OK; }
-    if (!strcmp(key, "fb_cfg")) { h->fb_cfg = (int)value; return PC_OK; }
+    if (!strcmp(key, "debug_flags")) { h->debug_flags = (int)value; return PC_OK; }
     if (!strcmp(key, "host_chunks")) { h->host_chunks = (int)value; return PC_OK; }
     if (!strcmp(key, "launches")) { h->launches = value; return PC_OK; }
     pc_set_error("pc_set_option: unknown key '%s'", key);
@@ -81,8 +80,7 @@ int pc_set_option(pc_handle h, const char *key, int64_t value) {
 int64_t pc_get_option(pc_handle h, const char *key) {
     if (!h || !key) return -1;
     if (!strcmp(key, "tensor_core")) return h->use_tc;
-    if (!strcmp(key, "fb_variant")) return h->fb_variant;
-    if (!strcmp(key, "fb_cfg")) return h->fb_cfg;
+    if (!strcmp(key, "debug_flags")) return h->debug_flags;
     if (!strcmp(key, "host_chunks")) return h->host_chunks;
     if (!strcmp(key, "launches")) return h->launches;
     if (!strcmp(key, "sm_count")) return h->sm_count;

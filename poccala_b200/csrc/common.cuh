@@ -123,8 +123,9 @@ struct pc_handle_s {
     int device;
     int sm_count;
     int use_tc;          // option "tensor_core"
-    int fb_variant;      // option "fb_variant"
-    int fb_cfg;          // option "fb_cfg": K2 launch shape experiments
+    // option "debug_flags" (tuning aid for the tcgen05 kernels): 1 skip epilogue math, 2 skip MMAs, 4 / 8 skip
+    // the B / A bulk copies, 16 skip the epilogue, 32 record block 0's phase clocks (pc_debug_read*)
+    int debug_flags;
     int host_chunks;     // option "host_chunks": cap on the transfer pipeline depth (0 = PC_MAX_CHUNKS)
     int64_t launches;    // kernels launched through this handle (bench: gpu_launches)
     // workspace for the host-buffer entry point

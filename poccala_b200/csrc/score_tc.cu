@@ -425,7 +425,7 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
     const int n = item_hi - item_lo;
     int grid = n < h->sm_count ? n : h->sm_count;
     kern<<<grid, Cfg<MIX>::NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, item_lo, item_hi,
-                                                          h->fb_variant);
+                                                          h->debug_flags);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

@@ -1,5 +1,5 @@
 """Micro-experiments on the scoring / accumulation kernels (bench workload): kernel-only timings
-under debug flags (fb_variant option doubles as the debug word for the tcgen05 kernels)."""
+under debug flags (option "debug_flags" is the debug word for the tcgen05 kernels)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -30,7 +30,7 @@ st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def k1(): nat.call("pc_gmm_score", eng.h, corpus.c, _p(corpus.X), _p(model.W), MIX, _p(es.b), st())
 def k3(): nat.call("pc_accumulate", eng.h, corpus.c, _p(corpus.X), _p(model.W), MIX, _p(es.b), _p(es.lgam), _p(es.acc), st())
 for flags in [int(a) for a in sys.argv[1:]] or [0]:
-    eng.set_option("fb_variant", flags)
+    eng.set_option("debug_flags", flags)
     print("flags", flags, "K1 us %.1f" % t_kernel(k1), "K3 us %.1f" % t_kernel(k3), flush=True)
-eng.set_option("fb_variant", 0)
+eng.set_option("debug_flags", 0)
 print("K3 active (tile, unit) pairs: %d of %d" % (nat.lib().pc_corpus_active_tiles(corpus.c), nat.lib().pc_corpus_total_tiles(corpus.c)))

@@ -1,4 +1,4 @@
-"""K2 launch-shape experiment on the bench workload: python profiles/exp_k2.py"""
+"""K2 timing and block 0 phase clocks on the bench workload: python profiles/exp_k2.py"""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -13,8 +13,7 @@ es = EStep(eng, corpus, model)
 es.load_frames(x)
 es.score()
 ref = None
-for cfg in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 5]:
-    eng.set_option("fb_cfg", cfg)
+for cfg in [0]:
     for _ in range(3):
         es.forward_backward()
     torch.cuda.synchronize()
@@ -29,7 +28,7 @@ for cfg in [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 5]:
     ev[1].record()
     torch.cuda.synchronize()
     lp = es.utt_logp.sum().item()
-    print("fb_cfg %d: %.1f us per call, sum logp %.6f" % (cfg, ev[0].elapsed_time(ev[1]) * 100, lp), flush=True)
+    print("K2: %.1f us per call, sum logp %.6f" % (ev[0].elapsed_time(ev[1]) * 100, lp), flush=True)
 
 import ctypes as C
 buf = (C.c_longlong * 16)()

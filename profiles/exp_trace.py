@@ -11,7 +11,7 @@ corpus = Corpus(eng, labels, np.full(N_UTT, T, dtype=np.int32), N_UNITS)
 model = Model(eng, *init, synth.default_transmat(N_UNITS))
 es = EStep(eng, corpus, model); es.load_frames(x); es.score(); torch.cuda.synchronize()
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-eng.set_option("fb_variant", flags)
+eng.set_option("debug_flags", flags)
 for _ in range(3):
     nat.call("pc_gmm_score", eng.h, corpus.c, _p(corpus.X), _p(model.W), MIX, _p(es.b), C.c_void_p(0))
 torch.cuda.synchronize()

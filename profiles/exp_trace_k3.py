@@ -9,7 +9,7 @@ truth, init, labels, x = synth.torch_corpus(N_UTT, T, L, N_UNITS, MIX, 2, eng.de
 corpus = Corpus(eng, labels, np.full(N_UTT, T, dtype=np.int32), N_UNITS)
 model = Model(eng, *init, synth.default_transmat(N_UNITS))
 es = EStep(eng, corpus, model); es.load_frames(x); es.score(); es.forward_backward(); torch.cuda.synchronize()
-eng.set_option("fb_variant", 32)
+eng.set_option("debug_flags", 32)
 for _ in range(2): es.accumulate()
 torch.cuda.synchronize()
 buf = (C.c_longlong * 8000)()
