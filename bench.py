@@ -311,6 +311,7 @@ def run_gpu(args):
         return
     pk, pk_src = peaks()
     vit = viterbi_leg(eng, pk)
+    sweep = scoring_sweep_leg(eng, pk)
     # dominant kernel and its roofline: K1/K3 are contractions, 158 flops per
     # (frame, Gaussian) pair; K2 moves 8 B per (emitting state, frame)
     pairs = frames * 3 * L * MIX
@@ -348,12 +349,65 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "viterbi": vit,
+        "scoring_sweep": sweep,
         "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d utterances x %d frames of the same workload (E-step), %.1f s" % (n_sample, T, cpu_wall)},
     }
     print(json.dumps(line), flush=True)
     if group is not None:
         dist.destroy_process_group()
+
+
+def scoring_sweep_leg(eng, pk, F=2_000_000, G=4096, mix=64):
+    """BASELINE.json configs[2] (GMM scoring sweep) on one GPU at a bounded size: F frames x G
+    39-dim diagonal Gaussians, 64 mixtures per state, through the tcgen05 scoring kernel
+    (Engine.score_dense_tc's layout; profiles/bench_cfg3.py runs the full 4k-64k sweep).
+    Tensor roofline: 158 flop per (frame, Gaussian) pair against the measured bf16 peak (the 3-product
+    fp16 split executes 3x these flops)."""
+    import torch
+
+    from poccala_b200 import _native as nat
+    from poccala_b200.engine import EMIT, Corpus, _p, _stream
+
+    dev = eng.device
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3)
+    x = torch.randn((F, DIM), generator=gen, device=dev, dtype=torch.float32)
+    mean = torch.randn((G, DIM), generator=gen, device=dev, dtype=torch.float64)
+    var = torch.rand((G, DIM), generator=gen, device=dev, dtype=torch.float64) + 0.5
+    alpha = torch.full((G,), 1.0 / mix, device=dev, dtype=torch.float64)
+    U = (G // mix + EMIT - 1) // EMIT
+    pad = U * EMIT * mix - G
+    if pad:
+        mean = torch.cat([mean, torch.zeros((pad, DIM), dtype=mean.dtype, device=dev)])
+        var = torch.cat([var, torch.ones((pad, DIM), dtype=var.dtype, device=dev)])
+        alpha = torch.cat([alpha, torch.zeros((pad,), dtype=alpha.dtype, device=dev)])
+    n_frames = np.full((F + 383) // 384, 384, dtype=np.int32)
+    if F % 384:
+        n_frames[-1] = F % 384
+    labels = np.ascontiguousarray(np.broadcast_to(np.arange(U, dtype=np.int32), (len(n_frames), U)))
+    corpus = Corpus(eng, labels, n_frames, U)
+    W = eng.pack_gmm(mean, var, alpha, mix=mix)
+    X = eng.prepare_frames(corpus, x)
+    b = eng.empty((corpus.emis_floats,), torch.float32)
+
+    def run():
+        nat.call("pc_gmm_score", eng.h, corpus.c, _p(X), _p(W), mix, _p(b), _stream())
+
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    tf = 158.0 * F * G / (ms * 1e-3) / 1e12
+    peak = float(pk["bf16_tflops_sustained"])
+    return {"value": F / (ms * 1e-3), "unit": "frames/s", "ms": ms,
+            "workload": "cfg3 shape: %d frames x %d Gaussians (39-dim diag, %d-mix), inputs larger than L2" % (F, G, mix),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak}}
 
 
 def viterbi_leg(eng, pk, n_utt=2000, T_v=1000, L_v=20, reps=5):

@@ -113,6 +113,38 @@ class Engine:
         return out
 
 
+    def score_dense_tc(self, x, mean, var, alpha, mix, frames_per_group=384, shift=None, inv_scale=None):
+        """Every frame against every state of ONE model (the GMM scoring sweep of BASELINE.json
+        configs[2]; LHMM.cal_observation_pro's arithmetic, LHMM.py:163-187) on the tensor-core kernel:
+        the frames are cut into groups of `frames_per_group`, each a pseudo utterance labelled with all
+        ceil(S/3) pseudo units, so K1 streams the whole model past every group of three frame tiles.
+        x [F,D] device tensor; mean / var [S*mix, D], alpha [S*mix] fp64 device tensors (S states).
+        Returns b [F, S] fp32 (a view of the [F, SP] emission buffer)."""
+        F, D = x.shape
+        G = mean.shape[0]
+        if G % mix:
+            raise ValueError("number of Gaussians is not a multiple of mix")
+        S = G // mix
+        U = (S + EMIT - 1) // EMIT
+        pad = U * EMIT * mix - G
+        if pad:  # dead Gaussians (alpha = 0) fill the last pseudo unit
+            mean = torch.cat([mean, torch.zeros((pad, D), dtype=mean.dtype, device=mean.device)])
+            var = torch.cat([var, torch.ones((pad, D), dtype=var.dtype, device=var.device)])
+            alpha = torch.cat([alpha, torch.zeros((pad,), dtype=alpha.dtype, device=alpha.device)])
+        n_frames = np.full((F + frames_per_group - 1) // frames_per_group, frames_per_group, dtype=np.int32)
+        if F % frames_per_group:
+            n_frames[-1] = F % frames_per_group
+        labels = np.ascontiguousarray(np.broadcast_to(np.arange(U, dtype=np.int32), (len(n_frames), U)))
+        corpus = Corpus(self, labels, n_frames, U)
+        W = self.pack_gmm(mean.contiguous(), var.contiguous(), alpha.contiguous(), shift, inv_scale, mix=mix)
+        X = self.prepare_frames(corpus, x, shift, inv_scale)
+        b = self.empty((corpus.emis_floats,), torch.float32)
+        nat.call("pc_gmm_score", self.h, corpus.c, _p(X), _p(W), int(mix), _p(b), _stream())
+        sp = (EMIT * U + 7) & ~7
+        self._dense_keep = (corpus, X, W)  # alive until the stream has run
+        return b.view(F, sp)[:, :S]
+
+
 class Corpus:
     """Descriptor tables of a set of utterances (pc_corpus) + the resident frame matrix."""
 

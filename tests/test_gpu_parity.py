@@ -361,6 +361,30 @@ def test_dense_scoring_matches_oracle(eng):
     assert _relerr(out, ref) < REL
 
 
+@pytest.mark.parametrize("mix,n_states", [(16, 40), (64, 7), (4, 3)])
+def test_dense_scoring_tensor_core_matches_oracle(eng, mix, n_states):
+    """configs[2] shape at test size: every frame against every state of one model through the tcgen05
+    kernel (frames in groups of 384 labelled with all pseudo units), against the fp64 closed form and
+    the CUDA-core dense kernel."""
+    rng = np.random.default_rng(100 + mix)
+    F = 1000
+    mean = rng.normal(size=(n_states * mix, 39))
+    var = rng.uniform(0.5, 1.5, size=(n_states * mix, 39))
+    alpha = rng.dirichlet(np.full(mix, 2.0), size=n_states).reshape(-1)
+    x = rng.normal(size=(F, 39))
+    dev = eng.device
+    t = lambda a: torch.as_tensor(a).to(dev)
+    out = eng.score_dense_tc(t(x), t(mean), t(var), t(alpha), mix).cpu().numpy()
+    d = x[:, None, :] - mean[None]
+    c = np.log(alpha) - 39 / 2 * np.log(2 * np.pi) - 0.5 * var.sum(-1) - 0.5 * (d * d / var).sum(-1)
+    ref = fast.lse(c.reshape(F, n_states, mix), axis=-1)
+    assert out.shape == ref.shape
+    assert _relerr(out, ref) < REL
+    W = eng.pack_gmm(t(mean), t(var), t(alpha))
+    simt = eng.score_dense(eng.prepare_rows(t(x)), W, n_states, mix).cpu().numpy()
+    assert np.abs(out - simt).max() < 2e-3
+
+
 def test_error_behaviour(eng):
     from poccala_b200 import _native as nat
     from poccala_b200.engine import Corpus
