@@ -12,7 +12,7 @@
 // K-major A operand of MMA1 (K = feature) and, through an MN-major descriptor over the same bytes,
 // as the A operand of MMA2 (M = feature, K = frame).  P (scaled by 2^15 to sit in the fp16 range)
 // is written by the softmax warps as the MN-major B operand of MMA2.  Work is UNIT-major so that
-// D2 stays in TMEM for a whole work item (<= 32 tiles of one unit) before one fp64-atomic flush.
+// D2 stays in TMEM for a whole work item (<= 64 tiles of one unit) before one fp64-atomic flush.
 //
 //   warp 19     TMA producer : per item the unit's Gaussian rows (B), per tile 20 x 2 KiB of frames
 //   warp 20     MMA issuer   : MMA1(i), then MMA2(i-1) (software pipelined), commits
@@ -66,9 +66,28 @@ __global__ void tile_active_kernel(CorpusView v, const float *__restrict__ lgam,
             m3 = fmaxf(m3, __ldg(base + (size_t)(r + 3) * sp + c));
         }
         for (; r < rows; ++r) m0 = fmaxf(m0, __ldg(base + (size_t)r * sp + c));
-        if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > ACTIVE_MIN_LGAM)
-            active[v.pair_tile0[p0 + c / PC_EMIT] + t0 / PC_TILE_ROWS] = 1;
+        if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > ACTIVE_MIN_LGAM) {
+            const int64_t tile = v.pair_tile0[p0 + c / PC_EMIT] + t0 / PC_TILE_ROWS;
+            if (atomicExch(active + tile, 1) == 0) atomicAdd(v.item_act + v.tile_item[tile], 1);  // once per tile
+        }
     }
+}
+
+// Work items differ a lot in how many of their tiles are active; with a static round-robin over the
+// SMs the kernel ends with its slowest SM.  One block orders the items by active tiles (counting
+// sort, heaviest first); the main kernel deals them out in snake order.
+__global__ void item_order_kernel(int n_items, const int32_t *__restrict__ item_act, int32_t *__restrict__ order) {
+    __shared__ int bin[64];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) bin[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) atomicAdd(&bin[63 - min(item_act[i], 63)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; ++k) { const int c = bin[k]; bin[k] = run; run += c; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) order[atomicAdd(&bin[63 - min(item_act[i], 63)], 1)] = i;
 }
 
 // NC = Gaussians handled per work item (a unit's 3*MIX Gaussians, or a slice of them)
@@ -100,7 +119,7 @@ struct Cfg {
 };
 
 struct Bars {
-    uint64_t a_full[3], a_empty[3];
+    uint64_t a_full[4], a_empty[4];
     uint64_t b_full, b_empty;
     uint64_t s_full[2], s_empty[2];
     uint64_t p_full[2], p_empty[2];
@@ -171,7 +190,7 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) { tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&bars->a_full[i], 1); tc::mbar_init(&bars->a_empty[i], 1); }
         tc::mbar_init(&bars->b_full, 1);
         tc::mbar_init(&bars->b_empty, 1);
         for (int i = 0; i < 2; ++i) {
@@ -201,24 +220,38 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
     constexpr uint32_t B_BYTES = C::NPAD / 8 * PC_WGROUP_BYTES;               // bytes of a slice
 
     uint32_t n_tile = 0, n_item = 0;  // running counters (tiles, items) of this CTA
+    long long t_begin = 0;
+    if ((dbg & 32) && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     const int n_work = v.n_items * C::N_SLICES;
-    for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++n_item) {
-        const int item = work / C::N_SLICES, slice = work - item * C::N_SLICES;
+    for (int round = 0;; ++round, ++n_item) {
+        // snake order over the sorted items: the SM that got the heaviest item of this round gets the
+        // lightest of the next
+        const int work = round * (int)gridDim.x + ((round & 1) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x);
+        if (round * (int)gridDim.x >= n_work) break;
+        if (work >= n_work) {
+            --n_item;  // nothing for this SM in the last, partial round
+            continue;
+        }
+        const int item = v.item_order[work / C::N_SLICES], slice = work % C::N_SLICES;
         const int unit = v.item_unit[item];
         const int g0 = slice * C::NC;  // first Gaussian of the slice inside the unit
         const size_t gfirst = (size_t)unit * C::N_UNIT + g0;
         const int64_t lo = v.item_tile_lo[item], hi = v.item_tile_lo[item + 1];
-        // the item's active tiles as a bit mask (an item has at most 32 tiles); every warp forms the
+        // the item's active tiles as a bit mask (an item has at most 64 tiles: two 32-bit masks); every warp forms the
         // same mask, so all roles skip the same tiles - and an item without any - consistently
-        const uint32_t amask = __ballot_sync(0xffffffffu, lane < (int)(hi - lo) && __ldg(active + lo + lane) != 0);
-        if (amask == 0u) {
+        const uint32_t amask0 = __ballot_sync(0xffffffffu, lane < (int)(hi - lo) && __ldg(active + lo + lane) != 0);
+        const uint32_t amask1 = __ballot_sync(0xffffffffu, 32 + lane < (int)(hi - lo) && __ldg(active + lo + 32 + lane) != 0);
+        if ((amask0 | amask1) == 0u) {
             --n_item;  // compensates the loop increment: barrier parities count non-empty items only
             continue;
         }
-        const int n_tiles_ = __popc(amask);
+        const int n_lo = __popc(amask0);
+        const int n_tiles_ = n_lo + __popc(amask1);
         const int n_tiles = n_tiles_;
         // i-th active tile of the item -> tile index
-        auto nth_tile = [&](int i) { return lo + (int64_t)(__fns(amask, 0, i + 1)); };
+        auto nth_tile = [&](int i) {
+            return lo + (int64_t)(i < n_lo ? __fns(amask0, 0, i + 1) : 32 + __fns(amask1, 0, i - n_lo + 1));
+        };
 
         if (warp == W_PROD) {
             // ------------------------------------------------------------ TMA producer
@@ -463,6 +496,14 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
     }
     tc::tc_fence_before();
     __syncthreads();
+    if ((dbg & 32) && threadIdx.x == 0) {  // per block: wall nanoseconds, tiles and items processed
+        long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        g_acc_dbg[4096 + blockIdx.x * 4 + 0] = t_begin;
+        g_acc_dbg[4096 + blockIdx.x * 4 + 1] = t_end;
+        g_acc_dbg[4096 + blockIdx.x * 4 + 2] = n_tile;
+        g_acc_dbg[4096 + blockIdx.x * 4 + 3] = n_item;
+    }
     if (warp == W_MMA) tc::tmem_dealloc(tmem_base, C::TM_COLS);
 }
 
@@ -478,9 +519,12 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
         const int threads = 128;
         const int64_t blocks = (warps * 32 + threads - 1) / threads;
         PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)v.n_tiles * sizeof(int32_t), st));
+        PC_CUDA_TRY(cudaMemsetAsync(v.item_act, 0, (size_t)v.n_items * sizeof(int32_t), st));
         tile_active_kernel<<<(unsigned)blocks, threads, 0, st>>>(v, lgam, v.tile_active);
         PC_LAUNCH_CHECK();
-        h->launches++;
+        item_order_kernel<<<1, 1024, 0, st>>>(v.n_items, v.item_act, v.item_order);
+        PC_LAUNCH_CHECK();
+        h->launches += 2;
     }
     kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc,
                                                  h->debug_flags);

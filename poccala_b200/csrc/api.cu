@@ -195,9 +195,10 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     const int64_t n_tiles = (int64_t)tile_pair.size();
     // work items: runs of <= chunk tiles inside one unit; aim at >= 8 items per SM
     int64_t chunk = n_tiles / ((int64_t)h->sm_count * 8);
-    // <= 32 tiles: the accumulation kernel keeps an item's sums in fp32 (TMEM) before the fp64 flush
-    // and addresses an item's tiles through a 32-bit activity mask (typically under half are active)
-    chunk = std::max<int64_t>(4, std::min<int64_t>(32, chunk));
+    // <= 64 tiles: the accumulation kernel keeps an item's sums in fp32 (TMEM) before the fp64 flush
+    // and addresses an item's tiles through two 32-bit activity masks (typically under half are
+    // active); every item costs a pipeline drain / fill and a flush of ~10 000 clk
+    chunk = std::max<int64_t>(4, std::min<int64_t>(64, 2 * chunk));
     std::vector<int64_t> item_tile_lo;
     std::vector<int32_t> item_unit;
     for (size_t blk = 0; blk + 1 < run_tile_off.size(); ++blk)
@@ -206,6 +207,9 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
             item_unit.push_back((int32_t)(blk % (size_t)n_units));
         }
     item_tile_lo.push_back(n_tiles);
+    std::vector<int32_t> tile_item((size_t)n_tiles);
+    for (size_t it = 0; it + 1 < item_tile_lo.size(); ++it)
+        for (int64_t t = item_tile_lo[it]; t < item_tile_lo[it + 1]; ++t) tile_item[(size_t)t] = (int32_t)it;
     const int64_t n_items = (int64_t)item_unit.size();
     PC_REQUIRE(n_items < 2147483647LL, "pc_corpus_create: too many work items");
     // transfer chunks for the host-buffer entry point: <= PC_MAX_CHUNKS runs of consecutive
@@ -281,6 +285,9 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 16);  // float4 per frame (K2)
     size_t o_scratch1 = add(nullptr, (size_t)emis_off[n_utt] * 4);    // beta_hat rows (K2)
     size_t o_tact = add(nullptr, (size_t)n_tiles * 4);                 // active-tile flags (K3)
+    size_t o_titem = add(tile_item.data(), (size_t)n_tiles * 4);
+    size_t o_iact = add(nullptr, (size_t)n_items * 4);
+    size_t o_iord = add(nullptr, (size_t)n_items * 4);
     size_t o_sutt = add(sitem_utt.data(), (size_t)n_sitems * 4);
     size_t o_st0 = add(sitem_t0.data(), (size_t)n_sitems * 4);
     size_t o_snt = add(sitem_nt.data(), (size_t)n_sitems * 4);
@@ -345,6 +352,9 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     v.scratch0 = (float *)(dev + o_scratch);
     v.scratch1 = (float *)(dev + o_scratch1);
     v.tile_active = (int32_t *)(dev + o_tact);
+    v.tile_item = (const int32_t *)(dev + o_titem);
+    v.item_act = (int32_t *)(dev + o_iact);
+    v.item_order = (int32_t *)(dev + o_iord);
     v.total_frames = frame_off[n_utt];
     v.n_sitems = (int32_t)n_sitems;
     v.sitem_utt = (const int32_t *)(dev + o_sutt);

@@ -15,7 +15,7 @@
 __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 #define PC_NEG_INF (-INFINITY)
-#define PC_L2_RUN_BYTES (32ll << 20)  // frame-tile images one K3 run of utterances may span (L2 = 126 MB)
+#define PC_L2_RUN_BYTES (64ll << 20)  // frame-tile images one K3 run of utterances may span (L2 = 126 MB)
 #define PC_MAX_CHUNKS 8  // host-buffer entry point: transfer / prepare / score pipeline depth
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
@@ -49,6 +49,9 @@ struct CorpusView {
     float *scratch0;              // [total_frames] float4 per frame (K2 scratch: beta_hat of the entry state)
     float *scratch1;              // [emission floats] K2 scratch: beta_hat rows, same layout as b / lgam
     int32_t *tile_active;         // [n_tiles] K3 scratch: 1 = the tile carries posterior mass
+    const int32_t *tile_item;     // [n_tiles] work item of each unit-major tile
+    int32_t *item_act;            // [n_items] K3 scratch: active tiles of the item
+    int32_t *item_order;          // [n_items] K3 scratch: items sorted by active tiles, heaviest first
     // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
     int64_t total_frames;
     int32_t n_sitems;

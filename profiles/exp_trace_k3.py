@@ -12,9 +12,13 @@ es = EStep(eng, corpus, model); es.load_frames(x); es.score(); es.forward_backwa
 eng.set_option("debug_flags", 32)
 for _ in range(2): es.accumulate()
 torch.cuda.synchronize()
-buf = (C.c_longlong * 8000)()
-lib = nat.lib(); lib.pc_debug_read_acc.argtypes = [C.c_void_p, C.c_int]; lib.pc_debug_read_acc(buf, 8000)
-a = np.array(buf[:]).reshape(1000, 8)
+buf = (C.c_longlong * 8192)()
+lib = nat.lib(); lib.pc_debug_read_acc.argtypes = [C.c_void_p, C.c_int]; lib.pc_debug_read_acc(buf, 8192)
+blk = np.array(buf[4096:4096 + 148 * 4]).reshape(148, 4)
+t0 = blk[:, 0].min()
+print('per block: start us min/max %.1f %.1f | end us min/median/max %.1f %.1f %.1f | tiles min/median/max %d %d %d | items %d..%d' % ((blk[:,0].min()-t0)/1e3, (blk[:,0].max()-t0)/1e3, (blk[:,1].min()-t0)/1e3, np.median(blk[:,1]-t0)/1e3, (blk[:,1].max()-t0)/1e3, blk[:,2].min(), np.median(blk[:,2]), blk[:,2].max(), blk[:,3].min(), blk[:,3].max()))
+print('ns per tile per block: min/median/max %.0f %.0f %.0f' % tuple(np.percentile((blk[:,1]-blk[:,0])/np.maximum(blk[:,2],1), [0,50,100])))
+a = np.array(buf[:8000]).reshape(1000, 8)
 n = 80
 a = a[:n] - a[0, 0]
 np.set_printoptions(linewidth=220)
