@@ -224,6 +224,37 @@ int pc_kmeans_finish(pc_handle h, int32_t n_problems, const int64_t *host_point_
                      const int32_t *dev_member_list, const int32_t *dev_member_count,
                      double *dev_mean, double *dev_var, double *dev_alpha, void *stream);
 
+/* ---- alignment post-processing ---------------------------------------------
+ * The steps either side of Viterbi / k-means in the reference's mode-1 training.
+ * pc_segment_keys: per frame the (unit, emitting state) whose data set the frame joins, as
+ * key = unit * 3 + state, or -1 when the frame is dropped.
+ *   mode 0  uniform segmentation, AcousticModel.__eq_segment(mode='e') (AcousticModel.py:605-612):
+ *           L chunks of T // L frames per utterance, the remainder dropped; dev_path is ignored
+ *   mode 1  after forced alignment, multi_process_data (AcousticModel.py:750-764): dev_path is the
+ *           composite-state path pc_viterbi wrote; the per-frame unit sequence is cut into maximal
+ *           runs of one unit (discriminate, :937-955); an utterance whose path visits fewer
+ *           distinct units than its label holds is dropped (dev_utt_kept = 0, :753-757)
+ * Every segment of n frames is then cut into 3 parts of n // 3 frames, the last taking the
+ * remainder (__eq_segment(mode='g') :613-626, __get_gmmdata :630-644).
+ * dev_frame_key int32 [total_frames]; dev_utt_kept int32 [n_utt] or NULL. */
+int pc_segment_keys(pc_handle h, pc_corpus c, int32_t mode, const int32_t *dev_path,
+                    int32_t *dev_frame_key, int32_t *dev_utt_kept, void *stream);
+
+/* Stable counting sort of the frames by key: frames of one key become contiguous, in ascending
+ * frame order (= utterance, then time: the order __get_gmmdata concatenates segments in).
+ *   dev_key_off int64 [n_keys + 2]: first slot of each key; [n_keys] = kept frames (keys outside
+ *               [0, n_keys) sort last); [n_keys + 1] = n_frames
+ *   dev_order   int32 [n_frames]: frame index held by each slot
+ * n_frames < 2^31, n_keys <= 12000.  Workspace: pc_group_workspace_bytes (-1 on bad sizes). */
+int64_t pc_group_workspace_bytes(int64_t n_frames, int32_t n_keys);
+int pc_group_frames(pc_handle h, const int32_t *dev_frame_key, int64_t n_frames, int32_t n_keys,
+                    void *dev_workspace, int64_t *dev_key_off, int32_t *dev_order, void *stream);
+
+/* dst[i] = src[order[i]] for rows of row_bytes bytes (a multiple of 4): the per-state data sets
+ * (AcousticModel.__get_gmmdata) that pc_kmeans_run and the stand-alone GMM EM consume. */
+int pc_gather_rows(pc_handle h, const int32_t *dev_order, int64_t n_rows, int32_t row_bytes,
+                   const void *dev_src, void *dev_dst, void *stream);
+
 /* ---- host-buffer entry point (end-to-end) --------------------------------------------------
  * One full EM iteration the way AcousticModel.embedded_training runs it (AcousticModel.py:842-882)
  * with HOST inputs and outputs: frames [total_frames][dim] float (pinned or pageable), parameters

@@ -466,3 +466,98 @@ def kmeans_compat(data, k, rng_random, max_passes=10 ** 9):
         var[kk] = (v ** 0.5) ** 2
     alpha = np.array([len(m) / n for m in members])
     return dict(mean=centre, var=var, alpha=alpha, owner=owner, members=members, passes=passes, seeds=seeds)
+
+
+# --------------------------------------------------------------------------- alignment post-processing (§8 f3)
+def split_segment(n, parts=E):
+    """AcousticModel.__eq_segment(mode='g') (AcousticModel.py:613-626): a segment of n frames cut
+    into `parts` slices of n // parts frames, the last slice taking the remainder.  Returns the
+    (start, end) offsets of the slices (empty slices when n < parts)."""
+    chunk = n // parts
+    cuts = [(i * chunk, (i + 1) * chunk) for i in range(parts - 1)]
+    cuts.append(((parts - 1) * chunk, n))
+    return cuts
+
+
+def segment_uniform(label, T):
+    """AcousticModel.__eq_segment(mode='e') (AcousticModel.py:605-612): T frames cut into len(label)
+    chunks of T // len(label) frames in label order; the remainder is never saved.
+    Returns [(unit, start, end)]."""
+    chunk = T // len(label)
+    return [(u, p * chunk, (p + 1) * chunk) for p, u in enumerate(label)]
+
+
+def discriminate(unit, sequence):
+    """AcousticModel.discriminate (AcousticModel.py:937-955): the frames labelled `unit`, one index
+    array per maximal run of consecutive frames (time order)."""
+    loc = np.flatnonzero(np.asarray(sequence) == unit)
+    runs = {}
+    for rank, f in enumerate(loc):
+        runs.setdefault(int(f) - rank, []).append(int(f))  # consecutive frames share f - rank
+    return [np.array(runs[k]) for k in sorted(runs)]
+
+
+def segment_alignment(label, unit_sequence):
+    """multi_process_data after Viterbi (AcousticModel.py:750-764): None when the aligned sequence
+    holds fewer distinct units than the label (the utterance is discarded, :753-757), else
+    [(unit, start, end)] for every run of every unit, in time order."""
+    seq = np.asarray(unit_sequence)
+    if len(set(seq.tolist())) < len(set(label)):
+        return None
+    out = []
+    for u in set(label):
+        for run in discriminate(u, seq):
+            out.append((u, int(run[0]), int(run[-1]) + 1))
+    return sorted(out, key=lambda s: s[1])
+
+
+def state_frames(segments_per_utt, frame_off, n_units):
+    """AcousticModel.__get_gmmdata (AcousticModel.py:630-644) over a corpus: for every (unit, state)
+    the corpus frame indices of its data set - each unit segment cut by `split_segment`, slices
+    concatenated in (utterance, time) order.  segments_per_utt[u] = [(unit, start, end)] or None.
+    Returns a list indexed by unit * 3 + state of int64 arrays."""
+    sets = [[] for _ in range(n_units * E)]
+    for u, segs in enumerate(segments_per_utt):
+        if segs is None:
+            continue
+        for unit, s, e in segs:
+            for r, (a, b) in enumerate(split_segment(e - s)):
+                sets[unit * E + r].extend(range(int(frame_off[u]) + s + a, int(frame_off[u]) + s + b))
+    return [np.array(x, dtype=np.int64) for x in sets]
+
+
+# --------------------------------------------------------------------------- stand-alone GMM EM (§8 f2)
+def gmm_em(data, mean, var, alpha, c_covariance=1e-3, max_iter=10 ** 6):
+    """Clustering.GMM.em(smem=False) (Clustering.py:695-719) in linear fp64 arithmetic:
+    expectation (:583-600) - posteriors from the reference's log-Gaussian (Q1: -1/2 sum(var));
+    maximization (:619-651) - mean, variance around the NEW mean floored at c_covariance,
+    alpha = occupancy / n; q_function (:602-613) with the new parameters; loop while Q grows by
+    more than 1.28.  Returns (mean, var, alpha, iterations, q_value); `gmm_em.margin` afterwards holds
+    the smallest distance of a Q increment from the 1.28 threshold (tests skip knife-edge cases)."""
+    X = np.asarray(data, dtype=np.float64)
+    mean, var, alpha = (np.array(a, dtype=np.float64) for a in (mean, var, alpha))
+    n, D = X.shape
+
+    def log_density(mean, var):  # [n, M]
+        d = X[:, None, :] - mean[None]
+        return -0.5 * D * LOG_2PI - 0.5 * var.sum(-1)[None] - 0.5 * (d * d / var[None]).sum(-1)
+
+    q_value, iters = -np.inf, 0
+    gmm_em.margin = np.inf
+    while iters < max_iter:
+        iters += 1
+        lg = log_density(mean, var) + np.log(alpha)[None]
+        gam = np.exp(lg - lse(lg, axis=1, keepdims=True))
+        occ = gam.sum(0)
+        mean = (gam.T @ X) / occ[:, None]
+        d = X[:, None, :] - mean[None]
+        var = np.einsum("nm,nmd->md", gam, d * d) / occ[:, None]
+        var = np.where(var < c_covariance, c_covariance, var)
+        alpha = occ / n
+        q = float((occ * np.log(alpha)).sum() + (gam * log_density(mean, var)).sum())
+        gmm_em.margin = min(gmm_em.margin, abs(q - q_value - 1.28))
+        if q - q_value > 1.28:
+            q_value = q
+        else:
+            break
+    return mean, var, alpha, iters, q_value

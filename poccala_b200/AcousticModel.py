@@ -29,6 +29,10 @@ from .runtime import NullLog, get_engine
 EMIT = _eng.EMIT
 
 
+class ModeError(Exception):
+    """Exceptions.ModeError: a training mode other than 1 / 2 (AcousticModel.py:732, 800)."""
+
+
 class UnitFileExistsError(Exception):
     """Exceptions.UnitFileExistsError: the unit inventory file is missing (AcousticModel.py:143-144)."""
 
@@ -54,6 +58,9 @@ class AcousticModel(object):
         self.__params = {}   # unit -> dict(mean[3,M,D], var[3,M,D], alpha[3,M], transmat[5,5])
         self.__acc = {}      # unit -> dict(ksai, gamma, gmm=[(occ, socc, sx, scc)]*3) for the per-utterance path
         self.__corpus = None
+        self.__frames = None
+        self.__utterances = None
+        self.__state_data = None  # per-(unit, state) data sets grouped by process_data(mode=1)
         self.__estep = None
         self.__model = None
         self.last_log_likelihood = None
@@ -278,6 +285,8 @@ class AcousticModel(object):
         n_frames = np.array([len(x) for x in data], dtype=np.int32)
         self.__corpus = _eng.Corpus(eng, lab, n_frames, len(self.__loaded_units))
         self.__frames = torch.as_tensor(np.concatenate([np.asarray(x) for x in data], axis=0)).to(eng.device)
+        self.__utterances = data
+        self.__state_data = None
         self.__estep = None
         return self.__corpus
 
@@ -313,12 +322,96 @@ class AcousticModel(object):
             self.log.note("sum log P(O) = %f" % self.last_log_likelihood, cls="i")
         return self.last_log_likelihood
 
+    # ---- mode 1: segment -> per-state data sets -> k-means / GMM EM --------
+    def process_data(self, mode=1, load_line=0, init=True, proportion=0.25, step=1, differentiation=True,
+                     coefficient=1):
+        """AcousticModel.py:681-733 over the resident corpus.  Mode 1: every utterance is cut
+        uniformly over its units (init, `__eq_segment` mode 'e', :605-612) or along the forced
+        alignment of the current models (multi_process_data, :736-764), each unit segment in three
+        (`__get_gmmdata`, :630-644), and the frames are grouped per (unit, state) on the device -
+        what the reference spreads over one pickle per segment.  Mode 2 with init: the flat start."""
+        if self.__corpus is None:
+            raise RuntimeError("add_corpus(labels, data) first")
+        if mode == 2:
+            if init:
+                self.flat_start(self.__utterances, proportion=proportion, step=step, differentiation=differentiation,
+                                coefficient=coefficient)
+            return None
+        if mode != 1:
+            raise ModeError("mode must be 1 or 2 (Exceptions.ModeError)")
+        path = None
+        if not init:
+            self.log.note("Viterbi Alignment...", cls="i")
+            _, path, _ = self.align()
+        key, kept = _eng.segment_keys(self.engine, self.__corpus, path)
+        frames = self.__frames if self.__frames.dtype == torch.float64 else self.__frames.double()
+        self.__state_data = _eng.group_frames(self.engine, key, EMIT * len(self.__loaded_units), frames)
+        self.__state_data["utt_kept"] = kept
+        return self.__state_data
+
+    def multi_training(self, unit, init, *args):
+        """AcousticModel.py:814-838 + `__cal_gmm` (:532-561): the unit's three state GMMs from their
+        data sets: k-means initialisation (ClusterInitialization.kmeans(algorithm=1), all three
+        states in one launch) when `init` or when the mixture count changed, then GMM.em.  A state
+        with fewer frames than mixtures is skipped (:546-548); a unit without data keeps its
+        parameters (:830-832).  args = (show_q, show_a, c_covariance, ...).  The reference runs
+        em(smem=init); the SMEM split / merge search is outside this path, so the EM
+        here is em(smem=False)."""
+        import random
+
+        show_q = args[0] if len(args) > 0 else False
+        c_cov = args[2] if len(args) > 2 else 1e-3
+        if self.__state_data is None:
+            raise RuntimeError("process_data(mode=1) first")
+        hmm = self.init_unit(unit, new_log=init, fix_code=2)
+        self.init_parameter(unit, hmm)
+        ui = self.__loaded_units.index(unit)
+        off, data = self.__state_data["key_off"], self.__state_data["data"]
+        M = self.__mix_level
+        rows = [data[off[ui * EMIT + r]:off[ui * EMIT + r + 1]] for r in range(EMIT)]
+        if sum(len(x) for x in rows) == 0:
+            self.log.note("unit %s has no data" % unit, cls="w")
+            self.__save_parameter(unit, hmm)
+            return hmm
+        todo = [r for r in range(EMIT) if len(rows[r]) >= M]
+        fresh = [r for r in todo if init or hmm.profunction[r + 1].mixture != M]
+        if fresh:
+            sub = torch.cat([rows[r] for r in fresh])
+            sub_off = np.concatenate([[0], np.cumsum([len(rows[r]) for r in fresh])]).astype(np.int64)
+            seeds = [_eng.kmeans_seed_points(np.ascontiguousarray(rows[r][:, 0].cpu().numpy()), M, random) for r in fresh]
+            km = _eng.kmeans_run(self.engine, sub, sub_off, M, np.array(seeds, dtype=np.int32))
+            k_mean, k_var, k_alpha = (km[k].cpu().numpy() for k in ("mean", "var", "alpha"))
+            for i, r in enumerate(fresh):
+                gmm = hmm.profunction[r + 1]
+                gmm.mean = k_mean[i]
+                gmm.covariance = np.stack([np.diag(v) for v in k_var[i]])
+                gmm.alpha = k_alpha[i]
+        for r in range(EMIT):
+            gmm = hmm.profunction[r + 1]
+            if r not in todo:
+                gmm.log.note("too little data, state skipped", cls="w")
+                continue
+            gmm.add_data(rows[r])
+            gmm.em(show_q=show_q, smem=False, c_covariance=c_cov)
+            gmm.clear_data()
+        self.__save_parameter(unit, hmm)
+        return hmm
+
     def training(self, mode=2, init=True, show_q=False, show_a=False, load_line=0, c_covariance=1e-3, group=None):
-        """AcousticModel.py:771-813, mode 2 (flat start + embedded training)."""
-        if mode != 2:
-            raise NotImplementedError("mode 1 (isolated-unit GMM.em training) is outside the E-step path (§8 f2)")
-        return self.embedded_training(self.__loaded_units, init=init, show_q=show_q, show_a=show_a,
-                                      load_line=load_line, c_covariance=c_covariance, group=group)
+        """AcousticModel.py:771-813.  Mode 1: per-unit GMM training on the data sets process_data
+        grouped, then one embedded iteration that re-estimates the transitions only (fix_code 2);
+        mode 2: one embedded iteration of everything."""
+        units = list(self.__loaded_units)
+        if mode == 1:
+            fix_code = 2
+            for n, unit in enumerate(units):
+                self.multi_training(unit, init, show_q, show_a, c_covariance, n + 1, len(units), len(units))
+        elif mode == 2:
+            fix_code = 0
+        else:
+            raise ModeError("mode must be 1 or 2 (Exceptions.ModeError)")
+        return self.embedded_training(units, init=init, show_q=show_q, show_a=show_a, load_line=load_line,
+                                      fix_code=fix_code, c_covariance=c_covariance, group=group)
 
     def align(self):
         """Forced alignment of the whole resident corpus (multi_process_data's Viterbi step,

@@ -157,8 +157,13 @@ class Clustering(object):
             return self.__gmm_id
 
         def add_data(self, data):
-            d = np.array(data)
-            self.__data = d if self.__data is None else np.append(self.__data, d, axis=0)
+            """Clustering.py:231 (DataInitialization.add_data).  A [n, D] CUDA tensor (the rows
+            engine.group_frames gathered) is taken as is and stays on the device."""
+            if isinstance(data, torch.Tensor):
+                self.__data = data if self.__data is None else torch.cat([torch.as_tensor(self.__data).to(data.device), data])
+            else:
+                d = np.array(data)
+                self.__data = d if self.__data is None else np.append(self.__data, d, axis=0)
             self._em_es = None
 
         def clear_data(self):
@@ -323,7 +328,9 @@ class Clustering(object):
         def _em_setup(self):
             if getattr(self, "_em_es", None) is not None:
                 return
-            data = None if self.__data is None else np.asarray(self.__data, dtype=np.float64)
+            data = self.__data
+            if data is not None and not isinstance(data, torch.Tensor):
+                data = np.asarray(data, dtype=np.float64)
             if data is None or len(data) == 0:
                 raise DataUnLoadError("GMM.em: no data loaded (Exceptions.DataUnLoadError)")
             if data.ndim != 2 or data.shape[1] != self.__dimension:

@@ -82,6 +82,10 @@ _SIGS = {
                       + [C.c_void_p] * 7 + [C.c_int64, C.c_void_p]),
     "pc_kmeans_finish": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
                          + [C.c_void_p] * 7),
+    "pc_segment_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4),
+    "pc_group_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "pc_group_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4),
+    "pc_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
     "pc_em_iteration_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
                              + [C.c_void_p] * 4 + [C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
 }

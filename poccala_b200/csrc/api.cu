@@ -570,6 +570,39 @@ int pc_viterbi(pc_handle h, pc_corpus c, const float *b, const double *b64, cons
                           unit_path, score, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ alignment post-processing
+int pc_segment_keys(pc_handle h, pc_corpus c, int32_t mode, const int32_t *path, int32_t *frame_key,
+                    int32_t *utt_kept, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(c && frame_key, "pc_segment_keys: NULL argument");
+    PC_REQUIRE(mode == 0 || mode == 1, "pc_segment_keys: mode %d (0 = uniform, 1 = aligned path)", mode);
+    PC_REQUIRE(mode == 0 || path, "pc_segment_keys: mode 1 needs the path pc_viterbi wrote");
+    return launch_segment_keys(h, c->v, mode, path, frame_key, utt_kept, (cudaStream_t)stream);
+}
+
+int64_t pc_group_workspace_bytes(int64_t n_frames, int32_t n_keys) {
+    if (n_frames < 0 || n_frames >= (1ll << 31) || n_keys < 1 || n_keys > 12000) return -1;
+    return group_workspace_bytes(n_frames, n_keys);
+}
+
+int pc_group_frames(pc_handle h, const int32_t *frame_key, int64_t n_frames, int32_t n_keys, void *ws,
+                    int64_t *key_off, int32_t *order, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(pc_group_workspace_bytes(n_frames, n_keys) >= 0,
+               "pc_group_frames: n_frames %lld / n_keys %d outside the supported range", (long long)n_frames, n_keys);
+    PC_REQUIRE(ws && key_off && (n_frames == 0 || (frame_key && order)), "pc_group_frames: NULL argument");
+    return launch_group_frames(h, frame_key, n_frames, n_keys, ws, key_off, order, (cudaStream_t)stream);
+}
+
+int pc_gather_rows(pc_handle h, const int32_t *order, int64_t n_rows, int32_t row_bytes, const void *src,
+                   void *dst, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n_rows >= 0 && row_bytes > 0 && row_bytes % 4 == 0,
+               "pc_gather_rows: row_bytes %d must be a positive multiple of 4", row_bytes);
+    PC_REQUIRE(n_rows == 0 || (order && src && dst), "pc_gather_rows: NULL argument");
+    return launch_gather_rows(h, order, n_rows, row_bytes, src, dst, (cudaStream_t)stream);
+}
+
 // --------------------------------------------------------------------------------- host e2e
 static int ensure_ws(pc_handle h, size_t bytes) {
     if (h->ws_bytes >= bytes) return PC_OK;

@@ -199,3 +199,10 @@ int launch_viterbi(pc_handle h, const CorpusView &v, const float *b, const doubl
                    const double *log_self, const double *log_next, const double *utt_logpi,
                    const double *state_logpi, int32_t *path, int32_t *unit_path, double *score,
                    cudaStream_t st);
+int launch_segment_keys(pc_handle h, const CorpusView &v, int mode, const int32_t *path, int32_t *key,
+                        int32_t *kept, cudaStream_t st);
+int64_t group_workspace_bytes(int64_t n_frames, int n_keys);
+int launch_group_frames(pc_handle h, const int32_t *key, int64_t n, int n_keys, void *ws, int64_t *key_off,
+                        int32_t *order, cudaStream_t st);
+int launch_gather_rows(pc_handle h, const int32_t *order, int64_t n_rows, int row_bytes, const void *src,
+                       void *dst, cudaStream_t st);

@@ -458,3 +458,48 @@ def kmeans_run(engine, x, point_off, k, seeds, max_passes=1 << 40):
              _p(out["alpha"]), _stream())
     out["workspace"] = ws  # keep alive until the stream has run
     return out
+
+
+# ---- alignment post-processing ------------------------------------------------
+def segment_keys(engine, corpus, path=None):
+    """pc_segment_keys: per corpus frame the data set it joins, key = unit * 3 + emitting state, or -1.
+    path=None: uniform segmentation (AcousticModel.__eq_segment mode 'e', AcousticModel.py:605-612);
+    path = the composite-state path `viterbi` returned: the re-segmentation of multi_process_data
+    (AcousticModel.py:750-764).  Either way each unit segment is cut in three (__get_gmmdata,
+    :630-644).  Returns (frame_key int32 [F], utt_kept int32 [U]) device tensors."""
+    F = int(corpus.frame_off[-1])
+    key = engine.empty((F,), torch.int32)
+    kept = engine.empty((len(corpus.frame_off) - 1,), torch.int32)
+    if path is not None:
+        if path.dtype != torch.int32 or path.numel() != F:
+            raise ValueError("path must be the int32 [total_frames] tensor viterbi() returned")
+        path = path.contiguous()
+    nat.call("pc_segment_keys", engine.h, corpus.c, 0 if path is None else 1, _p(path), _p(key), _p(kept), _stream())
+    return key, kept
+
+
+def group_frames(engine, frame_key, n_keys, x=None):
+    """pc_group_frames (+ pc_gather_rows when x is given): frames of one key made contiguous, in
+    (utterance, time) order - the per-state data sets AcousticModel.__get_gmmdata builds.
+    Returns dict(key_off: host int64 [n_keys+1], order: device int32 [F], data: x[order[:kept]] or None)."""
+    frame_key = frame_key.contiguous()
+    F = frame_key.numel()
+    ws_bytes = int(nat.lib().pc_group_workspace_bytes(F, int(n_keys)))
+    if ws_bytes < 0:
+        raise ValueError("group_frames: %d frames / %d keys outside the supported range" % (F, n_keys))
+    ws = engine.empty((ws_bytes,), torch.uint8)
+    key_off = engine.empty((n_keys + 2,), torch.int64)
+    order = engine.empty((max(F, 1),), torch.int32)
+    nat.call("pc_group_frames", engine.h, _p(frame_key), F, int(n_keys), _p(ws), _p(key_off), _p(order), _stream())
+    off = key_off.cpu().numpy()  # the caller sizes the per-state problems from it: one host sync
+    kept = int(off[n_keys])
+    data = None
+    if x is not None:
+        if x.dim() != 2 or x.shape[0] != F:
+            raise ValueError("x must hold one row per corpus frame")
+        x = x.contiguous()
+        row_bytes = x.shape[1] * x.element_size()
+        data = engine.empty((kept, x.shape[1]), x.dtype)
+        nat.call("pc_gather_rows", engine.h, _p(order), kept, row_bytes, _p(x), _p(data), _stream())
+    return dict(key_off=off[:n_keys + 1].copy(), order=order[:F], data=data)
+

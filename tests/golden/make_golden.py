@@ -186,8 +186,86 @@ def gmm_em_golden():
     print("gmm_em.npz written", [int(out[f"e{c}_iters"]) for c in range(2)])
 
 
+def alignment_golden():
+    """Mode-1 data preparation executed as is: __eq_segment(mode='e') (AcousticModel.py:605-612), the
+    post-Viterbi part of multi_process_data (:750-764, with discriminate :937-955) and __get_gmmdata
+    (:630-644).  Frames are their own corpus index ([T,1] arrays), the segment writer is replaced by a
+    capture, and for the aligned case the model set-up / Viterbi calls in front of line 750 are
+    stubbed to hand back the unit sequence under test."""
+    from unittest.mock import MagicMock
+
+    units = ["a", "b", "c", "d"]
+    H = rh.Harness(units, MIX)
+    am = H.am
+    am.log = rh._Quiet()  # multi_process_data closes its log after every utterance
+    rng = np.random.default_rng(77)
+    out = {}
+
+    def run_case(tag, labels, lens, sequences):
+        captured = {}
+        am._AcousticModel__save_data = lambda unit, d: captured.setdefault(unit, []).append(np.array(d))
+        off = 0
+        for u, (lab, T) in enumerate(zip(labels, lens)):
+            data = (np.arange(T) + off)[:, None].astype(np.float64)
+            names = [units[i] for i in lab]
+            if sequences is None:
+                am._AcousticModel__eq_segment(data, names, mode='e')
+            else:
+                seq = np.array([units[i] for i in sequences[u]])
+                am.init_unit = lambda unit=None, new_log=True, fix_code=0: MagicMock()
+                am.init_parameter = lambda unit=None, hmm=None: None
+                am.embedded = lambda *a, **k: (None, None, np.zeros((1, 1)), None)
+                am.viterbi = lambda *a, seq=seq: (0., seq)
+                cwd = os.getcwd()
+                os.chdir(H.tmp)  # the reference drops a prob.csv into the working directory (:746)
+                try:
+                    am.multi_process_data(names, data, False, u + 1, len(labels), 2)
+                finally:
+                    os.chdir(cwd)
+            off += T
+        n_sets = 0
+        for i, unit in enumerate(units):
+            if unit not in captured:
+                continue
+            g = am._AcousticModel__get_gmmdata(captured[unit])
+            for r in range(3):
+                out[f"{tag}_set_{i * 3 + r}"] = np.asarray(g[r]).reshape(-1).astype(np.int64)
+                n_sets += 1
+        out[f"{tag}_n_utt"] = len(labels)
+        out[f"{tag}_lens"] = np.array(lens)
+        for u, lab in enumerate(labels):
+            out[f"{tag}_label{u}"] = np.array(lab)
+            if sequences is not None:
+                out[f"{tag}_seq{u}"] = np.array(sequences[u])
+        return n_sets
+
+    # uniform: remainders dropped, chunks shorter than 3 frames, repeated units
+    labels = [[0, 1, 2], [1, 1, 3, 0], [2], [0, 3, 0, 3, 1, 2, 1], [3, 2]]
+    lens = [31, 50, 7, 16, 5]
+    n0 = run_case("uni", labels, lens, None)
+
+    # aligned: random monotone unit sequences; runs of 1-2 frames; adjacent equal units merge into one
+    # run; one utterance stops short of its last unit (discarded), one skips nothing but repeats units
+    def walk(lab, T, stop_early=False):
+        L = len(lab) - (1 if stop_early else 0)
+        cuts = np.sort(rng.choice(np.arange(1, T), size=L - 1, replace=False)) if L > 1 else np.array([], dtype=int)
+        pos = np.searchsorted(cuts, np.arange(T), side="right")
+        return [lab[p] for p in pos]
+
+    labels = [[0, 1, 2], [1, 1, 3, 0], [2, 0, 2], [0, 3, 0, 3, 1, 2, 1], [3, 2, 1], [0, 1]]
+    lens = [40, 33, 9, 64, 25, 2]
+    seqs = [walk(l, T) for l, T in zip(labels, lens)]
+    seqs[4] = walk(labels[4], lens[4], stop_early=True)  # unit 1 never reached -> utterance dropped
+    n1 = run_case("ali", labels, lens, seqs)
+    np.savez_compressed(os.path.join(OUT, "alignment.npz"), **out)
+    print("alignment.npz written", n0, n1)
+
+
 if __name__ == "__main__":
     assert rh.available(), "needs /root/reference"
+    if "--alignment-only" in sys.argv:
+        alignment_golden()
+        sys.exit(0)
     if "--flat-start-only" in sys.argv:
         flat_start_golden()
         sys.exit(0)
@@ -199,3 +277,4 @@ if __name__ == "__main__":
     kmeans_golden()
     flat_start_golden()
     gmm_em_golden()
+    alignment_golden()

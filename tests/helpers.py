@@ -38,3 +38,13 @@ def port_units(mean, var, alpha, names=UNITS3, transmat=None):
             d["transmat"] = np.array(transmat[i], dtype=np.float64)
         units[u] = d
     return units
+
+
+def alignment_case(g, tag):
+    """One case of tests/golden/alignment.npz: (labels, lens, sequences or None, {key: frame set})."""
+    n = int(g[f"{tag}_n_utt"])
+    labels = [g[f"{tag}_label{u}"].astype(np.int32) for u in range(n)]
+    lens = g[f"{tag}_lens"].astype(np.int32)
+    seqs = [g[f"{tag}_seq{u}"] for u in range(n)] if f"{tag}_seq0" in g else None
+    sets = {int(k[len(tag) + 5:]): g[k] for k in g if k.startswith(tag + "_set_")}
+    return labels, lens, seqs, sets

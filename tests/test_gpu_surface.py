@@ -259,3 +259,56 @@ def test_gmm_em_matches_executed_reference():
         assert sorted(gm.theta()) == ["theta_%d" % i for i in range(M)]
     with pytest.raises(DataUnLoadError):
         Clustering.GMM(None, dimension=39, mix_level=2).em()
+
+
+def test_mode1_training_segment_kmeans_gmm_em():
+    """§8 f2 + f3 through the reference-shaped surface: process_data(mode=1, init=True) (uniform
+    segmentation, per-state data sets grouped on the device), multi_training (k-means initialisation
+    + GMM.em per state) against the oracle restatement of the same steps; then the re-estimation
+    round: process_data(init=False) (forced alignment -> runs -> data sets) and training(mode=1)."""
+    from oracle import fast
+    from poccala_b200 import synth
+    from poccala_b200.AcousticModel import AcousticModel, ModeError
+    from poccala_b200.engine import kmeans_seed_points
+
+    M = 2
+    truth, init, labels, utts = synth.make_corpus(36, 90, 3, 3, M, 12)
+    am = AcousticModel(None, "T", state_num=5, mix_level=M)
+    am.set_units(UNITS3)
+    am.set_parameters(*init)
+    am.add_corpus([[UNITS3[i] for i in l] for l in labels], utts)
+    random.seed(11)
+    sd = am.process_data(mode=1, init=True)
+    for unit in UNITS3:
+        am.multi_training(unit, True, False, False, 1e-3)
+    mean, var, alpha, tm = am.get_parameters()
+    # ---- the same steps on the oracle
+    off = np.concatenate([[0], np.cumsum([len(x) for x in utts])])
+    sets = fast.state_frames([fast.segment_uniform([int(v) for v in l], len(x)) for l, x in zip(labels, utts)], off, 3)
+    assert np.array_equal(sd["key_off"], np.concatenate([[0], np.cumsum([len(s) for s in sets])]))
+    xs = np.concatenate(utts, axis=0)
+    random.seed(11)
+    compared = 0
+    for k in range(9):
+        data = xs[sets[k]]
+        twin = random.Random()
+        twin.setstate(random.getstate())
+        km = fast.kmeans_compat(data, M, twin)
+        kmeans_seed_points(np.ascontiguousarray(data[:, 0]), M, random)  # advance the stream as multi_training does
+        o_mean, o_var, o_alpha, iters, _ = fast.gmm_em(data, km["mean"], km["var"], km["alpha"], c_covariance=1e-3)
+        if fast.gmm_em.margin < 0.05:
+            continue  # a Q increment within 0.05 of the 1.28 threshold: the iteration count is a coin toss
+        u, r = divmod(k, 3)
+        assert np.all(np.abs(alpha[u, r] - o_alpha) <= 2e-3 * np.maximum(o_alpha, 1e-2))
+        assert np.all(np.abs(mean[u, r] - o_mean) <= 2e-3 * np.maximum(np.abs(o_mean), np.sqrt(o_var)))
+        assert np.all(np.abs(var[u, r] - o_var) <= 2e-3 * o_var)
+        compared += 1
+    assert compared >= 6
+    # ---- re-estimation round on the aligned data
+    sd = am.process_data(mode=1, init=False)
+    kept = sd["utt_kept"].cpu().numpy()
+    assert kept.sum() >= 30 and int(sd["key_off"][-1]) == int(sum(len(x) for x, k in zip(utts, kept) if k))
+    ll = am.training(mode=1, init=False, c_covariance=1e-3)
+    assert np.isfinite(ll) and all(np.isfinite(p).all() for p in am.get_parameters())
+    with pytest.raises(ModeError):
+        am.process_data(mode=3)
