@@ -235,14 +235,28 @@ key_scatter_kernel(const int32_t *__restrict__ key, int64_t n, int n_keys, const
     }
 }
 
+// W = 8- or 4-byte words; 32-bit index arithmetic (the launcher slices to < 2^31 words),
+// four independent row fetches in flight per thread
+template <typename W>
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(const int32_t *__restrict__ order, int64_t n_rows, int words, const uint32_t *__restrict__ src,
-                   uint32_t *__restrict__ dst) {
-    const int64_t total = n_rows * words;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t row = i / words;
-        int w = (int)(i - row * words);
-        dst[i] = src[(int64_t)order[row] * words + w];
+gather_rows_kernel(const int32_t *__restrict__ order, uint32_t n_rows, uint32_t words, const W *__restrict__ src,
+                   W *__restrict__ dst) {
+    const uint32_t total = n_rows * words;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < total && total - i > 3 * stride; i += 4 * stride) {
+        W v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t e = i + j * stride, row = e / words;
+            v[j] = src[(size_t)order[row] * words + (e - row * words)];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[i + j * stride] = v[j];
+    }
+    for (; i < total; i += stride) {
+        uint32_t row = i / words;
+        dst[i] = src[(size_t)order[row] * words + (i - row * words)];
     }
 }
 
@@ -286,12 +300,23 @@ int launch_group_frames(pc_handle h, const int32_t *key, int64_t n, int n_keys, 
 int launch_gather_rows(pc_handle h, const int32_t *order, int64_t n_rows, int row_bytes, const void *src, void *dst,
                        cudaStream_t st) {
     if (n_rows == 0) return PC_OK;
-    int words = row_bytes / 4;
-    int64_t total = n_rows * words;
-    int64_t want = (total + 255) / 256;
-    int grid = (int)(want < (int64_t)h->sm_count * 16 ? want : (int64_t)h->sm_count * 16);
-    gather_rows_kernel<<<grid, 256, 0, st>>>(order, n_rows, words, (const uint32_t *)src, (uint32_t *)dst);
-    PC_LAUNCH_CHECK();
-    h->launches++;
+    const bool wide = row_bytes % 8 == 0 && ((uintptr_t)src | (uintptr_t)dst) % 8 == 0;
+    const int words = row_bytes / (wide ? 8 : 4);
+    // slices of < 2^31 words per launch
+    const int64_t rows_per_launch = ((1ll << 31) - 1) / words;  // 32-bit index arithmetic with headroom
+    for (int64_t r0 = 0; r0 < n_rows; r0 += rows_per_launch) {
+        int64_t nr = n_rows - r0 < rows_per_launch ? n_rows - r0 : rows_per_launch;
+        int64_t want = (nr * words + 1023) / 1024;
+        int grid = (int)(want < (int64_t)h->sm_count * 8 ? want : (int64_t)h->sm_count * 8);
+        char *d = (char *)dst + (size_t)r0 * row_bytes;
+        if (wide)
+            gather_rows_kernel<uint64_t><<<grid, 256, 0, st>>>(order + r0, (uint32_t)nr, (uint32_t)words,
+                                                               (const uint64_t *)src, (uint64_t *)d);
+        else
+            gather_rows_kernel<uint32_t><<<grid, 256, 0, st>>>(order + r0, (uint32_t)nr, (uint32_t)words,
+                                                               (const uint32_t *)src, (uint32_t *)d);
+        PC_LAUNCH_CHECK();
+        h->launches++;
+    }
     return PC_OK;
 }
