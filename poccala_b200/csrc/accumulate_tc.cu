@@ -28,8 +28,10 @@ namespace {
 using tc::T_KCH;
 using tc::T_PIECE;
 using tc::T_ROWS;
-constexpr int W_FLUSH = 16, W_PROD = 19, W_MMA = 20;  // warps 0-15 softmax, 16-18 flush
-constexpr int NTHREADS = 21 * 32;
+// warps 0-15 softmax, 16-18 flush, then the TMA producer and one MMA issuer per contraction: with a single
+// issuer the barrier waits in front of each contraction (~400 clk per tile) left the tensor pipe idle
+constexpr int W_FLUSH = 16, W_PROD = 19, W_MMA = 20, W_MMA2 = 21;
+constexpr int NTHREADS = 22 * 32;
 constexpr float LOG2E = 1.4426950408889634f;
 // posteriors are stored as P * 2^15 so that the fp16 window [6e-8, 65504] covers [1.8e-12, 2]
 constexpr float P_SHIFT = 15.f;
@@ -275,122 +277,126 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                 __syncwarp();
             }
         } else if (warp == W_MMA) {
-            // ------------------------------------------------------------ MMA issuer
+            // ------------------------------------------------------------ MMA1 issuer: S = X * W^T
             constexpr uint32_t idesc1 = tc::umma_idesc_f16(T_ROWS, C::NPAD, 0, 0);
-            constexpr uint32_t idesc2 = tc::umma_idesc_f16(128, C::NPAD, 1, 1);
             constexpr uint32_t idesc1s = tc::umma_idesc_f16(T_ROWS, 2 * C::NPAD, 0, 0);
-            constexpr uint32_t idesc2s = tc::umma_idesc_f16(128, 2 * C::NPAD, 1, 1);
-            const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s), p_base = tc::smem_u32(p_s);
+            const uint32_t a_base = tc::smem_u32(a_s), b_base = tc::smem_u32(b_s);
             // loop bounds / ring counters through redux.sync: uniform registers for the descriptors
             const int n_tiles = __reduce_max_sync(0xffffffffu, n_tiles_);
             const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, tmem_base_);
             const uint32_t n_tile_u = __reduce_max_sync(0xffffffffu, n_tile);
-            const uint32_t d2 = tmem_base + C::D2_COL;
             tc::mbar_wait(&bars->b_full, n_item & 1);
-            for (int i = 0; i <= n_tiles; ++i) {
-                if (i < n_tiles) {
-                    const uint32_t n = n_tile_u + i;
-                    const int slot = n % C::NA, sb = n & 1;
-                    const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n < 1000;
-                    if (rec) g_acc_dbg[n * 8 + 0] = clock64();
-                    tc::mbar_wait(&bars->a_full[slot], (n / C::NA) & 1);
-                    if (rec) g_acc_dbg[n * 8 + 1] = clock64();
-                    tc::mbar_wait(&bars->s_empty[sb], ((n >> 1) & 1) ^ 1);
-                    if (rec) g_acc_dbg[n * 8 + 2] = clock64();
-                    tc::tc_fence_after();
-                    if (tc::elect_one()) {
-                        const uint32_t d = tmem_base + sb * C::S_STRIDE;
-                        const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
-                        const uint32_t bh = b_base, bl = b_base + PC_WGROUP_BYTES / 2;
-                        uint32_t accum = 0;
-                        if constexpr (C::STACK) {
+            for (int i = 0; i < n_tiles; ++i) {
+                const uint32_t n = n_tile_u + i;
+                const int slot = n % C::NA, sb = n & 1;
+                const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n < 1000;
+                if (rec) g_acc_dbg[n * 8 + 0] = clock64();
+                tc::mbar_wait(&bars->a_full[slot], (n / C::NA) & 1);
+                if (rec) g_acc_dbg[n * 8 + 1] = clock64();
+                tc::mbar_wait(&bars->s_empty[sb], ((n >> 1) & 1) ^ 1);
+                if (rec) g_acc_dbg[n * 8 + 2] = clock64();
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t d = tmem_base + sb * C::S_STRIDE;
+                    const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
+                    const uint32_t bh = b_base, bl = b_base + PC_WGROUP_BYTES / 2;
+                    uint32_t accum = 0;
+                    if constexpr (C::STACK) {
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const uint32_t ap = q ? al : ah;
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t ap = q ? al : ah;
 #pragma unroll
-                                for (int k = 0; k < T_KCH / 2; ++k) {
-                                    const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
-                                    const uint64_t bd = tc::umma_desc(bh + 2 * k * 128, 128, PC_WGROUP_BYTES / 2);
-                                    tc::mma_f16_ss(d, ad, bd, idesc1s, accum);
-                                    accum = 1;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const uint32_t ap = (q == 2) ? al : ah;
-                                const uint32_t bp = (q == 1) ? bl : bh;
-#pragma unroll
-                                for (int k = 0; k < T_KCH / 2; ++k) {
-                                    const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
-                                    const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
-                                    tc::mma_f16_ss(d, ad, bd, idesc1, accum);
-                                    accum = 1;
-                                }
+                            for (int k = 0; k < T_KCH / 2; ++k) {
+                                const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
+                                const uint64_t bd = tc::umma_desc(bh + 2 * k * 128, 128, PC_WGROUP_BYTES / 2);
+                                tc::mma_f16_ss(d, ad, bd, idesc1s, accum);
+                                accum = 1;
                             }
                         }
-                        tc::tc_commit(&bars->s_full[sb]);
-                        if (i == n_tiles - 1) tc::tc_commit(&bars->b_empty);  // last use of this item's B
-                    }
-                    __syncwarp();
-                }
-                if (i >= 1) {
-                    // MMA2 of tile i-1: D2[f, g] += sum_t A[t, f] * P[t, g]
-                    const uint32_t n = n_tile_u + i - 1;
-                    const int slot = n % C::NA, ps = n & 1;
-                    const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n < 1000;
-                    if (rec) g_acc_dbg[n * 8 + 3] = clock64();
-                    tc::mbar_wait(&bars->p_full[ps], (n >> 1) & 1);
-                    if (rec) g_acc_dbg[n * 8 + 4] = clock64();
-                    if (i == 1) tc::mbar_wait(&bars->d2_empty, (n_item & 1) ^ 1);  // previous flush done
-                    tc::tc_fence_after();
-                    // active 16-frame K-steps of this tile (2 bits per lane quarter)
-                    uint32_t kmask;
-                    {
-                        const uint32_t w = *reinterpret_cast<const volatile uint32_t *>(&bars->kact[ps][0]);
-                        kmask = (w & 3u) | (((w >> 8) & 3u) << 2) | (((w >> 16) & 3u) << 4) | (((w >> 24) & 3u) << 6);
-                        kmask = __reduce_or_sync(0xffffffffu, kmask);
-                    }
-                    if (tc::elect_one()) {
-                        const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
-                        const uint32_t ph = p_base + ps * 2 * C::P_PIECE, pl = ph + C::P_PIECE;
-                        uint32_t accum = (i == 1) ? 0u : 1u;  // first tile of the item resets D2
-                        if constexpr (C::STACK) {
+                    } else {
 #pragma unroll
-                            for (int q = 0; q < 2; ++q) {
-                                const uint32_t ap = q ? al : ah;
+                        for (int q = 0; q < 3; ++q) {
+                            const uint32_t ap = (q == 2) ? al : ah;
+                            const uint32_t bp = (q == 1) ? bl : bh;
 #pragma unroll
-                                for (int k = 0; k < T_ROWS / 16; ++k) {
-                                    if (!((kmask >> k) & 1u)) continue;
-                                    const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
-                                    const uint64_t bd = tc::umma_desc(ph + k * 256, 128, T_ROWS * 16);  // hi then lo blocks
-                                    tc::mma_f16_ss(d2, ad, bd, idesc2s, accum);
-                                    accum = 1;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const uint32_t ap = (q == 1) ? al : ah;
-                                const uint32_t pp = (q == 2) ? pl : ph;
-#pragma unroll
-                                for (int k = 0; k < T_ROWS / 16; ++k) {
-                                    if (!((kmask >> k) & 1u)) continue;
-                                    // MN-major views: 8 frames x 16 B core matrices; LBO = 128 B between
-                                    // 8-frame groups, SBO = 2048 B between 8-feature / 8-Gaussian blocks
-                                    const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
-                                    const uint64_t bd = tc::umma_desc(pp + k * 256, 128, T_ROWS * 16);
-                                    tc::mma_f16_ss(d2, ad, bd, idesc2, accum);
-                                    accum = 1;
-                                }
+                            for (int k = 0; k < T_KCH / 2; ++k) {
+                                const uint64_t ad = tc::umma_desc(ap + 2 * k * T_ROWS * 16, T_ROWS * 16, 128);
+                                const uint64_t bd = tc::umma_desc(bp + 2 * k * 128, 128, PC_WGROUP_BYTES);
+                                tc::mma_f16_ss(d, ad, bd, idesc1, accum);
+                                accum = 1;
                             }
                         }
-                        tc::tc_commit(&bars->a_empty[slot]);
-                        tc::tc_commit(&bars->p_empty[ps]);
-                        if (i == n_tiles) tc::tc_commit(&bars->d2_full);
                     }
-                    __syncwarp();
+                    tc::tc_commit(&bars->s_full[sb]);
+                    if (i == n_tiles - 1) tc::tc_commit(&bars->b_empty);  // last use of this item's B
                 }
+                __syncwarp();
+            }
+        } else if (warp == W_MMA2) {
+            // ------------------------------------------------------------ MMA2 issuer: D2[f, g] += sum_t A[t, f] * P[t, g]
+            constexpr uint32_t idesc2 = tc::umma_idesc_f16(128, C::NPAD, 1, 1);
+            constexpr uint32_t idesc2s = tc::umma_idesc_f16(128, 2 * C::NPAD, 1, 1);
+            const uint32_t a_base = tc::smem_u32(a_s), p_base = tc::smem_u32(p_s);
+            const int n_tiles = __reduce_max_sync(0xffffffffu, n_tiles_);
+            const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, tmem_base_);
+            const uint32_t n_tile_u = __reduce_max_sync(0xffffffffu, n_tile);
+            const uint32_t d2 = tmem_base + C::D2_COL;
+            for (int i = 0; i < n_tiles; ++i) {
+                const uint32_t n = n_tile_u + i;
+                const int slot = n % C::NA, ps = n & 1;
+                const bool rec = (dbg & 32) && blockIdx.x == 0 && lane == 0 && n < 1000;
+                if (rec) g_acc_dbg[n * 8 + 3] = clock64();
+                tc::mbar_wait(&bars->p_full[ps], (n >> 1) & 1);
+                tc::mbar_wait(&bars->a_full[slot], (n / C::NA) & 1);  // long complete; this thread's own view of the tile
+                if (rec) g_acc_dbg[n * 8 + 4] = clock64();
+                if (i == 0) tc::mbar_wait(&bars->d2_empty, (n_item & 1) ^ 1);  // previous flush done
+                tc::tc_fence_after();
+                // active 16-frame K-steps of this tile (2 bits per lane quarter)
+                uint32_t kmask;
+                {
+                    const uint32_t w = *reinterpret_cast<const volatile uint32_t *>(&bars->kact[ps][0]);
+                    kmask = (w & 3u) | (((w >> 8) & 3u) << 2) | (((w >> 16) & 3u) << 4) | (((w >> 24) & 3u) << 6);
+                    kmask = __reduce_or_sync(0xffffffffu, kmask);
+                }
+                if (tc::elect_one()) {
+                    const uint32_t ah = a_base + slot * 2 * T_PIECE, al = ah + T_PIECE;
+                    const uint32_t ph = p_base + ps * 2 * C::P_PIECE, pl = ph + C::P_PIECE;
+                    uint32_t accum = (i == 0) ? 0u : 1u;  // first tile of the item resets D2
+                    if constexpr (C::STACK) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const uint32_t ap = q ? al : ah;
+#pragma unroll
+                            for (int k = 0; k < T_ROWS / 16; ++k) {
+                                if (!((kmask >> k) & 1u)) continue;
+                                const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
+                                const uint64_t bd = tc::umma_desc(ph + k * 256, 128, T_ROWS * 16);  // hi then lo blocks
+                                tc::mma_f16_ss(d2, ad, bd, idesc2s, accum);
+                                accum = 1;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const uint32_t ap = (q == 1) ? al : ah;
+                            const uint32_t pp = (q == 2) ? pl : ph;
+#pragma unroll
+                            for (int k = 0; k < T_ROWS / 16; ++k) {
+                                if (!((kmask >> k) & 1u)) continue;
+                                // MN-major views: 8 frames x 16 B core matrices; LBO = 128 B between
+                                // 8-frame groups, SBO = 2048 B between 8-feature / 8-Gaussian blocks
+                                const uint64_t ad = tc::umma_desc(ap + k * 256, 128, T_ROWS * 16);
+                                const uint64_t bd = tc::umma_desc(pp + k * 256, 128, T_ROWS * 16);
+                                tc::mma_f16_ss(d2, ad, bd, idesc2, accum);
+                                accum = 1;
+                            }
+                        }
+                    }
+                    tc::tc_commit(&bars->a_empty[slot]);
+                    tc::tc_commit(&bars->p_empty[ps]);
+                    if (i == n_tiles - 1) tc::tc_commit(&bars->d2_full);
+                }
+                __syncwarp();
             }
         } else if (warp < W_FLUSH) {
             // ------------------------------------------------------------ softmax: 2 tile groups x

@@ -22,9 +22,9 @@ a = np.array(buf[:8000]).reshape(1000, 8)
 n = 80
 a = a[:n] - a[0, 0]
 np.set_printoptions(linewidth=220)
-print("cols: mma_start, tile_landed, S_free, MMA1_issued(wait P), P_ready | smx_start, S_ready, P_written")
+print("cols: mma1_start, tile_landed, S_free | mma2_start, P_ready | smx_start, S_ready, P_written")
 for i in range(0, 40): print(i, a[i])
 d = np.diff(a[:, 0])
 print("mean clk per tile (mma start to start): %.0f median %.0f" % (d.mean(), np.median(d)))
-print("mma: wait tile %.0f, wait S free %.0f, MMA1 issue+loop %.0f, wait P %.0f" % ((a[:,1]-a[:,0]).mean(), (a[:,2]-a[:,1]).mean(), (a[:,3]-a[:,2]).mean(), (a[:,4]-a[:,3]).mean()))
+print("mma1: wait tile %.0f, wait S free %.0f, issue (to next start) %.0f | mma2: wait P %.0f, issue (to next start) %.0f" % ((a[:,1]-a[:,0]).mean(), (a[:,2]-a[:,1]).mean(), (a[1:,0]-a[:-1,2]).mean(), (a[:,4]-a[:,3]).mean(), (a[1:,3]-a[:-1,4]).mean()))
 print("softmax: wait S %.0f, work %.0f" % ((a[:,6]-a[:,5]).mean(), (a[:,7]-a[:,6]).mean()))
