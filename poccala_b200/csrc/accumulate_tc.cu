@@ -45,51 +45,67 @@ constexpr float P_UNSHIFT = 1.f / 32768.f;
 // utterance) that is more than half of the tiles.
 constexpr float ACTIVE_MIN_LGAM = -41.f * 0.6931471805599453f;
 
-// One warp per 128-frame tile of an utterance: coalesced rows of log gamma (lane = state column),
-// running maximum per column, then active[(tile, position)] = 1 where any of the position's states
-// exceeds ACTIVE_MIN_LGAM (the flags are zeroed by the launcher; NaN columns stay inactive).
-__global__ void tile_active_kernel(CorpusView v, const float *__restrict__ lgam, int32_t *__restrict__ active) {
-    const int64_t xt = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Four warps per 128-frame tile of an utterance (32 frames each): coalesced rows of log gamma (lane =
+// state column), eight rows in flight per lane, running maximum per column, then
+// active[(tile, position)] = 1 where any of the position's states exceeds ACTIVE_MIN_LGAM (the flags
+// are zeroed by the launcher; NaN columns stay inactive).
+constexpr int ACT_SPLIT = 4;
+constexpr int ACT_THREADS = 128;
+// Work items differ a lot in how many of their tiles are active; with a static round-robin over the
+// SMs the kernel ends with its slowest SM.  The block that finishes last (ticket counter behind the
+// item counts) orders the items by active tiles (counting sort, heaviest first); the main kernel deals
+// them out in snake order.
+__global__ void __launch_bounds__(ACT_THREADS)
+tile_active_kernel(CorpusView v, const float *__restrict__ lgam, int32_t *__restrict__ active) {
+    __shared__ int bin[64];
+    __shared__ int is_last;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (xt >= v.n_xtiles) return;
-    const int u = v.xtile_utt[xt], t0 = v.xtile_t0[xt];
-    const int T = (int)(v.frame_off[u + 1] - v.frame_off[u]);
-    const int64_t p0 = v.pair_off[u];
-    const int L = (int)(v.pair_off[u + 1] - p0);
-    const int sp = pc_spad(L), rows = min(PC_TILE_ROWS, T - t0);
-    const float *base = lgam + v.emis_off[u] + (size_t)t0 * sp;
-    for (int c = lane; c < PC_EMIT * L; c += 32) {
-        float m0 = PC_NEG_INF, m1 = PC_NEG_INF, m2 = PC_NEG_INF, m3 = PC_NEG_INF;
-        int r = 0;
-        for (; r + 3 < rows; r += 4) {
-            m0 = fmaxf(m0, __ldg(base + (size_t)r * sp + c));
-            m1 = fmaxf(m1, __ldg(base + (size_t)(r + 1) * sp + c));
-            m2 = fmaxf(m2, __ldg(base + (size_t)(r + 2) * sp + c));
-            m3 = fmaxf(m3, __ldg(base + (size_t)(r + 3) * sp + c));
-        }
-        for (; r < rows; ++r) m0 = fmaxf(m0, __ldg(base + (size_t)r * sp + c));
-        if (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > ACTIVE_MIN_LGAM) {
-            const int64_t tile = v.pair_tile0[p0 + c / PC_EMIT] + t0 / PC_TILE_ROWS;
-            if (atomicExch(active + tile, 1) == 0) atomicAdd(v.item_act + v.tile_item[tile], 1);  // once per tile
+    const int64_t xt = w / ACT_SPLIT;
+    const int part = (int)(w - xt * ACT_SPLIT);
+    if (xt < v.n_xtiles) {
+        const int u = v.xtile_utt[xt], t0 = v.xtile_t0[xt];
+        const int T = (int)(v.frame_off[u + 1] - v.frame_off[u]);
+        const int64_t p0 = v.pair_off[u];
+        const int L = (int)(v.pair_off[u + 1] - p0);
+        const int sp = pc_spad(L), rows = min(PC_TILE_ROWS, T - t0);
+        const int r_lo = part * (PC_TILE_ROWS / ACT_SPLIT), r_hi = min(rows, r_lo + PC_TILE_ROWS / ACT_SPLIT);
+        const float *base = lgam + v.emis_off[u] + (size_t)t0 * sp;
+        for (int c = lane; c < PC_EMIT * L && r_lo < r_hi; c += 32) {
+            float m[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m[j] = PC_NEG_INF;
+            int r = r_lo;
+            for (; r + 7 < r_hi; r += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], __ldg(base + (size_t)(r + j) * sp + c));
+            }
+            for (; r < r_hi; ++r) m[0] = fmaxf(m[0], __ldg(base + (size_t)r * sp + c));
+#pragma unroll
+            for (int j = 1; j < 8; ++j) m[0] = fmaxf(m[0], m[j]);
+            if (m[0] > ACTIVE_MIN_LGAM) {
+                const int64_t tile = v.pair_tile0[p0 + c / PC_EMIT] + t0 / PC_TILE_ROWS;
+                if (atomicExch(active + tile, 1) == 0) atomicAdd(v.item_act + v.tile_item[tile], 1);  // once per tile
+            }
         }
     }
-}
-
-// Work items differ a lot in how many of their tiles are active; with a static round-robin over the
-// SMs the kernel ends with its slowest SM.  One block orders the items by active tiles (counting
-// sort, heaviest first); the main kernel deals them out in snake order.
-__global__ void item_order_kernel(int n_items, const int32_t *__restrict__ item_act, int32_t *__restrict__ order) {
-    __shared__ int bin[64];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) bin[i] = 0;
+    __threadfence();
     __syncthreads();
-    for (int i = threadIdx.x; i < n_items; i += blockDim.x) atomicAdd(&bin[63 - min(item_act[i], 63)], 1);
+    if (threadIdx.x == 0) is_last = atomicAdd(v.item_act + v.n_items, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < 64; i += ACT_THREADS) bin[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < v.n_items; i += ACT_THREADS) atomicAdd(&bin[63 - min(__ldcg(v.item_act + i), 63)], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
         for (int k = 0; k < 64; ++k) { const int c = bin[k]; bin[k] = run; run += c; }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_items; i += blockDim.x) order[atomicAdd(&bin[63 - min(item_act[i], 63)], 1)] = i;
+    for (int i = threadIdx.x; i < v.n_items; i += ACT_THREADS)
+        v.item_order[atomicAdd(&bin[63 - min(__ldcg(v.item_act + i), 63)], 1)] = i;
 }
 
 // NC = Gaussians handled per work item (a unit's 3*MIX Gaussians, or a slice of them)
@@ -521,16 +537,13 @@ int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W,
     const int n_work = v.n_items * Cfg<MIX>::N_SLICES;
     const int grid = n_work < h->sm_count ? n_work : h->sm_count;
     {
-        const int64_t warps = v.n_xtiles;
-        const int threads = 128;
-        const int64_t blocks = (warps * 32 + threads - 1) / threads;
-        PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)v.n_tiles * sizeof(int32_t), st));
-        PC_CUDA_TRY(cudaMemsetAsync(v.item_act, 0, (size_t)v.n_items * sizeof(int32_t), st));
-        tile_active_kernel<<<(unsigned)blocks, threads, 0, st>>>(v, lgam, v.tile_active);
+        const int64_t warps = v.n_xtiles * ACT_SPLIT;
+        const int64_t blocks = (warps * 32 + ACT_THREADS - 1) / ACT_THREADS;
+        // tile flags, item counts and the ticket counter behind them are one scratch range
+        PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)((char *)(v.item_act + v.n_items + 1) - (char *)v.tile_active), st));
+        tile_active_kernel<<<(unsigned)blocks, ACT_THREADS, 0, st>>>(v, lgam, v.tile_active);
         PC_LAUNCH_CHECK();
-        item_order_kernel<<<1, 1024, 0, st>>>(v.n_items, v.item_act, v.item_order);
-        PC_LAUNCH_CHECK();
-        h->launches += 2;
+        h->launches += 1;
     }
     kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc,
                                                  h->debug_flags);

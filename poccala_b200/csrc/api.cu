@@ -285,8 +285,8 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_scratch = add(nullptr, (size_t)frame_off[n_utt] * 16);  // float4 per frame (K2)
     size_t o_scratch1 = add(nullptr, (size_t)emis_off[n_utt] * 4);    // beta_hat rows (K2)
     size_t o_tact = add(nullptr, (size_t)n_tiles * 4);                 // active-tile flags (K3)
+    size_t o_iact = add(nullptr, (size_t)(n_items + 1) * 4);           // directly behind: item counts + a ticket counter
     size_t o_titem = add(tile_item.data(), (size_t)n_tiles * 4);
-    size_t o_iact = add(nullptr, (size_t)n_items * 4);
     size_t o_iord = add(nullptr, (size_t)n_items * 4);
     size_t o_sutt = add(sitem_utt.data(), (size_t)n_sitems * 4);
     size_t o_st0 = add(sitem_t0.data(), (size_t)n_sitems * 4);

@@ -50,7 +50,7 @@ struct CorpusView {
     float *scratch1;              // [emission floats] K2 scratch: beta_hat rows, same layout as b / lgam
     int32_t *tile_active;         // [n_tiles] K3 scratch: 1 = the tile carries posterior mass
     const int32_t *tile_item;     // [n_tiles] work item of each unit-major tile
-    int32_t *item_act;            // [n_items] K3 scratch: active tiles of the item
+    int32_t *item_act;            // [n_items + 1] K3 scratch, directly behind tile_active: active tiles of the item; [n_items] = block ticket counter
     int32_t *item_order;          // [n_items] K3 scratch: items sorted by active tiles, heaviest first
     // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
     int64_t total_frames;
