@@ -249,8 +249,9 @@ def run_gpu(args):
             es.em_iteration(c_covariance=1e-6, group=group)
             return
         ev[0].record(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
+        es.reduce_transitions_async(group)  # side stream: transition log-sum-exp + the MAX collective, under K3
         es.accumulate(); ev[3].record()
-        es.reduce_statistics(group)  # transition log-sum-exp + the two NCCL collectives
+        es.reduce_statistics(group)  # join + the SUM collective over the flat statistics buffer
         es.mstep(c_covariance=1e-6)
         ev[4].record()
 

@@ -61,6 +61,8 @@ int pc_destroy(pc_handle h) {
     if (h->copy_stream) {
         cudaStreamDestroy(h->copy_stream);
         cudaEventDestroy(h->start_ev);
+        cudaEventDestroy(h->fork_ev);
+        cudaEventDestroy(h->join_ev);
         for (int k = 0; k < PC_MAX_CHUNKS; ++k) cudaEventDestroy(h->chunk_ev[k]);
     }
     delete h;
@@ -693,6 +695,8 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     if (!h->copy_stream) {
         PC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         PC_CUDA_TRY(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
         for (int k = 0; k < PC_MAX_CHUNKS; ++k)
             PC_CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
     }
@@ -730,6 +734,13 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     }
     if (!tc_score && (rc = launch_score_simt(h, c->v, X, W, mix, b, st))) return rc;
     if ((rc = launch_forward_backward(h, c->v, b, ls, ln, lg, c->v.scratch0, logp, iters, pt, st))) return rc;
+    // the transition reductions need K2's outputs only: they run on the (by now idle) copy stream,
+    // beside the accumulation kernel
+    PC_CUDA_TRY(cudaEventRecord(h->fork_ev, st));
+    PC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->fork_ev, 0));
+    if ((rc = launch_transitions_max(h, c->v, logp, pt, tmax, h->copy_stream))) return rc;
+    if ((rc = launch_transitions_sum(h, c->v, logp, pt, tmax, tsum, h->copy_stream))) return rc;
+    PC_CUDA_TRY(cudaEventRecord(h->join_ev, h->copy_stream));
     if (!(fix_code & 2))
     {
         if (h->use_tc && accumulate_tc_supported(mix)) {
@@ -738,8 +749,7 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
             return rc;
         }
     }
-    if ((rc = launch_transitions_max(h, c->v, logp, pt, tmax, st))) return rc;
-    if ((rc = launch_transitions_sum(h, c->v, logp, pt, tmax, tsum, st))) return rc;
+    PC_CUDA_TRY(cudaStreamWaitEvent(st, h->join_ev, 0));
     if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, nullptr, nullptr, c_cov,
                                    fix_code, mean, var, alpha, tm, st))) return rc;
     sum_double_kernel<<<1, 32, 0, st>>>(logp, c->v.n_utt, sum);

@@ -15,7 +15,7 @@
 __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 #define PC_NEG_INF (-INFINITY)
-#define PC_L2_RUN_BYTES (64ll << 20)  // frame-tile images one K3 run of utterances may span (L2 = 126 MB)
+#define PC_L2_RUN_BYTES (32ll << 20)  // frame-tile images one (run, unit) block of K3 work items may span
 #define PC_MAX_CHUNKS 8  // host-buffer entry point: transfer / prepare / score pipeline depth
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
@@ -139,6 +139,7 @@ struct pc_handle_s {
     cudaStream_t copy_stream;                 // host-buffer entry point: frames travel on their own stream
     cudaEvent_t chunk_ev[PC_MAX_CHUNKS];
     cudaEvent_t start_ev;
+    cudaEvent_t fork_ev, join_ev;             // transition reductions beside the accumulation kernel
 };
 
 struct pc_corpus_s {

@@ -23,16 +23,27 @@ def shard_utterances(n_utt, rank, world):
     return list(range(rank, n_utt, world))
 
 
+def allreduce_transition_maxima(tmax, group=None):
+    """Collective 1: local maxima of the log-domain transition accumulators -> global maxima."""
+    if group is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX, group=group)
+
+
+def allreduce_flat_statistics(flat, group=None):
+    """Collective 2: one SUM over [linear GMM statistics | transition sums relative to the global maxima]."""
+    if group is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+
+
 def allreduce_em_statistics(flat, tmax, compute_tsum, group=None):
     """flat: 1-D fp64 tensor = [linear GMM statistics | transition sums]; the transition-sum part is
     (re)computed by `compute_tsum()` AFTER the maxima are global, then the whole buffer is summed.
     tmax: fp64 tensor of local maxima, replaced by the global ones.  No-op collectives when
-    `group` is None (single rank)."""
-    if group is not None:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX, group=group)
+    `group` is None (single rank).  (EStep issues the same three steps itself, the first two on a
+    side stream so that they run under the accumulation kernel.)"""
+    allreduce_transition_maxima(tmax, group)
     compute_tsum()
-    if group is not None:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    allreduce_flat_statistics(flat, group)
 
 
 def log_accumulators(tmax, tsum):

@@ -55,6 +55,12 @@ class Engine:
     def get_option(self, key):
         return int(nat.lib().pc_get_option(self.h, key.encode()))
 
+    def side_stream(self):
+        """Stream for work that may run beside the main kernels (transition reductions under K3)."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     @property
     def launches(self):
         return self.get_option("launches")
@@ -295,24 +301,42 @@ class EStep:
         nat.call("pc_accumulate", self.engine.h, self.corpus.c, _p(self.corpus.X), _p(m.W), m.mix, _p(self.b),
                  _p(self.lgam), _p(self.acc), _stream())
 
-    def reduce_statistics(self, group=None):
-        """Per-unit log-sum-exp of the transition counts (pc_transitions_max / _sum) and, with a
-        process group, the two collectives of poccala_b200.distributed."""
-        nat.call("pc_transitions_max", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
-                 _p(self.tmax), _stream())  # writes every (unit, slot): -inf where the unit has no pair
-
-        def local_sums():
+    def reduce_transitions_async(self, group=None):
+        """Per-unit log-sum-exp of the transition counts (pc_transitions_max / _sum) and, with a process
+        group, the MAX collective between the two - on the engine's side stream, forked from the current
+        stream: they depend on K2's outputs only, so they run under the accumulation kernel (small
+        blocks fit beside its one persistent CTA per SM).  reduce_statistics() joins."""
+        cur = torch.cuda.current_stream()
+        side = self.engine.side_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            nat.call("pc_transitions_max", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
+                     _p(self.tmax), _stream())  # writes every (unit, slot): -inf where the unit has no pair
+            _dist.allreduce_transition_maxima(self.tmax, group)
             nat.call("pc_transitions_sum", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
                      _p(self.tmax), _p(self.tsum), _stream())
+            self._side_done = torch.cuda.Event()
+            self._side_done.record(side)
 
-        _dist.allreduce_em_statistics(self.flat, self.tmax, local_sums, group)
+    def reduce_statistics(self, group=None):
+        """Accumulator reduction: the transition reductions (started by
+        reduce_transitions_async, or here) joined into the current stream, then ONE SUM collective over
+        the flat buffer [linear GMM statistics | transition sums] when `group` is a process group."""
+        if getattr(self, "_side_done", None) is None:
+            self.reduce_transitions_async(group)
+        torch.cuda.current_stream().wait_event(self._side_done)
+        self._side_done = None
+        _dist.allreduce_flat_statistics(self.flat, group)
 
     reduce_transitions = reduce_statistics
 
     def estep(self, fix_code=0, group=None):
-        """K1 -> K2 -> K3 -> accumulator reduction (+ allreduce when `group` is a process group)."""
+        """K1 -> K2 -> (K3 || transition reductions) -> accumulator reduction."""
         self.score()
         self.forward_backward()
+        self.reduce_transitions_async(group)
         if not (fix_code & 2):
             self.accumulate()
         else:
