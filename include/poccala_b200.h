@@ -139,7 +139,12 @@ int pc_gmm_score_dense(pc_handle h, const float *dev_X, int64_t n, const float *
  * transmat diagonal / super-diagonal (host-computed np.log).  Outputs: lgam (same layout as b),
  * utt_logp double [n_utt], utt_iters int32 [n_utt] (Baum-Welch iterations the reference would
  * run), pair_trans float [n_pairs][9]: log expected (self, next, occupancy) counts over t<T-1 per
- * emitting state, RELATIVE to utt_logp (reference value = utt_logp + pair_trans, Q6). */
+ * emitting state, RELATIVE to utt_logp (reference value = utt_logp + pair_trans, Q6).
+ * Side effect: the corpus object remembers, for dev_lgam, which (128-frame tile, label position)
+ * pairs carry posterior mass (every log gamma of the others lies below log 2^-41); the next
+ * pc_accumulate on this corpus with the same dev_lgam pointer uses that once instead of re-reading
+ * the rows.  A caller that edits dev_lgam in place between the two calls must pass it through a
+ * different pointer, or call pc_forward_backward again. */
 int pc_forward_backward(pc_handle h, pc_corpus c, const float *dev_b, const double *dev_log_self,
                         const double *dev_log_next, float *dev_lgam, double *dev_utt_logp,
                         int32_t *dev_utt_iters, float *dev_pair_trans, void *stream);
@@ -153,7 +158,9 @@ int pc_log_bands(pc_handle h, const double *dev_transmat, int32_t n_units, doubl
 /* ---- K3: Baum-Welch accumulation -----------------------------------------------------------
  * LHMM.update_acc -> Clustering.GMM.update_acc (LHMM.py:473-507, Clustering.py:653-680) in the
  * linear-equivalent form of SURVEY A.4: acc[g] += sum_t gamma_t(j,m) * [x, x^2, 1, 1].
- * dev_acc is accumulated into (caller zeroes it at the start of an EM iteration). */
+ * dev_acc is accumulated into (caller zeroes it at the start of an EM iteration).  Pairs without
+ * posterior mass are skipped exactly (their fp16 posterior tiles are all zero): the flags come from
+ * the preceding pc_forward_backward on the same dev_lgam, else from a pre-pass over dev_lgam. */
 int pc_accumulate(pc_handle h, pc_corpus c, const float *dev_X, const float *dev_W, int32_t mix,
                   const float *dev_b, const float *dev_lgam, double *dev_acc, void *stream);
 

@@ -43,7 +43,7 @@ constexpr float P_UNSHIFT = 1.f / 32768.f;
 // the kernel would multiply by an all-zero P tile; such tiles are dropped from the work list.  On
 // forced-alignment-like posteriors (a label position is occupied during a small part of its
 // utterance) that is more than half of the tiles.
-constexpr float ACTIVE_MIN_LGAM = -41.f * 0.6931471805599453f;
+constexpr float ACTIVE_MIN_LGAM = PC_ACTIVE_MIN_LGAM;
 
 // Four warps per 128-frame tile of an utterance (32 frames each): coalesced rows of log gamma (lane =
 // state column), eight rows in flight per lane, running maximum per column, then
@@ -99,6 +99,7 @@ tile_active_kernel(CorpusView v, const float *__restrict__ lgam, int32_t *__rest
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    if (threadIdx.x == 0) v.item_act[v.n_items] = 0;  // the ticket counter is left clean for the next launch
     for (int i = threadIdx.x; i < 64; i += ACT_THREADS) bin[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < v.n_items; i += ACT_THREADS) atomicAdd(&bin[63 - min(__ldcg(v.item_act + i), 63)], 1);
@@ -110,6 +111,40 @@ tile_active_kernel(CorpusView v, const float *__restrict__ lgam, int32_t *__rest
     __syncthreads();
     for (int i = threadIdx.x; i < v.n_items; i += ACT_THREADS)
         v.item_order[atomicAdd(&bin[63 - min(__ldcg(v.item_act + i), 63)], 1)] = i;
+}
+
+// For flags that K2 set (launch_forward_backward): one warp per item counts its active tiles, the block that
+// finishes last orders the items.
+__global__ void __launch_bounds__(1024)
+item_order_kernel(CorpusView v) {
+    __shared__ int bin[64];
+    __shared__ int is_last;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i < v.n_items) {
+        const int64_t lo = v.item_tile_lo[i], hi = v.item_tile_lo[i + 1];  // <= 64 tiles
+        const unsigned a0 = __ballot_sync(0xffffffffu, lo + lane < hi && __ldcg(v.tile_active + lo + lane) != 0);
+        const unsigned a1 = __ballot_sync(0xffffffffu, lo + 32 + lane < hi && __ldcg(v.tile_active + lo + 32 + lane) != 0);
+        if (lane == 0) v.item_act[i] = __popc(a0) + __popc(a1);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(v.item_act + v.n_items, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) v.item_act[v.n_items] = 0;  // the ticket counter is left clean for the next launch
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) bin[k] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < v.n_items; k += blockDim.x) atomicAdd(&bin[63 - min(__ldcg(v.item_act + k), 63)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int k = 0; k < 64; ++k) { const int c = bin[k]; bin[k] = run; run += c; }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < v.n_items; k += blockDim.x)
+        v.item_order[atomicAdd(&bin[63 - min(__ldcg(v.item_act + k), 63)], 1)] = k;
 }
 
 // NC = Gaussians handled per work item (a unit's 3*MIX Gaussians, or a slice of them)
@@ -535,21 +570,25 @@ accumulate_tc_kernel(CorpusView v, const float *__restrict__ X, const float *__r
 
 template <int MIX>
 int launch_mix(pc_handle h, const CorpusView &v, const float *X, const float *W, const float *b,
-               const float *lgam, double *acc, cudaStream_t st) {
+               const float *lgam, double *acc, bool flags_fresh, cudaStream_t st) {
     auto kern = accumulate_tc_kernel<MIX>;
     PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MIX>::SMEM));
     const int n_work = v.n_items * Cfg<MIX>::N_SLICES;
     const int grid = n_work < h->sm_count ? n_work : h->sm_count;
-    {
+    if (flags_fresh) {
+        item_order_kernel<<<(v.n_items + 31) / 32, 1024, 0, st>>>(v);
+        PC_LAUNCH_CHECK();
+        h->launches += 1;
+    } else {
         const int64_t warps = v.n_xtiles * ACT_SPLIT;
         const int64_t blocks = (warps * 32 + ACT_THREADS - 1) / ACT_THREADS;
-        // tile flags, item counts and the ticket counter behind them are one scratch range
-        PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)((char *)(v.item_act + v.n_items + 1) - (char *)v.tile_active), st));
+        // tile flags and the item counts behind them are one scratch range (the ticket counter cleans itself)
+        PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)((char *)(v.item_act + v.n_items) - (char *)v.tile_active), st));
         tile_active_kernel<<<(unsigned)blocks, ACT_THREADS, 0, st>>>(v, lgam, v.tile_active, h->debug_flags);
         PC_LAUNCH_CHECK();
         h->launches += 1;
-        if (h->debug_flags & 256) return PC_OK;  // timing experiment: pre-pass only
     }
+    if (h->debug_flags & 256) return PC_OK;  // timing experiment: pre-pass only
     kern<<<grid, NTHREADS, Cfg<MIX>::SMEM, st>>>(v, X, W, v.n_units * PC_EMIT * MIX, b, lgam, v.tile_active, acc,
                                                  h->debug_flags);
     PC_LAUNCH_CHECK();
@@ -568,14 +607,14 @@ extern "C" int pc_debug_read_acc(long long *host_out, int n) {
 bool accumulate_tc_supported(int mix) { return mix == 4 || mix == 8 || mix == 16 || mix == 32 || mix == 64; }
 
 int launch_accumulate_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
-                         const float *b, const float *lgam, double *acc, cudaStream_t st) {
+                         const float *b, const float *lgam, double *acc, bool flags_fresh, cudaStream_t st) {
     if (v.n_items == 0) return PC_OK;
     switch (mix) {
-        case 4: return launch_mix<4>(h, v, X, W, b, lgam, acc, st);
-        case 8: return launch_mix<8>(h, v, X, W, b, lgam, acc, st);
-        case 16: return launch_mix<16>(h, v, X, W, b, lgam, acc, st);
-        case 32: return launch_mix<32>(h, v, X, W, b, lgam, acc, st);
-        case 64: return launch_mix<64>(h, v, X, W, b, lgam, acc, st);
+        case 4: return launch_mix<4>(h, v, X, W, b, lgam, acc, flags_fresh, st);
+        case 8: return launch_mix<8>(h, v, X, W, b, lgam, acc, flags_fresh, st);
+        case 16: return launch_mix<16>(h, v, X, W, b, lgam, acc, flags_fresh, st);
+        case 32: return launch_mix<32>(h, v, X, W, b, lgam, acc, flags_fresh, st);
+        case 64: return launch_mix<64>(h, v, X, W, b, lgam, acc, flags_fresh, st);
     }
     pc_set_error("launch_accumulate_tc: mix=%d not covered", mix);
     return PC_ERR_UNSUPPORTED;

@@ -300,6 +300,11 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     PC_CUDA_TRY(cudaSetDevice(h->device));
     char *dev = nullptr;
     PC_CUDA_TRY(cudaMalloc((void **)&dev, std::max<size_t>(total, 256)));
+    if (cudaMemset(dev, 0, std::max<size_t>(total, 256)) != cudaSuccess) {  // scratch regions start clean (K3's ticket counter)
+        cudaFree(dev);
+        pc_set_error("pc_corpus_create: cudaMemset failed");
+        return PC_ERR_CUDA;
+    }
     for (const Seg &s : segs)
         if (s.src && s.bytes) {
             cudaError_t e = cudaMemcpy(dev + s.off, s.src, s.bytes, cudaMemcpyHostToDevice);
@@ -517,8 +522,10 @@ int pc_forward_backward(pc_handle h, pc_corpus c, const float *b, const double *
     PC_ENTER(h);
     PC_REQUIRE(c && b && log_self && log_next && lgam && utt_logp && utt_iters && pair_trans,
                "pc_forward_backward: NULL argument");
-    return launch_forward_backward(h, c->v, b, log_self, log_next, lgam, c->v.scratch0, utt_logp,
-                                   utt_iters, pair_trans, (cudaStream_t)stream);
+    int rc = launch_forward_backward(h, c->v, b, log_self, log_next, lgam, c->v.scratch0, utt_logp,
+                                     utt_iters, pair_trans, (cudaStream_t)stream);
+    c->flags_lgam = rc == PC_OK ? lgam : nullptr;
+    return rc;
 }
 
 int pc_accumulate(pc_handle h, pc_corpus c, const float *X, const float *W, int32_t mix,
@@ -527,8 +534,12 @@ int pc_accumulate(pc_handle h, pc_corpus c, const float *X, const float *W, int3
     PC_REQUIRE(c && X && W && b && lgam && acc, "pc_accumulate: NULL argument");
     int rc = check_dim_mix("pc_accumulate", 1, mix);
     if (rc) return rc;
+    // the flags K2 left behind are used once, for the buffer it wrote, on the stream order the caller
+    // gives; log gamma from anywhere else (or a second pass) goes through the pre-pass
+    const bool fresh = c->flags_lgam == lgam && !(h->debug_flags & 2048);
+    c->flags_lgam = nullptr;
     if (h->use_tc && accumulate_tc_supported(mix))
-        return launch_accumulate_tc(h, c->v, X, W, mix, b, lgam, acc, (cudaStream_t)stream);
+        return launch_accumulate_tc(h, c->v, X, W, mix, b, lgam, acc, fresh, (cudaStream_t)stream);
     return launch_accumulate_simt(h, c->v, X, W, mix, b, lgam, acc, (cudaStream_t)stream);
 }
 
@@ -734,6 +745,7 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     }
     if (!tc_score && (rc = launch_score_simt(h, c->v, X, W, mix, b, st))) return rc;
     if ((rc = launch_forward_backward(h, c->v, b, ls, ln, lg, c->v.scratch0, logp, iters, pt, st))) return rc;
+    c->flags_lgam = nullptr;  // consumed below
     // the transition reductions need K2's outputs only: they run on the (by now idle) copy stream,
     // beside the accumulation kernel
     PC_CUDA_TRY(cudaEventRecord(h->fork_ev, st));
@@ -744,7 +756,7 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     if (!(fix_code & 2))
     {
         if (h->use_tc && accumulate_tc_supported(mix)) {
-            if ((rc = launch_accumulate_tc(h, c->v, X, W, mix, b, lg, acc, st))) return rc;
+            if ((rc = launch_accumulate_tc(h, c->v, X, W, mix, b, lg, acc, true, st))) return rc;
         } else if ((rc = launch_accumulate_simt(h, c->v, X, W, mix, b, lg, acc, st))) {
             return rc;
         }

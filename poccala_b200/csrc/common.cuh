@@ -16,6 +16,10 @@ __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 #define PC_NEG_INF (-INFINITY)
 #define PC_L2_RUN_BYTES (32ll << 20)  // frame-tile images one (run, unit) block of K3 work items may span
+// A (tile, unit) pair whose log gamma all lie below log(2^-41) contributes exactly nothing to K3 (see
+// accumulate_tc.cu); K2 sets the activity flags while it writes the rows, K3's own pre-pass does it
+// for log gamma that came from elsewhere.
+#define PC_ACTIVE_MIN_LGAM (-41.f * 0.6931471805599453f)
 #define PC_MAX_CHUNKS 8  // host-buffer entry point: transfer / prepare / score pipeline depth
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
@@ -152,6 +156,7 @@ struct pc_corpus_s {
     void *dev_block;     // one allocation holding every table
     int64_t *host_frame_off, *host_emis_off, *host_pair_off, *host_state_off;
     int32_t items_per_chunk;
+    const float *flags_lgam;  // log-gamma buffer whose K3 activity flags K2 left in v.tile_active (consumed by pc_accumulate)
     // runs of consecutive utterances the host-buffer entry point pipelines (copy k+1 under score k)
     int32_t n_chunks;
     int64_t chunk_frame[PC_MAX_CHUNKS + 1];  // first frame of each chunk
@@ -176,8 +181,9 @@ bool score_tc_supported(int mix);
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                     float *b, int item_lo, int item_hi, cudaStream_t st);
 bool accumulate_tc_supported(int mix);
+// flags_fresh: the activity flags of `lgam` were set by launch_forward_backward (skip the pre-pass)
 int launch_accumulate_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
-                         const float *b, const float *lgam, double *acc, cudaStream_t st);
+                         const float *b, const float *lgam, double *acc, bool flags_fresh, cudaStream_t st);
 int launch_score_dense_simt(pc_handle h, const float *X, int64_t n, const float *W, int n_states,
                             int mix, float *out, cudaStream_t st);
 int launch_accumulate_simt(pc_handle h, const CorpusView &v, const float *X, const float *W,

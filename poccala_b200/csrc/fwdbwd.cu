@@ -395,6 +395,23 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             }
         };
         load_beta(tau_lo, bt_nxt);
+        // K3's activity flags, set while the rows are at hand: running maximum of log gamma per state over
+        // the current 128-frame tile (frame 0 comes from the chain warp's row0), flag of the (tile, position)
+        // pair at the tile's last frame - the same values and threshold as K3's own pre-pass reads back
+        float tmx[SPL];
+        int32_t *flag0[SPL];  // -> flag of (tile 0, this state's position); the pair's tiles are consecutive
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            tmx[q] = (kind[q] == 1) ? sm->row0[lane * SPL + q] * kLn2 : PC_NEG_INF;
+            flag0[q] = v.tile_active + ((kind[q] == 1) ? v.pair_tile0[p0 + col[q] / PC_EMIT] : 0);
+        }
+        auto flag_tile = [&](int k_tile) {  // plain stores: idempotent, nothing to wait for
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                if (kind[q] == 1 && tmx[q] > PC_ACTIVE_MIN_LGAM) flag0[q][k_tile] = 1;
+                tmx[q] = PC_NEG_INF;
+            }
+        };
         uint32_t grp = 0;
         while (tau_lo <= T - 1) {
             float bt[FB_GRP][SPL];
@@ -437,6 +454,10 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
                 for (int k = 0; k < FB_GRP; ++k) ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], o);
             }
             tc::mbar_wait(&sm->empty2[gs], ((grp / FB_NGRP) & 1) ^ 1);  // helper B is done with this slot
+            const int kb = (tau_lo | (PC_TILE_ROWS - 1)) - tau_lo;  // group index of the tile's last frame (>= FB_GRP: not here)
+            float tnx[SPL];
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) tnx[q] = PC_NEG_INF;
 #pragma unroll
             for (int k = 0; k < FB_GRP; ++k) {
                 const float Z = mm[k] + lg2f(ssum[k]);  // -inf when the frame carries no mass at all
@@ -445,14 +466,25 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
                 for (int q = 0; q < SPL; ++q) {
                     const float lg = ab[k][q] - Z;
                     sm->lgr[gs * FB_GRP + k][lane * SPL + q] = lg;
-                    if (valid && kind[q] == 1) grow[q][(tau_lo + k) * sp] = lg * kLn2;
+                    if (valid && kind[q] == 1) {
+                        grow[q][(tau_lo + k) * sp] = lg * kLn2;
+                        // frames up to the tile's last one (index kb inside the group) / frames of the next tile
+                        if (k <= kb) tmx[q] = fmaxf(tmx[q], lg * kLn2);
+                        else tnx[q] = fmaxf(tnx[q], lg * kLn2);
+                    }
                 }
+            }
+            if (kb < FB_GRP) {  // a tile ended inside this group: one uniform branch per group
+                flag_tile(tau_lo / PC_TILE_ROWS);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) tmx[q] = tnx[q];
             }
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sm->full2[gs]);
             tau_lo += FB_GRP;
             ++grp;
         }
+        flag_tile((T - 1) / PC_TILE_ROWS);  // the last, partial tile (all -inf if it ended on a boundary)
         if (trace) g_fb_dbg[5] = clock64();
     } else {
         // ============================================================ HELPER B: transition counts
@@ -564,6 +596,8 @@ int launch_fb(pc_handle h, const CorpusView &v, const float *b, const double *lo
     const int blocks = (v.n_utt + FB_UPB - 1) / FB_UPB;
     const size_t smem = FB_UPB * sizeof(PairSmem<SPL>);
     auto kern = fwdbwd_kernel<SPL, FB_GRP>;
+    // K3's tile flags: the log-gamma helper warps set them
+    if (v.n_tiles > 0) PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)v.n_tiles * sizeof(int32_t), st));
     if (smem > 48 * 1024)
         PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, FB_UPB * 96, smem, st>>>(v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters,

@@ -395,3 +395,35 @@ def test_error_behaviour(eng):
         Corpus(eng, [np.array([0, 7])], np.array([10], dtype=np.int32), 3)  # label outside the unit set
     with pytest.raises(nat.NativeError):
         Corpus(eng, [np.array([0])], np.array([0], dtype=np.int32), 3)  # empty utterance
+
+
+@pytest.mark.parametrize("L", [3, 14])  # one state per lane / two states per lane in K2
+def test_activity_flags_from_forward_backward_equal_the_pre_pass(eng, L):
+    """K2's log-gamma helper sets K3's (tile, position) activity flags while it writes the rows; K3's
+    own pre-pass derives them from log gamma that came from elsewhere.  Same flags and the same
+    statistics either way, including utterances of 3, 127, 128, 129 and 300 frames."""
+    from poccala_b200 import _native as nat
+
+    n_units, mix = 5, 4
+    truth, init, _, _ = synth.make_corpus(2, 8, L, n_units, mix, 7)
+    rng = np.random.default_rng(70 + L)
+    lens = [3, 5, 127, 128, 129, 255, 256, 257, 300, 40, 77]
+    labels = [rng.integers(0, n_units, size=int(rng.integers(1, L + 1))).astype(np.int32) for _ in lens]
+    labels[0] = labels[0][:1]
+    utts = [synth.make_utterance(lab, T, truth, 900 + i) for i, (lab, T) in enumerate(zip(labels, lens))]
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
+    es.score()
+    es.forward_backward()
+    es.accumulate()  # flags set by K2
+    torch.cuda.synchronize()
+    n_k2 = int(nat.lib().pc_corpus_active_tiles(corpus.c))
+    acc_k2 = es.acc.clone()
+    es.accumulate()  # the flags were consumed: K3's own pre-pass
+    torch.cuda.synchronize()
+    n_pre = int(nat.lib().pc_corpus_active_tiles(corpus.c))
+    assert n_k2 == n_pre and 0 < n_k2 <= int(nat.lib().pc_corpus_total_tiles(corpus.c))
+    scale = es.acc.abs().amax(dim=1, keepdim=True).clamp_min(1e-6)
+    assert ((acc_k2 - es.acc).abs() <= 1e-9 * scale).all()  # fp64 atomics: order only
+    stats, info = fast.estep_corpus(om, labels, utts)
+    occ = acc_k2.cpu().numpy().reshape(n_units, 3, om.mix, 80)[..., 39]
+    assert _relerr(occ, stats.occ, floor=1e-3) < REL
