@@ -248,7 +248,10 @@ def run_gpu(args):
         if ev is None:
             es.em_iteration(c_covariance=1e-6, group=group)
             return
-        ev[0].record(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
+        ev[0].record()
+        if not os.environ.get("PC_NO_BANDS_ASYNC"):
+            es.log_bands_async()  # log(transmat) bands on the side stream, beside K1
+        es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
         es.reduce_transitions_async(group)  # side stream: transition log-sum-exp + the MAX collective, under K3
         es.accumulate(); ev[3].record()
         es.reduce_statistics(group)  # join + the SUM collective over the flat statistics buffer

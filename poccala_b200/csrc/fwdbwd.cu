@@ -90,6 +90,7 @@ struct PairSmem {
     float ring[FB_NGRP * FB_GRP][32 * SPL];  // alpha_hat rows of frames 1.. (slot (t-1) % depth)
     float lgr[FB_NGRP * FB_GRP][32 * SPL];   // log2 gamma rows of the same frames (helper A -> helper B)
     float row0[32 * SPL];                    // log2 gamma_0 (all materialised states)
+    float tmx_row[32 * SPL + 2];             // per-state maxima of log gamma over a tile (helper A, at tile ends)
     uint64_t full[FB_NGRP], empty[FB_NGRP], full2[FB_NGRP], empty2[FB_NGRP], start;
 };
 
@@ -405,12 +406,22 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             tmx[q] = (kind[q] == 1) ? sm->row0[lane * SPL + q] * kLn2 : PC_NEG_INF;
             flag0[q] = v.tile_active + ((kind[q] == 1) ? v.pair_tile0[p0 + col[q] / PC_EMIT] : 0);
         }
-        auto flag_tile = [&](int k_tile) {  // plain stores: idempotent, nothing to wait for
+        // every (tile, position) flag is written exactly once per run, 0 or 1, by the lane that holds the
+        // position's first state (the three states' maxima meet in shared memory): no memset, no atomics
+        auto flag_tile = [&](int k_tile) {
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) sm->tmx_row[lane * SPL + q] = tmx[q];
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < SPL; ++q) {
-                if (kind[q] == 1 && tmx[q] > PC_ACTIVE_MIN_LGAM) flag0[q][k_tile] = 1;
+                if (kind[q] == 1 && col[q] % PC_EMIT == 0) {
+                    const int s = lane * SPL + q;
+                    const float m = fmaxf(fmaxf(sm->tmx_row[s], sm->tmx_row[s + 1]), sm->tmx_row[s + 2]);
+                    flag0[q][k_tile] = m > PC_ACTIVE_MIN_LGAM ? 1 : 0;
+                }
                 tmx[q] = PC_NEG_INF;
             }
+            __syncwarp();
         };
         uint32_t grp = 0;
         while (tau_lo <= T - 1) {
@@ -474,7 +485,7 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
                     }
                 }
             }
-            if (kb < FB_GRP) {  // a tile ended inside this group: one uniform branch per group
+            if (kb < FB_GRP && tau_lo + kb <= T - 1) {  // a tile's last frame lies in this group: one uniform branch per group
                 flag_tile(tau_lo / PC_TILE_ROWS);
 #pragma unroll
                 for (int q = 0; q < SPL; ++q) tmx[q] = tnx[q];
@@ -484,7 +495,7 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             tau_lo += FB_GRP;
             ++grp;
         }
-        flag_tile((T - 1) / PC_TILE_ROWS);  // the last, partial tile (all -inf if it ended on a boundary)
+        if (((T - 1) & (PC_TILE_ROWS - 1)) != PC_TILE_ROWS - 1) flag_tile((T - 1) / PC_TILE_ROWS);  // the last, partial tile
         if (trace) g_fb_dbg[5] = clock64();
     } else {
         // ============================================================ HELPER B: transition counts
@@ -596,8 +607,6 @@ int launch_fb(pc_handle h, const CorpusView &v, const float *b, const double *lo
     const int blocks = (v.n_utt + FB_UPB - 1) / FB_UPB;
     const size_t smem = FB_UPB * sizeof(PairSmem<SPL>);
     auto kern = fwdbwd_kernel<SPL, FB_GRP>;
-    // K3's tile flags: the log-gamma helper warps set them
-    if (v.n_tiles > 0) PC_CUDA_TRY(cudaMemsetAsync(v.tile_active, 0, (size_t)v.n_tiles * sizeof(int32_t), st));
     if (smem > 48 * 1024)
         PC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<blocks, FB_UPB * 96, smem, st>>>(v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters,

@@ -290,8 +290,25 @@ class EStep:
         nat.call("pc_gmm_score", self.engine.h, self.corpus.c, _p(self.corpus.X), _p(m.W), m.mix, _p(self.b),
                  _stream())
 
+    def log_bands_async(self):
+        """log(transmat) bands on the side stream: they depend on the model only, so they are formed
+        beside K1 (forward_backward() joins)."""
+        cur = torch.cuda.current_stream()
+        side = self.engine.side_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            self._bands = self.model.log_bands()
+            self._bands_done = torch.cuda.Event()
+            self._bands_done.record(side)
+
     def forward_backward(self):
-        ls, ln = self.model.log_bands()
+        if getattr(self, "_bands_done", None) is not None:
+            torch.cuda.current_stream().wait_event(self._bands_done)
+            (ls, ln), self._bands_done = self._bands, None
+        else:
+            ls, ln = self.model.log_bands()
         nat.call("pc_forward_backward", self.engine.h, self.corpus.c, _p(self.b), _p(ls), _p(ln), _p(self.lgam),
                  _p(self.utt_logp), _p(self.utt_iters), _p(self.pair_trans), _stream())
 
@@ -333,7 +350,8 @@ class EStep:
     reduce_transitions = reduce_statistics
 
     def estep(self, fix_code=0, group=None):
-        """K1 -> K2 -> (K3 || transition reductions) -> accumulator reduction."""
+        """(K1 || log bands) -> K2 -> (K3 || transition reductions) -> accumulator reduction."""
+        self.log_bands_async()
         self.score()
         self.forward_backward()
         self.reduce_transitions_async(group)
