@@ -291,14 +291,16 @@ class EStep:
                  _stream())
 
     def log_bands_async(self):
-        """log(transmat) bands on the side stream: they depend on the model only, so they are formed
-        beside K1 (forward_backward() joins)."""
+        """log(transmat) bands and the clearing of the statistics buffer on the side stream: they depend
+        on the model / on nothing, so they run beside K1 (forward_backward() joins)."""
         cur = torch.cuda.current_stream()
         side = self.engine.side_stream()
         fork = torch.cuda.Event()
         fork.record(cur)
         side.wait_event(fork)
         with torch.cuda.stream(side):
+            self.acc.zero_()  # K3 accumulates into it; cleared here, beside K1, instead of in front of K3
+            self._acc_clean = True
             self._bands = self.model.log_bands()
             self._bands_done = torch.cuda.Event()
             self._bands_done.record(side)
@@ -314,7 +316,11 @@ class EStep:
 
     def accumulate(self):
         m = self.model
-        self.acc.zero_()
+        if not getattr(self, "_acc_clean", False):
+            self.acc.zero_()
+        elif getattr(self, "_bands_done", None) is not None:  # cleared on the side stream, not joined yet
+            torch.cuda.current_stream().wait_event(self._bands_done)
+        self._acc_clean = False
         nat.call("pc_accumulate", self.engine.h, self.corpus.c, _p(self.corpus.X), _p(m.W), m.mix, _p(self.b),
                  _p(self.lgam), _p(self.acc), _stream())
 
