@@ -69,10 +69,19 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
     const bool trace = blockIdx.x == 0 && threadIdx.x == 0;
     if (trace) g_vit_dbg[0] = clock64();
     uint32_t bits[SPL];
+    double econst[SPL];  // emission of the states that do not read b: log 1 (entry), log 0 (exit, padding)
 #pragma unroll
-    for (int q = 0; q < SPL; ++q) bits[q] = 0u;
-    // emission rows are fetched VT_CH frames ahead of the recurrence (they do not depend on it):
-    // without the prefetch every step waited for its own global load (~1 350 clk per frame)
+    for (int q = 0; q < SPL; ++q) {
+        bits[q] = 0u;
+        econst[q] = (kind[q] == 0) ? 0.0 : NINF;
+    }
+    // Frames go in chunks of VT_CH = 16 (8 with more than two states per lane: registers), aligned inside
+    // the 32-bit backpointer words.  The
+    // emission rows of a chunk are fetched one chunk ahead of the recurrence (they do not depend on it:
+    // without the prefetch every step waited for its own global load, ~1 350 clk per frame).  Whole
+    // chunks run unrolled without per-frame bounds checks or branches (the loop is issue-bound once the
+    // SM holds its 28 utterances: ~100 instructions per frame before, ~35 now); the first chunk (frame 0
+    // is the initialisation) and the last, partial one take the checked path.
     constexpr int VT_CH = (SPL <= 2) ? 16 : 8;
     auto load_rows = [&](int t0, E (&e)[VT_CH][SPL]) {
 #pragma unroll
@@ -82,9 +91,27 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
             for (int q = 0; q < SPL; ++q) e[k][q] = (kind[q] == 1) ? bu[(int64_t)t * sp + row[q]] : (E)0;
         }
     };
+    // one frame: p_t(j) = max(p_{t-1}(j-1) + log A_{j-1,j}, p_{t-1}(j) + log A_jj) + B[j,t], tie -> j-1
+    auto frame_step = [&](const E (&erow)[SPL], uint32_t bit) {
+        double left = __shfl_up_sync(0xffffffffu, p[SPL - 1] + ln[SPL - 1], 1);
+        if (lane == 0) left = NINF;
+        double np_[SPL];
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            const double move = (q > 0) ? p[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
+            const double stay = p[q] + ls[q];
+            const bool take = move >= stay;  // tie -> lower index (j-1)
+            const double best = take ? move : stay;
+            const double e = kind[q] == 1 ? (double)erow[q] : econst[q];
+            np_[q] = best + e;  // -inf for the exit state and the padding (their emission is log 0)
+            bits[q] |= take ? bit : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) p[q] = np_[q];
+    };
     E e_nxt[VT_CH][SPL];
-    load_rows(1, e_nxt);
-    for (int t0 = 1; t0 < T; t0 += VT_CH) {
+    load_rows(0, e_nxt);
+    for (int t0 = 0; t0 < T; t0 += VT_CH) {
         E e_cur[VT_CH][SPL];
 #pragma unroll
         for (int k = 0; k < VT_CH; ++k) {
@@ -92,32 +119,22 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
             for (int q = 0; q < SPL; ++q) e_cur[k][q] = e_nxt[k][q];
         }
         load_rows(t0 + VT_CH, e_nxt);
+        const uint32_t half = (uint32_t)(t0 & 31);  // bit position of the chunk's first frame in its word
+        if (t0 > 0 && t0 + VT_CH <= T) {
 #pragma unroll
-        for (int k = 0; k < VT_CH; ++k) {
-            const int t = t0 + k;
-            if (t < T) {
-                double left = __shfl_up_sync(0xffffffffu, p[SPL - 1] + ln[SPL - 1], 1);
-                if (lane == 0) left = NINF;
-                double np_[SPL];
+            for (int k = 0; k < VT_CH; ++k) frame_step(e_cur[k], (1u << k) << half);
+        } else {
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) {
-                    const double move = (q > 0) ? p[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
-                    const double stay = p[q] + ls[q];
-                    const bool take = move >= stay;  // tie -> lower index (j-1)
-                    const double best = take ? move : stay;
-                    const double e = kind[q] == 1 ? (double)e_cur[k][q] : (kind[q] == 0 ? 0.0 : NINF);
-                    np_[q] = (kind[q] == 2) ? NINF : best + e;
-                    bits[q] |= (take ? 1u : 0u) << (t & 31);
-                }
+            for (int k = 0; k < VT_CH; ++k) {
+                const int t = t0 + k;
+                if (t >= 1 && t < T) frame_step(e_cur[k], (1u << k) << half);
+            }
+        }
+        if (((t0 + VT_CH) & 31) == 0 || t0 + VT_CH >= T) {  // the word of frames [32 * (t0 / 32), +32) is complete
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) p[q] = np_[q];
-                if ((t & 31) == 31 || t == T - 1) {
-#pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        bp[((t >> 5) * SPL + q) * 32 + lane] = bits[q];
-                        bits[q] = 0u;
-                    }
-                }
+            for (int q = 0; q < SPL; ++q) {
+                bp[((t0 >> 5) * SPL + q) * 32 + lane] = bits[q];
+                bits[q] = 0u;
             }
         }
     }
@@ -146,30 +163,38 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
     if (lane == 0) score[u] = best;
     // traceback, 32 frames at a time: every lane follows the same chain; the block's backpointer words
     // sit in registers (lane l holds the words of its own states) and the one for the current state
-    // comes by shuffle; lane k keeps the state of frame 32*blk + k, so the stores are coalesced
+    // comes by shuffle.  The walk only records WHERE the path steps down (one bit per frame); lane k
+    // then gets the state of frame 32*blk + k as the block's end state minus the steps taken after
+    // frame k, so the stores are coalesced.  Whole blocks run without per-frame bounds checks.
     int cur = best_s;
     for (int blk = (T - 1) >> 5; blk >= 0; --blk) {
         uint32_t w[SPL];
 #pragma unroll
         for (int q = 0; q < SPL; ++q) w[q] = bp[(blk * SPL + q) * 32 + lane];
         const int t_lo = blk * 32, t_hi = min(T - 1, t_lo + 31);
-        int keep = 0;
+        const int end_state = cur;  // state of frame t_hi
+        uint32_t steps = 0u;        // bit k: the path steps down between frame t_lo + k - 1 and t_lo + k
+        auto back = [&](int k) {
+            uint32_t wsel = w[0];
 #pragma unroll
-        for (int k = 31; k >= 0; --k) {
-            const int t = t_lo + k;
-            if (t <= t_hi) {  // warp-uniform
-                if (k == lane) keep = cur;
-                if (t > 0) {
-                    uint32_t wsel = w[0];
+            for (int q = 1; q < SPL; ++q) wsel = ((cur % SPL) == q) ? w[q] : wsel;
+            const uint32_t bit = (__shfl_sync(0xffffffffu, wsel, cur / SPL) >> k) & 1u;
+            cur -= (int)bit;
+            steps |= bit << k;
+        };
+        if (blk > 0 && t_hi == t_lo + 31) {
 #pragma unroll
-                    for (int q = 1; q < SPL; ++q) wsel = ((cur % SPL) == q) ? w[q] : wsel;
-                    const uint32_t wb = __shfl_sync(0xffffffffu, wsel, cur / SPL);
-                    cur -= (int)((wb >> k) & 1u);
-                }
+            for (int k = 31; k >= 0; --k) back(k);
+        } else {
+#pragma unroll
+            for (int k = 31; k >= 0; --k) {
+                if (t_lo + k <= t_hi && t_lo + k > 0) back(k);  // warp-uniform
             }
         }
         const int tt = t_lo + lane;
         if (tt <= t_hi) {
+            // steps taken after frame tt inside this block: bits lane+1 .. 31
+            const int keep = end_state - __popc(lane < 31 ? (steps >> (lane + 1)) : 0u);
             path[f0 + tt] = keep;
             if (unit_path) {
                 const int pos = keep == 0 ? 0 : (keep > NE ? L - 1 : (keep - 1) / PC_EMIT);
