@@ -414,10 +414,10 @@ def scoring_sweep_leg(eng, pk, F=2_000_000, G=4096, mix=64):
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak}}
 
 
-def viterbi_leg(eng, pk, n_utt=2000, T_v=1000, L_v=20, reps=5):
+def viterbi_leg(eng, pk, n_utt=10000, T_v=1000, L_v=20, reps=5):
     """Second half of BASELINE.json's metric: Viterbi forced alignment frames/s on the configs[3]
     shape (1000-frame utterances against 20 concatenated IF unit HMMs, N = 62 states, 16-mix
-    emissions scored by K1), 2 000 utterances per GPU, emissions resident in HBM.  HBM roofline:
+    emissions scored by K1) at its full size, 10 000 utterances, emissions resident in HBM.  HBM roofline:
     4 B per (emitting state, frame) read + 4 B per frame written."""
     import torch
 
@@ -464,7 +464,7 @@ def viterbi_leg(eng, pk, n_utt=2000, T_v=1000, L_v=20, reps=5):
     d = p[:, 1:] - p[:, :-1]
     ok = bool(((d == 0) | (d == 1)).all().item())
     return {"value": frames / t, "unit": "frames/s", "ms": t * 1e3,
-            "workload": "cfg4 shape: %d utt x %d frames x %d units (N=%d), 16-mix emissions, bit-exact fp64 recurrence"
+            "workload": "cfg4: %d utt x %d frames x %d units (N=%d), 16-mix emissions, bit-exact fp64 recurrence"
                         % (n_utt, T_v, L_v, n_states),
             "roofline": {"bound": "hbm", "achieved": ach, "peak": float(pk["hbm_gbs"]), "unit": "GB/s",
                          "frac": ach / float(pk["hbm_gbs"])},
