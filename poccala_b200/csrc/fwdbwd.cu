@@ -39,7 +39,14 @@
 #define FB_RENORM 8
 #define FB_GRP 8    // frames per ring group (producer / consumer hand-over granularity)
 #define FB_NGRP 4   // ring depth in groups
-#define FB_UPB 2    // utterances (warp pairs) per block
+// utterances (warp triples) per block: 4 with the warps in role-major order when registers allow, so
+// that every SM sub-partition (warp index mod 4) hosts one chain warp and one helper of each kind per
+// block; with 2 (utterance-major order) one chain warp shared its sub-partition with a helper and
+// ran the forward pass at 272 clk per frame while the other ran alone
+template <int SPL>
+struct FbCfg {
+    static constexpr int UPB = (SPL <= 2) ? 4 : 2;
+};
 
 __device__ long long g_fb_dbg[16];
 
@@ -95,7 +102,7 @@ struct PairSmem {
 };
 
 template <int SPL, int CH>
-__global__ void __launch_bounds__(FB_UPB * 96)
+__global__ void __launch_bounds__(FbCfg<SPL>::UPB * 96)
 fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restrict__ log_self,
               const double *__restrict__ log_next, float *lgam, float *scratch,
               double *__restrict__ utt_logp, int32_t *__restrict__ utt_iters,
@@ -103,8 +110,10 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int slot = warp / 3;       // utterance slot inside the block
-    const int role = warp - 3 * slot;  // 0 chain, 1 helper A (log gamma), 2 helper B (transition counts)
+    constexpr int FB_UPB = FbCfg<SPL>::UPB;
+    // role: 0 chain, 1 helper A (log gamma), 2 helper B (transition counts); slot: utterance inside the block
+    const int slot = (FB_UPB == 4) ? (warp & 3) : warp / 3;
+    const int role = (FB_UPB == 4) ? (warp >> 2) : warp - 3 * slot;
     const bool helper = role != 0;
     const int idx = blockIdx.x * FB_UPB + slot;
     if (idx >= v.n_utt) return;      // the three warps of an utterance leave together
@@ -175,7 +184,7 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
             es[q] = (kind[q] == 1) ? (e[q] - g) * kLog2e : (kind[q] == 0 ? -g * kLog2e : PC_NEG_INF);
     };
 
-    const bool trace = (blockIdx.x == 0 && warp <= 2 && lane == 0);
+    const bool trace = (blockIdx.x == 0 && slot == 0 && lane == 0);
     if (trace) g_fb_dbg[role * 4] = clock64();
     // per-lane row pointers: an emitting state lives in column col of the [T][SP] blocks, the entry
     // state's beta_hat in eb (one float per frame); one predicated store serves both
@@ -604,6 +613,7 @@ template <int SPL>
 int launch_fb(pc_handle h, const CorpusView &v, const float *b, const double *log_self,
               const double *log_next, float *lgam, float *scratch0, double *utt_logp,
               int32_t *utt_iters, float *pair_trans, cudaStream_t st) {
+    constexpr int FB_UPB = FbCfg<SPL>::UPB;
     const int blocks = (v.n_utt + FB_UPB - 1) / FB_UPB;
     const size_t smem = FB_UPB * sizeof(PairSmem<SPL>);
     auto kern = fwdbwd_kernel<SPL, FB_GRP>;
