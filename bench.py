@@ -131,49 +131,63 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """SM clock + throttle reasons sampled through NVML every ~2 ms while the timed region runs
-    (nvidia-smi is too slow for a region of tens of milliseconds)."""
+    (nvidia-smi is too slow for a region of tens of milliseconds).  NVML is initialised before the
+    region starts (round 1 lost every sample to a slow nvmlInit)."""
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
         self.max_mhz = None
         self.err = None
-
-    def _run(self):
+        self.h = self.nv = self.get_reasons = None
         try:
             import pynvml as nv
 
             nv.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = self.index
+            idx = index
             if vis:
                 try:
-                    idx = int(vis.split(",")[self.index])
+                    idx = int(vis.split(",")[index])
                 except ValueError:
-                    idx = self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                    idx = index
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self.stop.is_set():
-                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h)),
-                                  time.perf_counter()))
+            self._sample()
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def _sample(self):
+        nv = self.nv
+        self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(self.get_reasons(self.h)),
+                          time.perf_counter()))
+
+    def _run(self):
+        try:
+            while self.h is not None and not self.stop.is_set():
+                self._sample()
                 self.stop.wait(0.002)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
     def __enter__(self):
         self.th.start()
-        time.sleep(0.05)
         return self
 
     def __exit__(self, *a):
+        if self.h is not None and not self.err:
+            try:
+                self._sample()
+            except Exception as e:  # pragma: no cover
+                self.err = repr(e)
         self.stop.set()
         self.th.join(timeout=6)
 
     def summary(self, t0=None, t1=None):
         if t0 is not None:
-            inside = [r for r in self.rows if t0 <= r[2] <= t1]
+            inside = [r for r in self.rows if t0 <= r[2] <= t1 + 0.01]
             self.rows = inside if inside else self.rows[-1:]
         bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
@@ -287,27 +301,50 @@ def run_gpu(args):
     total_ms = float(total_ms.item())
     value = world * frames * args.steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the host-buffer C-ABI call (pinned host frames, H2D + D2H inside)
+    # ---- end-to-end through the host-buffer C-ABI call (pinned host frames, H2D + D2H inside).
+    # The corpus' standardisation constants are computed once (pc_frame_moments_host + all-reduce of the
+    # moments); at N > 1 the reduce hook puts the two NCCL collectives inside the call, so an e2e step is
+    # one distributed EM iteration that leaves identical models on every rank.
+    from poccala_b200.engine import HostReduceHook, frame_moments_host
+
     host_x = torch.empty((frames, DIM), dtype=torch.float32).pin_memory()
     host_x.copy_(x.cpu())
     hp = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init0] + [tm0.copy()]
+    shift_h, isc_h = frame_moments_host(eng, host_x.numpy(), group=group)
+    hook = HostReduceHook(eng, N_UNITS, N_UNITS * 3 * MIX, group) if group is not None else None
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         p = [a.copy() for a in hp]
-        em_iteration_host(eng, corpus, host_x.numpy(), *p, c_covariance=1e-6)
+        em_iteration_host(eng, corpus, host_x.numpy(), *p, c_covariance=1e-6, shift=shift_h, inv_scale=isc_h)
     sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         p = [a.copy() for a in hp]
-        em_iteration_host(eng, corpus, host_x.numpy(), *p, c_covariance=1e-6)
+        em_iteration_host(eng, corpus, host_x.numpy(), *p, c_covariance=1e-6, shift=shift_h, inv_scale=isc_h)
     sync_all()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if group is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX, group=group)
     e2e_val = world * frames * e2e_steps / float(e2e_s.item())
+    if hook is not None:
+        if hook.error is not None:
+            raise hook.error
+        hook.remove()
     G = N_UNITS * 3 * MIX
-    h2d = frames * DIM * 4 + (2 * G * DIM + G + N_UNITS * 25) * 8
+    h2d = frames * DIM * 4 + (2 * G * DIM + G + N_UNITS * 25 + 2 * DIM) * 8
     d2h = (2 * G * DIM + G + N_UNITS * 25) * 8 + 8
+    # the plain pinned copy of the same frames, for scale (the e2e step is transfer-bound)
+    dst = torch.empty((frames, DIM), dtype=torch.float32, device=dev)
+    dst.copy_(host_x, non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        dst.copy_(host_x, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * frames * DIM * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del dst
 
     if rank != 0:
         if group is not None:
@@ -349,7 +386,8 @@ def run_gpu(args):
                    "wall_s_timed_region": wall, "parallelism": "dp%d" % world},
         "clocks": clocks.summary(w0, w0 + wall),
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "api": "pc_em_iteration_host"},
+                "steps": e2e_steps, "api": "pc_em_iteration_host", "pinned_h2d_gbs": h2d_gbs,
+                "collectives_inside": world > 1},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "viterbi": vit,

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 1
+#define PC_ABI_VERSION 2
 
 #define PC_OK 0
 #define PC_ERR_INVALID (-1)     /* bad argument (shape, NULL pointer, dimension mismatch) */
@@ -66,7 +66,12 @@ int pc_destroy(pc_handle h);
 /* Options: "tensor_core" 0 = CUDA-core kernels, 1 = tcgen05/TMA kernels (default when the shape is
  * covered; the tests cross-check both on the same inputs); "host_chunks" caps the transfer pipeline
  * depth of pc_em_iteration_host (0 = 8); "debug_flags" is a tuning aid for the tcgen05 kernels (skip
- * stages, record block 0's phase clocks); read-only: "launches" (kernels launched), "sm_count". */
+ * stages, record block 0's phase clocks); "k2_kernel" 1 (default) = one warp per utterance, posteriors
+ * normalised by the utterance likelihood; 0 = three warps per utterance with a per-frame normaliser (the
+ * tests cross-check both); read-only: "launches" (kernels launched), "sm_count", "clamped" (standardised
+ * feature values the frame preparation had to clamp to +-240 since the counter was last read: synchronises
+ * the device and clears the counter; anything but 0 means the frames were not standardised - see
+ * pc_frame_moments_host). */
 int pc_set_option(pc_handle h, const char *key, int64_t value);
 int64_t pc_get_option(pc_handle h, const char *key);
 
@@ -263,14 +268,38 @@ int pc_gather_rows(pc_handle h, const int32_t *dev_order, int64_t n_rows, int32_
                    const void *dev_src, void *dev_dst, void *stream);
 
 /* ---- host-buffer entry point (end-to-end) --------------------------------------------------
- * One full EM iteration the way AcousticModel.embedded_training runs it (AcousticModel.py:842-882)
+ * Standardisation constants of a corpus: per-dimension sum and sum of squares (fp64) of host frames
+ * [n_frames][dim] float, reduced on the device.  The caller forms shift = sum/n and inv_scale =
+ * 1/sqrt(sumsq/n - shift^2) - across ranks after adding up the three quantities - once per corpus
+ * (the expanded quadratic of the scoring contraction cancels when |mu| >> sigma). */
+int pc_frame_moments_host(pc_handle h, const float *host_frames, int64_t n_frames, int32_t dim,
+                          double *host_sum, double *host_sumsq, void *stream);
+
+/* Cross-rank reduction hook of pc_em_iteration_host (the reference merges accumulator files of all
+ * machines, LHMM.py:256-290, Clustering.py:314-367).  With a hook installed the entry point keeps its
+ * exchange buffers in caller-owned device memory - dev_tmax double [n_units][9], dev_flat double
+ * [n_gauss*PC_KA + n_units*9] (GMM statistics, then the transition sums) - and calls
+ *     fn(user, 0, stream)   after the local transition maxima are in dev_tmax  (all-reduce MAX)
+ *     fn(user, 1, stream)   after the local statistics are in dev_flat          (all-reduce SUM)
+ * on the host thread, between kernel launches; `stream` is the CUDA stream the collective must be
+ * queued on.  A non-zero return aborts the iteration (PC_ERR_CUDA).  fn = NULL removes the hook. */
+typedef int (*pc_reduce_hook)(void *user, int32_t op, void *stream);
+int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_tmax, double *dev_flat,
+                       int64_t flat_len);
+
+/* One full EM iteration the way AcousticModel.embedded_training runs it (AcousticModel.py:842-882)
  * with HOST inputs and outputs: frames [total_frames][dim] float (pinned or pageable), parameters
- * double, updated in place on return.  Copies host->device, runs K1,K2,K3,K6,M-step, copies the
- * new parameters and sum log-likelihood back, and synchronises the stream. */
+ * double, updated in place on return.  Copies host->device, runs K1,K2,K3,K6 (+ the reduce hook),
+ * the M-step, copies the new parameters and sum log-likelihood back, and synchronises the stream.
+ * host_shift / host_inv_scale double [dim]: the corpus' standardisation constants
+ * (pc_frame_moments_host); both NULL = computed from this call's frames (the scoring then waits
+ * for the whole copy instead of overlapping it).  Fails with PC_ERR_INVALID when a standardised
+ * feature exceeds +-240 (wrong constants). */
 int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int32_t dim,
                          int32_t n_units, int32_t mix, double *host_mean, double *host_var,
-                         double *host_alpha, double *host_transmat, double c_covariance,
-                         int32_t fix_code, double *host_sum_logp, void *stream);
+                         double *host_alpha, double *host_transmat, const double *host_shift,
+                         const double *host_inv_scale, double c_covariance, int32_t fix_code,
+                         double *host_sum_logp, void *stream);
 
 #ifdef __cplusplus
 }

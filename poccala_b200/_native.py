@@ -86,9 +86,14 @@ _SIGS = {
     "pc_group_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "pc_group_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4),
     "pc_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
+    "pc_frame_moments_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
+    "pc_set_reduce_hook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "pc_em_iteration_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
-                             + [C.c_void_p] * 4 + [C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
+                             + [C.c_void_p] * 6 + [C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
 }
+
+# int hook(void *user, int32_t op, void *stream)  (pc_reduce_hook)
+REDUCE_HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_void_p)
 
 EXPORTS = tuple(_SIGS)
 
@@ -106,7 +111,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.pc_abi_version() != 1:
+        if l.pc_abi_version() != 2:
             raise RuntimeError("poccala_b200: ABI version mismatch")
         _lib = l
     return _lib

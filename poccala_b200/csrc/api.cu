@@ -49,6 +49,13 @@ int pc_create(int device, pc_handle *out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     h->use_tc = 1;
+    h->k2_kernel = 1;
+    if (cudaMalloc((void **)&h->dev_counters, PC_CNT_N * sizeof(int)) != cudaSuccess ||
+        cudaMemset(h->dev_counters, 0, PC_CNT_N * sizeof(int)) != cudaSuccess) {
+        pc_set_error("pc_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return PC_ERR_CUDA;
+    }
     *out = h;
     return PC_OK;
 }
@@ -57,6 +64,7 @@ int pc_destroy(pc_handle h) {
     if (!h) return PC_OK;
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
+    if (h->dev_counters) cudaFree(h->dev_counters);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->copy_stream) {
         cudaStreamDestroy(h->copy_stream);
@@ -75,6 +83,7 @@ int pc_set_option(pc_handle h, const char *key, int64_t value) {
     if (!strcmp(key, "debug_flags")) { h->debug_flags = (int)value; return PC_OK; }
     if (!strcmp(key, "host_chunks")) { h->host_chunks = (int)value; return PC_OK; }
     if (!strcmp(key, "launches")) { h->launches = value; return PC_OK; }
+    if (!strcmp(key, "k2_kernel")) { h->k2_kernel = (int)value; return PC_OK; }
     pc_set_error("pc_set_option: unknown key '%s'", key);
     return PC_ERR_INVALID;
 }
@@ -86,6 +95,16 @@ int64_t pc_get_option(pc_handle h, const char *key) {
     if (!strcmp(key, "host_chunks")) return h->host_chunks;
     if (!strcmp(key, "launches")) return h->launches;
     if (!strcmp(key, "sm_count")) return h->sm_count;
+    if (!strcmp(key, "k2_kernel")) return h->k2_kernel;
+    if (!strcmp(key, "clamped")) {
+        const int idx = PC_CNT_CLAMPED;
+        int n = 0;
+        if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+            cudaMemcpy(&n, h->dev_counters + idx, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return -1;
+        if (idx == PC_CNT_CLAMPED && n != 0) cudaMemset(h->dev_counters + idx, 0, sizeof(int));
+        return n;
+    }
     return -1;
 }
 
@@ -661,56 +680,155 @@ __global__ void sum_double_kernel(const double *p, int n, double *out) {
     if (threadIdx.x == 0) *out = s;
 }
 
+// per-dimension sum / sum of squares of float frames [n][dim]: a block strides over rows, thread =
+// (row slot, dimension); fp64 partial sums, one atomicAdd per block and dimension
+__global__ void __launch_bounds__(256)
+frame_moments_kernel(const float *__restrict__ x, int64_t n, int dim, double *__restrict__ mom) {
+    __shared__ double sh[2][256];
+    const int d = threadIdx.x % 64, slot = threadIdx.x / 64;  // 4 row slots x 64 dimension lanes
+    double s = 0.0, q = 0.0;
+    if (d < dim)
+        for (int64_t r = (int64_t)blockIdx.x * 4 + slot; r < n; r += (int64_t)gridDim.x * 4) {
+            const double v = (double)x[r * dim + d];
+            s += v;
+            q += v * v;
+        }
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = q;
+    __syncthreads();
+    if (slot == 0 && d < dim) {
+        for (int k = 1; k < 4; ++k) { s += sh[0][k * 64 + d]; q += sh[1][k * 64 + d]; }
+        atomicAdd(mom + d, s);
+        atomicAdd(mom + PC_XS + d, q);
+    }
+}
+
+// shift = mean, inv_scale = 1 / std from the moments (one thread per dimension)
+__global__ void moments_to_affine_kernel(const double *__restrict__ mom, int64_t n, int dim, double *shift,
+                                         double *inv_scale) {
+    const int d = threadIdx.x;
+    if (d >= dim) return;
+    const double mu = mom[d] / (double)n;
+    double var = mom[PC_XS + d] / (double)n - mu * mu;
+    if (!(var > 0.0)) var = 0.0;
+    double sd = sqrt(var);
+    if (sd < 1e-12) sd = 1e-12;
+    shift[d] = mu;
+    inv_scale[d] = 1.0 / sd;
+}
+
+static int ensure_streams(pc_handle h) {
+    if (h->copy_stream) return PC_OK;
+    PC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    PC_CUDA_TRY(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
+    PC_CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+    PC_CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
+    for (int k = 0; k < PC_MAX_CHUNKS; ++k)
+        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
+    return PC_OK;
+}
+
+int pc_frame_moments_host(pc_handle h, const float *host_frames, int64_t n_frames, int32_t dim,
+                          double *host_sum, double *host_sumsq, void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(n_frames >= 0 && host_sum && host_sumsq && (n_frames == 0 || host_frames),
+               "pc_frame_moments_host: bad arguments");
+    int rc = check_dim_mix("pc_frame_moments_host", dim, 1);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // frames go through the workspace in slabs of <= 64 MiB, two in flight
+    const int64_t slab_rows = std::max<int64_t>(1, (64ll << 20) / ((int64_t)dim * 4));
+    const size_t slab_bytes = (size_t)slab_rows * dim * 4;
+    if ((rc = ensure_ws(h, 2 * slab_bytes + 4096))) return rc;
+    double *mom = (double *)((char *)h->ws + 2 * slab_bytes);
+    PC_CUDA_TRY(cudaMemsetAsync(mom, 0, 2 * PC_XS * 8, st));
+    for (int64_t r0 = 0, k = 0; r0 < n_frames; r0 += slab_rows, ++k) {
+        const int64_t rows = std::min(slab_rows, n_frames - r0);
+        float *dst = (float *)((char *)h->ws + (k & 1) * slab_bytes);
+        PC_CUDA_TRY(cudaMemcpyAsync(dst, host_frames + (size_t)r0 * dim, (size_t)rows * dim * 4,
+                                    cudaMemcpyHostToDevice, st));
+        const int blocks = (int)std::min<int64_t>((rows + 3) / 4, (int64_t)h->sm_count * 8);
+        frame_moments_kernel<<<blocks, 256, 0, st>>>(dst, rows, dim, mom);
+        PC_LAUNCH_CHECK();
+        h->launches++;
+    }
+    double out[2 * PC_XS];
+    PC_CUDA_TRY(cudaMemcpyAsync(out, mom, sizeof(out), cudaMemcpyDeviceToHost, st));
+    PC_CUDA_TRY(cudaStreamSynchronize(st));
+    for (int d = 0; d < dim; ++d) {
+        host_sum[d] = out[d];
+        host_sumsq[d] = out[PC_XS + d];
+    }
+    return PC_OK;
+}
+
+int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_tmax, double *dev_flat,
+                       int64_t flat_len) {
+    PC_REQUIRE(h, "pc_set_reduce_hook: NULL handle");
+    PC_REQUIRE(fn == nullptr || (dev_tmax && dev_flat && flat_len > 0),
+               "pc_set_reduce_hook: a hook needs its exchange buffers");
+    h->hook = fn;
+    h->hook_user = user;
+    h->hook_tmax = fn ? dev_tmax : nullptr;
+    h->hook_flat = fn ? dev_flat : nullptr;
+    h->hook_flat_len = fn ? flat_len : 0;
+    return PC_OK;
+}
+
 int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int32_t dim,
                          int32_t n_units, int32_t mix, double *host_mean, double *host_var,
-                         double *host_alpha, double *host_transmat, double c_cov, int32_t fix_code,
+                         double *host_alpha, double *host_transmat, const double *host_shift,
+                         const double *host_inv_scale, double c_cov, int32_t fix_code,
                          double *host_sum_logp, void *stream) {
     PC_ENTER(h);
     PC_REQUIRE(c && host_frames && host_mean && host_var && host_alpha && host_transmat,
                "pc_em_iteration_host: NULL argument");
     PC_REQUIRE(n_units == c->v.n_units, "pc_em_iteration_host: n_units %d != corpus %d", n_units,
                c->v.n_units);
+    PC_REQUIRE((host_shift != nullptr) == (host_inv_scale != nullptr),
+               "pc_em_iteration_host: host_shift / host_inv_scale go together");
     int rc = check_dim_mix("pc_em_iteration_host", dim, mix);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t F = c->total_frames;
     const int64_t G = (int64_t)n_units * PC_EMIT * mix;
+    const int64_t flat_len = G * PC_KA + (int64_t)n_units * PC_TRANS_SLOTS;
+    PC_REQUIRE(!h->hook || h->hook_flat_len == flat_len,
+               "pc_em_iteration_host: the reduce hook's flat buffer holds %lld doubles, this model needs %lld",
+               (long long)h->hook_flat_len, (long long)flat_len);
     // workspace carve-up (256-byte aligned)
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_raw = carve((size_t)F * dim * 4), o_X = carve((size_t)pc_corpus_frames_bytes(c));
     size_t o_b = carve((size_t)c->emis_floats * 4), o_lg = carve((size_t)c->emis_floats * 4);
-    size_t o_W = carve((size_t)pc_gmm_bytes(G)), o_acc = carve((size_t)G * PC_KA * 8);
+    size_t o_W = carve((size_t)pc_gmm_bytes(G)), o_flat = carve((size_t)flat_len * 8);
     size_t o_mean = carve((size_t)G * dim * 8), o_var = carve((size_t)G * dim * 8);
     size_t o_alpha = carve((size_t)G * 8), o_tm = carve((size_t)n_units * 25 * 8);
     size_t o_ls = carve((size_t)n_units * 5 * 8), o_ln = carve((size_t)n_units * 5 * 8);
     size_t o_logp = carve((size_t)c->v.n_utt * 8), o_it = carve((size_t)c->v.n_utt * 4);
     size_t o_pt = carve((size_t)c->v.n_pairs * PC_TRANS_SLOTS * 4);
     size_t o_tmax = carve((size_t)n_units * PC_TRANS_SLOTS * 8);
-    size_t o_tsum = carve((size_t)n_units * PC_TRANS_SLOTS * 8), o_sum = carve(8);
+    size_t o_sum = carve(8), o_aff = carve(2 * PC_XS * 8), o_mom = carve(2 * PC_XS * 8);
     rc = ensure_ws(h, off);
     if (rc) return rc;
     char *ws = (char *)h->ws;
     float *raw = (float *)(ws + o_raw), *X = (float *)(ws + o_X), *b = (float *)(ws + o_b);
     float *lg = (float *)(ws + o_lg), *W = (float *)(ws + o_W), *pt = (float *)(ws + o_pt);
-    double *acc = (double *)(ws + o_acc), *mean = (double *)(ws + o_mean);
+    double *flat = h->hook ? h->hook_flat : (double *)(ws + o_flat);
+    double *acc = flat, *tsum = flat + G * PC_KA;
+    double *tmax = h->hook ? h->hook_tmax : (double *)(ws + o_tmax);
+    double *mean = (double *)(ws + o_mean);
     double *var = (double *)(ws + o_var), *alpha = (double *)(ws + o_alpha);
     double *tm = (double *)(ws + o_tm), *ls = (double *)(ws + o_ls), *ln = (double *)(ws + o_ln);
-    double *logp = (double *)(ws + o_logp), *tmax = (double *)(ws + o_tmax);
-    double *tsum = (double *)(ws + o_tsum), *sum = (double *)(ws + o_sum);
+    double *logp = (double *)(ws + o_logp);
+    double *sum = (double *)(ws + o_sum);
+    double *shift = (double *)(ws + o_aff), *inv_scale = shift + PC_XS, *mom = (double *)(ws + o_mom);
     int32_t *iters = (int32_t *)(ws + o_it);
 
     // Frames travel on their own stream in <= PC_MAX_CHUNKS runs of utterances; the compute stream
     // prepares and scores run k as soon as it has landed, under the copy of run k+1 (pinned host
     // memory makes the copies asynchronous; pageable memory still works, without the overlap).
-    if (!h->copy_stream) {
-        PC_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->start_ev, cudaEventDisableTiming));
-        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
-        PC_CUDA_TRY(cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming));
-        for (int k = 0; k < PC_MAX_CHUNKS; ++k)
-            PC_CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_ev[k], cudaEventDisableTiming));
-    }
+    if ((rc = ensure_streams(h))) return rc;
     PC_CUDA_TRY(cudaEventRecord(h->start_ev, st));  // whatever the caller queued before us
     PC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->start_ev, 0));
     // option "host_chunks" merges neighbouring runs (1 = one copy, no overlap)
@@ -733,12 +851,33 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
         PC_LAUNCH_CHECK();
         h->launches += 1;
     }
-    if ((rc = launch_pack_gmm(h, mean, var, alpha, nullptr, nullptr, (int)G, dim, mix, W, st))) return rc;
+    // Standardisation: the caller's corpus constants, or - without them - the
+    // moments of this call's frames, which every chunk has to land for
+    if (host_shift) {
+        PC_CUDA_TRY(cudaMemcpyAsync(shift, host_shift, (size_t)dim * 8, cudaMemcpyHostToDevice, st));
+        PC_CUDA_TRY(cudaMemcpyAsync(inv_scale, host_inv_scale, (size_t)dim * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        PC_CUDA_TRY(cudaMemsetAsync(mom, 0, 2 * PC_XS * 8, st));
+        for (int k = 0; k < c->n_chunks; k += kstep) {
+            const int k1 = k + kstep < c->n_chunks ? k + kstep : c->n_chunks;
+            const int64_t f_lo = c->chunk_frame[k], rows = c->chunk_frame[k1] - f_lo;
+            PC_CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_ev[k], 0));
+            if (rows <= 0) continue;
+            const int blocks = (int)std::min<int64_t>((rows + 3) / 4, (int64_t)h->sm_count * 8);
+            frame_moments_kernel<<<blocks, 256, 0, st>>>(raw + (size_t)f_lo * dim, rows, dim, mom);
+            PC_LAUNCH_CHECK();
+            h->launches++;
+        }
+        moments_to_affine_kernel<<<1, 64, 0, st>>>(mom, F, dim, shift, inv_scale);
+        PC_LAUNCH_CHECK();
+        h->launches++;
+    }
+    if ((rc = launch_pack_gmm(h, mean, var, alpha, shift, inv_scale, (int)G, dim, mix, W, st))) return rc;
     const bool tc_score = h->use_tc && score_tc_supported(mix);
     for (int k = 0; k < c->n_chunks; k += kstep) {
         const int k1 = k + kstep < c->n_chunks ? k + kstep : c->n_chunks;
         PC_CUDA_TRY(cudaStreamWaitEvent(st, h->chunk_ev[k], 0));
-        if ((rc = launch_prepare_frames(h, c->v, raw, 0, dim, nullptr, nullptr, X, c->chunk_xtile[k],
+        if ((rc = launch_prepare_frames(h, c->v, raw, 0, dim, shift, inv_scale, X, c->chunk_xtile[k],
                                         c->chunk_xtile[k1], st))) return rc;
         if (tc_score && (rc = launch_score_tc(h, c->v, X, W, mix, b, c->chunk_sitem[k], c->chunk_sitem[k1], st)))
             return rc;
@@ -747,10 +886,14 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     if ((rc = launch_forward_backward(h, c->v, b, ls, ln, lg, c->v.scratch0, logp, iters, pt, st))) return rc;
     c->flags_lgam = nullptr;  // consumed below
     // the transition reductions need K2's outputs only: they run on the (by now idle) copy stream,
-    // beside the accumulation kernel
+    // beside the accumulation kernel - and so does the MAX collective of the reduce hook
     PC_CUDA_TRY(cudaEventRecord(h->fork_ev, st));
     PC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->fork_ev, 0));
     if ((rc = launch_transitions_max(h, c->v, logp, pt, tmax, h->copy_stream))) return rc;
+    if (h->hook && h->hook(h->hook_user, 0, (void *)h->copy_stream) != 0) {
+        pc_set_error("pc_em_iteration_host: the reduce hook failed (MAX)");
+        return PC_ERR_CUDA;
+    }
     if ((rc = launch_transitions_sum(h, c->v, logp, pt, tmax, tsum, h->copy_stream))) return rc;
     PC_CUDA_TRY(cudaEventRecord(h->join_ev, h->copy_stream));
     if (!(fix_code & 2))
@@ -762,7 +905,11 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
         }
     }
     PC_CUDA_TRY(cudaStreamWaitEvent(st, h->join_ev, 0));
-    if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, nullptr, nullptr, c_cov,
+    if (h->hook && h->hook(h->hook_user, 1, (void *)st) != 0) {
+        pc_set_error("pc_em_iteration_host: the reduce hook failed (SUM)");
+        return PC_ERR_CUDA;
+    }
+    if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, shift, inv_scale, c_cov,
                                    fix_code, mean, var, alpha, tm, st))) return rc;
     sum_double_kernel<<<1, 32, 0, st>>>(logp, c->v.n_utt, sum);
     PC_LAUNCH_CHECK();
@@ -772,9 +919,17 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     PC_CUDA_TRY(cudaMemcpyAsync(host_alpha, alpha, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
     PC_CUDA_TRY(cudaMemcpyAsync(host_transmat, tm, (size_t)n_units * 25 * 8, cudaMemcpyDeviceToHost, st));
     double s = 0.0;
+    int clamped = 0;
     PC_CUDA_TRY(cudaMemcpyAsync(&s, sum, 8, cudaMemcpyDeviceToHost, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(&clamped, h->dev_counters + PC_CNT_CLAMPED, sizeof(int), cudaMemcpyDeviceToHost, st));
     PC_CUDA_TRY(cudaStreamSynchronize(st));
     if (host_sum_logp) *host_sum_logp = s;
+    if (clamped) {
+        cudaMemset(h->dev_counters + PC_CNT_CLAMPED, 0, sizeof(int));
+        pc_set_error("pc_em_iteration_host: %d standardised feature values exceeded +-240 and were clamped: "
+                     "host_shift / host_inv_scale do not describe these frames (pc_frame_moments_host)", clamped);
+        return PC_ERR_INVALID;
+    }
     return PC_OK;
 }
 

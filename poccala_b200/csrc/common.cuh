@@ -144,7 +144,17 @@ struct pc_handle_s {
     cudaEvent_t chunk_ev[PC_MAX_CHUNKS];
     cudaEvent_t start_ev;
     cudaEvent_t fork_ev, join_ev;             // transition reductions beside the accumulation kernel
+    // device counters: [PC_CNT_CLAMPED] standardised features clamped by the frame preparation
+    int *dev_counters;
+    int k2_kernel;       // option "k2_kernel": 1 = one warp per utterance (fwdbwd_warp.cu), 0 = three warps (fwdbwd.cu)
+    // cross-rank reduction hook of the host-buffer entry point (pc_set_reduce_hook)
+    pc_reduce_hook hook;
+    void *hook_user;
+    double *hook_tmax, *hook_flat;
+    int64_t hook_flat_len;
 };
+#define PC_CNT_CLAMPED 0
+#define PC_CNT_N 8
 
 struct pc_corpus_s {
     pc_handle h;
@@ -193,6 +203,10 @@ int launch_forward_backward(pc_handle h, const CorpusView &v, const float *b,
                             const double *log_self, const double *log_next, float *lgam,
                             float *scratch0, double *utt_logp, int32_t *utt_iters,
                             float *pair_trans, cudaStream_t st);
+int launch_forward_backward_warp(pc_handle h, const CorpusView &v, const float *b,
+                                 const double *log_self, const double *log_next, float *lgam,
+                                 float *scratch0, double *utt_logp, int32_t *utt_iters,
+                                 float *pair_trans, cudaStream_t st);
 int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_logp,
                            const float *pair_trans, double *tmax, cudaStream_t st);
 int launch_transitions_sum(pc_handle h, const CorpusView &v, const double *utt_logp,

@@ -639,6 +639,9 @@ int launch_forward_backward(pc_handle h, const CorpusView &v, const float *b,
                             float *scratch0, double *utt_logp, int32_t *utt_iters,
                             float *pair_trans, cudaStream_t st) {
     if (v.n_utt == 0) return PC_OK;
+    if (h->k2_kernel)  // one warp per utterance (fwdbwd_warp.cu); this file's kernel stays as the cross-check
+        return launch_forward_backward_warp(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters,
+                                            pair_trans, st);
     const int states = PC_EMIT * v.max_labels + 1;
     if (states <= 32) return launch_fb<1>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
     if (states <= 64) return launch_fb<2>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);

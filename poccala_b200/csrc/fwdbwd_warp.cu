@@ -1,0 +1,433 @@
+// K2, one warp per utterance: log-space forward-backward over the banded sentence HMM with the
+// posteriors and the expected transition counts formed in the forward pass itself.
+//
+// Same mathematics as fwdbwd.cu (LHMM.baulm_welch on the HMM of AcousticModel.embedded:
+// LHMM.py:335-366 forward / backward, :426-471 ksai / gamma / pi, :412-422 likelihood, :526-544 pi
+// iteration, :486-500 log gamma), restated around two identities that remove the
+// per-frame reductions of the three-warp kernel (139 instructions per frame there, ~55 here):
+//   * sum_j alpha_t(j) beta_t(j) = P(O) for EVERY t, so log gamma_t(j) = log alpha_t(j) +
+//     log beta_t(j) - log P(O): the normaliser is the utterance likelihood the pi iteration
+//     produced after the backward pass, not a log-sum-exp over the states of each frame
+//     (LHMM.py:486-500 computes that sum numerically; it equals log P(O) to 1e-12 in fp64);
+//   * with nb_t(j) = log b_t(j) + log beta_t(j) (one row per frame, written by the backward pass)
+//         log gamma_t(j)    = [stay_t(j) (+) move_t(j)] + nb_t(j) - log P
+//         log xi_t-1(j, j)  =  stay_t(j) + nb_t(j) - log P,   stay_t(j) = log alpha_t-1(j)   + log a_jj
+//         log xi_t-1(j-1,j) =  move_t(j) + nb_t(j) - log P,   move_t(j) = log alpha_t-1(j-1) + log a_j-1,j
+//     i.e. the forward recurrence's own two terms, one add each (LHMM.py:431-445).
+// The recurrences stay in the log domain: the reference's transition accumulators are weighted by
+// the utterance likelihood (Q6), so expected counts of e^-300 can decide a unit's transition row
+// and a scaled linear-domain recurrence would flush them.
+//
+// Arithmetic: fp32 log2 domain.  Every frame's emissions are shifted by g_t = max_j b_t(j) and every
+// FW_CH frames the state vector is renormalised exactly (one CREDUX on the chain); the shifts are
+// carried in fp64 per frame (backward: stored beside nb; forward: a running sum), so the scale
+// constant of frame t, (forward shifts to t-1) + (backward shifts from t) - log2 P, is an fp64
+// difference of numbers of size 1e4 rounded to fp32 once.  Lane l owns states [l*SPL, (l+1)*SPL);
+// emissions are time-major, a warp reads / writes one coalesced row per frame.  Scratch: nb rows in
+// the corpus' beta scratch (same layout as b), one float4 per frame {shift (fp64), g_t*log2e, nb of
+// the entry state}.  K3's activity flags are set from the log gamma rows while they are at hand.
+#include <type_traits>
+
+#include "common.cuh"
+
+#define FW_CH 8   // frames per chunk: prefetch depth and renormalisation period
+#define FW_WPB 2  // warps (utterances) per block
+
+__device__ long long g_fw_dbg[16];
+
+namespace {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float redux_max(float v) {
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
+}
+// log2(2^a + 2^b) with -inf handling
+__device__ __forceinline__ float logadd2(float a, float b) {
+    const float m = fmaxf(a, b);
+    float d = fminf(a, b) - m;  // NaN only when a == b == -inf
+    d = (m == PC_NEG_INF) ? 0.f : d;
+    return m + lg2f(1.f + ex2f(d));
+}
+// sum * 2^mx += 2^x, rescaling only when x overtakes the reference by a wide margin
+__device__ __forceinline__ void acc_lse2(float &mx, float &sum, float x) {
+    if (x > mx + 24.f) {
+        sum *= ex2f(mx - x);
+        mx = x;
+    }
+    sum += ex2f(x - mx);
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(FW_WPB * 32)
+fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__restrict__ log_self,
+                   const double *__restrict__ log_next, float *__restrict__ lgam, float4 *__restrict__ fscr,
+                   double *__restrict__ utt_logp, int32_t *__restrict__ utt_iters,
+                   float *__restrict__ pair_trans) {
+    constexpr int CH = FW_CH;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * FW_WPB + (threadIdx.x >> 5);
+    if (idx >= v.n_utt) return;
+    const int u = v.fb_order[idx];
+    const int64_t f0 = v.frame_off[u];
+    const int T = (int)(v.frame_off[u + 1] - f0);
+    const int64_t p0 = v.pair_off[u];
+    const int L = (int)(v.pair_off[u + 1] - p0);
+    const int NE = PC_EMIT * L;  // states 0..NE are materialised; N = NE + 2
+    const int sp = pc_spad(L);
+    const float *bu = b + v.emis_off[u];
+    float *gu = lgam + v.emis_off[u];
+    float *nbu = v.scratch1 + v.emis_off[u];  // nb rows of the emitting states
+    float4 *fs = fscr + f0;                   // per frame: {shift lo, shift hi, g*log2e, nb of the entry state}
+    const bool trace = (blockIdx.x == 0 && threadIdx.x == 0);
+    if (trace) g_fw_dbg[0] = clock64();
+
+    float ls[SPL], ln[SPL];
+    int kind[SPL], col[SPL];  // kind: 0 entry, 1 emitting, 2 inactive
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        const int s = lane * SPL + q;
+        col[q] = 0;
+        if (s == 0) {
+            const int unit = v.labels[p0];
+            kind[q] = 0;
+            ls[q] = (float)log_self[unit * PC_STATES] * kLog2e;
+            ln[q] = (float)log_next[unit * PC_STATES] * kLog2e;
+        } else if (s <= NE) {
+            const int p = (s - 1) / PC_EMIT, r = (s - 1) - p * PC_EMIT;
+            const int unit = v.labels[p0 + p];
+            kind[q] = 1;
+            col[q] = s - 1;
+            ls[q] = (float)log_self[unit * PC_STATES + 1 + r] * kLog2e;
+            // the last emitting state's successor is the exit state (emission log 0): no mass
+            ln[q] = (s == NE) ? PC_NEG_INF : (float)log_next[unit * PC_STATES + 1 + r] * kLog2e;
+        } else {
+            kind[q] = 2;
+            ls[q] = PC_NEG_INF;
+            ln[q] = PC_NEG_INF;
+        }
+    }
+    auto load_row = [&](int t, float (&e)[SPL]) {
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) e[q] = (kind[q] == 1) ? __ldg(bu + (size_t)t * sp + col[q]) : PC_NEG_INF;
+    };
+    auto frame_max = [&](const float (&e)[SPL]) {
+        float m = e[0];
+#pragma unroll
+        for (int q = 1; q < SPL; ++q) m = fmaxf(m, e[q]);
+        m = redux_max(m);
+        return (m == PC_NEG_INF) ? 0.f : m;
+    };
+    // shifted log2 emissions: b*log2e - g2; the entry state emits log 1 = 0
+    auto shift_row = [&](const float (&e)[SPL], float g2, float (&es)[SPL]) {
+#pragma unroll
+        for (int q = 0; q < SPL; ++q)
+            es[q] = (kind[q] == 1) ? fmaf(e[q], kLog2e, -g2) : (kind[q] == 0 ? -g2 : PC_NEG_INF);
+    };
+
+    // ------------------------------------------------------------------ backward (LHMM.py:353-366)
+    float bh[SPL];
+    double Cb = 0.0;  // log2 beta_t = bh + Cb
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) bh[q] = (kind[q] != 2) ? 0.f : PC_NEG_INF;
+    {
+        // step tau (= T-1 .. 1) consumes emission row tau, stores nb_tau and produces beta_hat_{tau-1}
+        float e_nxt[CH][SPL];
+        int tau_hi = T - 1;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) load_row(max(tau_hi - k, 0), e_nxt[k]);
+        auto chunk = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            float es[CH][SPL], g2[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {  // off the dependency chain
+                g2[k] = frame_max(e_nxt[k]) * kLog2e;
+                shift_row(e_nxt[k], g2[k], es[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < CH; ++k) load_row(max(tau_hi - CH - k, 0), e_nxt[k]);  // prefetch
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int tau = tau_hi - k;
+                if (FULL || tau >= 1) {
+                    float nb[SPL], raw[SPL];
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) {
+                        nb[q] = bh[q] + es[k][q];
+                        if (kind[q] == 1) nbu[(size_t)tau * sp + col[q]] = nb[q];
+                    }
+                    if (lane == 0) {  // lane 0 holds the entry state in slot 0
+                        const double db = Cb + (double)g2[k];  // log2(b_tau beta_tau) = nb_tau + db
+                        fs[tau] = make_float4(__int_as_float(__double2loint(db)), __int_as_float(__double2hiint(db)),
+                                              g2[k], nb[0]);
+                    }
+                    float up = __shfl_down_sync(0xffffffffu, nb[0], 1);
+                    if (lane == 31) up = PC_NEG_INF;
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) {
+                        const float nxt = (q + 1 < SPL) ? nb[(q + 1) % SPL] : up;
+                        raw[q] = logadd2(ls[q] + nb[q], ln[q] + nxt);
+                    }
+                    float r = 0.f;
+                    if (FULL && k == CH - 1) {  // exact renormalisation once per full chunk
+                        float m = raw[0];
+#pragma unroll
+                        for (int q = 1; q < SPL; ++q) m = fmaxf(m, raw[q]);
+                        m = redux_max(m);
+                        r = (m == PC_NEG_INF) ? 0.f : m;
+                    }
+                    Cb += (double)g2[k] + (double)r;
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) bh[q] = raw[q] - r;
+                }
+            }
+            tau_hi -= CH;
+        };
+        while (tau_hi >= CH) chunk(std::true_type{});
+        if (tau_hi >= 1) chunk(std::false_type{});
+    }
+    if (trace) g_fw_dbg[1] = clock64();
+    float e0[SPL];
+    load_row(0, e0);
+    const float g20 = frame_max(e0) * kLog2e;
+
+    // ----------------------------------------- pi iteration (LHMM.py:447-452,526-544; A.3)
+    // natural-log fp64 on w = B[:,0] + beta_0, relative to Cb (added back for log P)
+    double w[SPL], lp[SPL], lp_used[SPL];
+    const double log_uniform = log(1.0 / (double)(NE + 2));
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        const double em = (kind[q] == 1) ? (double)e0[q] : (kind[q] == 0 ? 0.0 : (double)PC_NEG_INF);
+        w[q] = (double)bh[q] * (double)kLn2 + em;
+        lp[q] = (kind[q] == 2) ? (double)PC_NEG_INF : log_uniform;
+        lp_used[q] = lp[q];
+    }
+    int iters = 0;
+    double q_prev = (double)PC_NEG_INF, qn = (double)PC_NEG_INF;
+    for (int guard = 0; guard < 100000; ++guard) {
+        double m = (double)PC_NEG_INF;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) m = fmax(m, lp[q] + w[q]);
+        m = warp_max_d(m);
+        qn = m;
+        if (m != (double)PC_NEG_INF) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) s += exp(lp[q] + w[q] - m);
+            qn = m + log(warp_sum_d(s));
+        }
+        ++iters;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) lp_used[q] = lp[q];
+        if (!((qn - q_prev) > 0.64)) break;
+        q_prev = qn;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) lp[q] = log(exp(lp[q] + w[q] - qn));  // linear-space pi (A.3)
+    }
+    // log gamma_0 = log pi + w - q (LHMM.py:486-500 at t = 0); log P(O) = q + backward shifts
+    float tmx[SPL];  // running maximum of log gamma per state over the current 128-frame tile (K3's flags)
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        const double lg0 = lp_used[q] + w[q] - qn;  // NaN when the utterance has no path at all
+        tmx[q] = (kind[q] == 1) ? (float)lg0 : PC_NEG_INF;
+        if (kind[q] == 1) gu[col[q]] = (float)lg0;
+    }
+    if (lane == 0) {
+        utt_logp[u] = qn + Cb * 0.6931471805599453;
+        utt_iters[u] = iters;
+    }
+    if (trace) g_fw_dbg[2] = clock64();
+
+    // K3's activity flags: every (tile, position) flag is written exactly once per run, 0 or 1, by the
+    // lane that holds the position's first state; the maxima of the position's other two states arrive by shuffle
+    int32_t *flag0[SPL];  // -> flag of (tile 0, this state's position); the pair's tiles are consecutive
+#pragma unroll
+    for (int q = 0; q < SPL; ++q)
+        flag0[q] = v.tile_active + ((kind[q] == 1) ? v.pair_tile0[p0 + col[q] / PC_EMIT] : 0);
+    auto next_state = [&](const float (&x)[SPL], float (&y)[SPL]) {  // y[state s] = x[state s + 1]
+        const float up = __shfl_down_sync(0xffffffffu, x[0], 1);
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) y[q] = (q + 1 < SPL) ? x[(q + 1) % SPL] : up;
+    };
+    auto flag_tile = [&](int k_tile) {
+        float m1[SPL], m2[SPL];
+        next_state(tmx, m1);
+        next_state(m1, m2);
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            if (kind[q] == 1 && col[q] % PC_EMIT == 0)
+                flag0[q][k_tile] = fmaxf(fmaxf(tmx[q], m1[q]), m2[q]) > PC_ACTIVE_MIN_LGAM ? 1 : 0;
+            tmx[q] = PC_NEG_INF;
+        }
+    };
+    if (T == 1) flag_tile(0);
+    __syncwarp();  // lane 0's per-frame records are read by every lane below
+
+    // ------------------------------------------------------------------ forward (LHMM.py:335-351)
+    // + log gamma (LHMM.py:486-500) + expected transition counts (LHMM.py:431-445)
+    float ah[SPL];
+    double CaLP;  // (forward shifts up to the previous frame) - log2 P:  log2 alpha_t = ah + CaLP + log2 P
+    {
+        float m = PC_NEG_INF;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            const float es0 = (kind[q] == 1) ? fmaf(e0[q], kLog2e, -g20) : (kind[q] == 0 ? -g20 : PC_NEG_INF);
+            ah[q] = (kind[q] == 2) ? PC_NEG_INF : (float)(lp_used[q] * 1.4426950408889634) + es0;
+            m = fmaxf(m, ah[q]);
+        }
+        m = redux_max(m);
+        if (m == PC_NEG_INF) m = 0.f;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) ah[q] -= m;
+        CaLP = (double)g20 + (double)m - (qn * 1.4426950408889634 + Cb);
+    }
+    float ms[SPL], cs[SPL], mn[SPL], cn[SPL];  // running log-sum-exp of the stay / move counts
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) {
+        ms[q] = mn[q] = -1e30f;  // finite floor: 2^(x - floor) = 0 for every real x below it
+        cs[q] = cn[q] = 0.f;
+    }
+    {
+        float e_nxt[CH][SPL], nb_nxt[CH][SPL];
+        float4 f_nxt[CH];
+        int tau_lo = 1;
+        auto load_fwd = [&](int t0) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int t = min(t0 + k, T - 1);
+                load_row(t, e_nxt[k]);
+                f_nxt[k] = __ldcg(fs + t);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    nb_nxt[k][q] = (kind[q] == 1) ? __ldcg(nbu + (size_t)t * sp + col[q])
+                                                  : (kind[q] == 0 ? f_nxt[k].w : PC_NEG_INF);
+            }
+        };
+        load_fwd(tau_lo);
+        auto chunk = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            float es[CH][SPL], nbc[CH][SPL], g2[CH];
+            double db[CH];
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                g2[k] = f_nxt[k].z;
+                db[k] = __hiloint2double(__float_as_int(f_nxt[k].y), __float_as_int(f_nxt[k].x));
+                shift_row(e_nxt[k], g2[k], es[k]);
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) nbc[k][q] = nb_nxt[k][q];
+            }
+            load_fwd(tau_lo + CH);  // prefetch
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const int t = tau_lo + k;
+                if (FULL || t <= T - 1) {
+                    const float cx = (float)(CaLP + db[k]);  // scale constant of frame t
+                    float left = __shfl_up_sync(0xffffffffu, ah[SPL - 1] + ln[SPL - 1], 1);
+                    if (lane == 0) left = PC_NEG_INF;
+                    float raw[SPL];
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) {
+                        const float stay = ah[q] + ls[q];
+                        const float move = (q > 0) ? ah[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
+                        raw[q] = logadd2(stay, move);
+                        const float nc = nbc[k][q] + cx;
+                        acc_lse2(ms[q], cs[q], stay + nc);
+                        acc_lse2(mn[q], cn[q], move + nc);
+                        const float lg = (raw[q] + nc) * kLn2;
+                        if (kind[q] == 1) {
+                            gu[(size_t)t * sp + col[q]] = lg;
+                            tmx[q] = fmaxf(tmx[q], lg);
+                        }
+                    }
+                    float r = 0.f;
+                    if (FULL && k == CH - 1) {
+                        float m = raw[0] + es[k][0];
+#pragma unroll
+                        for (int q = 1; q < SPL; ++q) m = fmaxf(m, raw[q] + es[k][q]);
+                        m = redux_max(m);
+                        r = (m == PC_NEG_INF) ? 0.f : m;
+                    }
+                    CaLP += (double)g2[k] + (double)r;
+#pragma unroll
+                    for (int q = 0; q < SPL; ++q) ah[q] = raw[q] + es[k][q] - r;
+                    // a tile's last frame: t = 127 mod 128 sits at k = CH - 2 of its chunk (chunks start at t = 1 mod CH)
+                    if ((k == CH - 2 && (t & (PC_TILE_ROWS - 1)) == PC_TILE_ROWS - 1) || t == T - 1)
+                        flag_tile(t / PC_TILE_ROWS);
+                }
+            }
+            tau_lo += CH;
+        };
+        while (tau_lo + CH - 1 <= T - 1) chunk(std::true_type{});
+        if (tau_lo <= T - 1) chunk(std::false_type{});
+    }
+    // the move counts were collected at the destination state: state s's "next" count sits with state s + 1
+    {
+        float mn1[SPL], cn1[SPL];
+        next_state(mn, mn1);
+        next_state(cn, cn1);
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) {
+            if (kind[q] == 1) {
+                const int s = lane * SPL + q;
+                float *o = pair_trans + (size_t)(p0 + (s - 1) / PC_EMIT) * PC_TRANS_SLOTS + ((s - 1) % PC_EMIT) * 3;
+                const float ks = (cs[q] > 0.f) ? ms[q] + lg2f(cs[q]) : PC_NEG_INF;
+                const float kn = (s < NE && cn1[q] > 0.f) ? mn1[q] + lg2f(cn1[q]) : PC_NEG_INF;
+                o[0] = ks * kLn2;
+                o[1] = kn * kLn2;
+                o[2] = logadd2(ks, kn) * kLn2;  // occupancy over t < T-1 = self + next
+            }
+        }
+    }
+    if (trace) g_fw_dbg[3] = clock64();
+}
+
+template <int SPL>
+int launch_fw(pc_handle h, const CorpusView &v, const float *b, const double *log_self, const double *log_next,
+              float *lgam, float *scratch0, double *utt_logp, int32_t *utt_iters, float *pair_trans,
+              cudaStream_t st) {
+    const int blocks = (v.n_utt + FW_WPB - 1) / FW_WPB;
+    fwdbwd_warp_kernel<SPL><<<blocks, FW_WPB * 32, 0, st>>>(v, b, log_self, log_next, lgam,
+                                                            reinterpret_cast<float4 *>(scratch0), utt_logp, utt_iters,
+                                                            pair_trans);
+    PC_LAUNCH_CHECK();
+    h->launches++;
+    return PC_OK;
+}
+
+}  // namespace
+
+// block 0's phase clocks: [0] start, [1] backward done, [2] pi iteration done, [3] forward done
+extern "C" int pc_debug_read_fw(long long *host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_fw_dbg, sizeof(long long) * 16) == cudaSuccess ? 0 : -2;
+}
+
+int launch_forward_backward_warp(pc_handle h, const CorpusView &v, const float *b, const double *log_self,
+                                 const double *log_next, float *lgam, float *scratch0, double *utt_logp,
+                                 int32_t *utt_iters, float *pair_trans, cudaStream_t st) {
+    if (v.n_utt == 0) return PC_OK;
+    const int states = PC_EMIT * v.max_labels + 1;
+    if (states <= 32) return launch_fw<1>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+    if (states <= 64) return launch_fw<2>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+    if (states <= 128) return launch_fw<4>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+    if (states <= 256) return launch_fw<8>(h, v, b, log_self, log_next, lgam, scratch0, utt_logp, utt_iters, pair_trans, st);
+    pc_set_error("pc_forward_backward: %d labels per utterance exceeds the limit of 85", v.max_labels);
+    return PC_ERR_UNSUPPORTED;
+}

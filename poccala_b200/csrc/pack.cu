@@ -139,9 +139,11 @@ __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *_
 template <typename T>
 __global__ void prepare_rows_kernel(const T *__restrict__ x, int64_t n, int dim,
                                     const double *__restrict__ shift,
-                                    const double *__restrict__ inv_scale, float *__restrict__ X) {
+                                    const double *__restrict__ inv_scale, float *__restrict__ X,
+                                    int *__restrict__ clamped) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * 5) return;
+    int n_clamped = 0;
     const int64_t f = i / 5;
     const int c = (int)(i - f * 5);
     float v[8];
@@ -152,6 +154,7 @@ __global__ void prepare_rows_kernel(const T *__restrict__ x, int64_t n, int dim,
         if (d < dim) {
             double val = (double)x[f * dim + d];
             out = (float)((val - (shift ? shift[d] : 0.0)) * (inv_scale ? inv_scale[d] : 1.0));
+            if (!(fabsf(out) <= 240.f)) ++n_clamped;  // reported through option "clamped"
             out = fminf(fmaxf(out, -240.f), 240.f);
         } else {
             out = (d == PC_XS - 1) ? 1.f : 0.f;
@@ -161,6 +164,7 @@ __global__ void prepare_rows_kernel(const T *__restrict__ x, int64_t n, int dim,
     float4 *row = reinterpret_cast<float4 *>(X + (size_t)f * PC_XS + 8 * c);
     row[0] = make_float4(v[0], v[1], v[2], v[3]);
     row[1] = make_float4(v[4], v[5], v[6], v[7]);
+    if (n_clamped) atomicAdd(clamped, n_clamped);
 }
 
 // corpus frames: one thread per (tile image, row, 8-feature chunk)
@@ -168,7 +172,7 @@ template <typename T>
 __global__ void prepare_frames_kernel(CorpusView cv, const T *__restrict__ x, int dim,
                                       const double *__restrict__ shift,
                                       const double *__restrict__ inv_scale, float *__restrict__ X,
-                                      int64_t xtile_lo, int64_t xtile_hi) {
+                                      int64_t xtile_lo, int64_t xtile_hi, int *__restrict__ clamped) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (xtile_hi - xtile_lo) * PC_TILE_ROWS * 5) return;
     const int64_t blk = xtile_lo + i / (PC_TILE_ROWS * 5);
@@ -189,7 +193,9 @@ __global__ void prepare_frames_kernel(CorpusView cv, const T *__restrict__ x, in
                 double val = (double)x[(f0 + t) * dim + d];
                 out = (float)((val - (shift ? shift[d] : 0.0)) * (inv_scale ? inv_scale[d] : 1.0));
                 // keep x^2 inside the fp16 range of the tensor-core operands (|x'| is in standard
-                // deviations when the engine standardises, so this never triggers on sane data)
+                // deviations when the engine standardises, so this never triggers on sane data; when it
+                // does the caller hears about it: option "clamped", PC_ERR_INVALID from the host entry point)
+                if (!(fabsf(out) <= 240.f)) atomicAdd(clamped, 1);
                 out = fminf(fmaxf(out, -240.f), 240.f);
             } else {
                 out = (d == PC_XS - 1) ? 1.f : 0.f;
@@ -243,9 +249,9 @@ int launch_prepare_rows(pc_handle h, const void *x, int is_f64, int64_t n, int d
         return PC_ERR_UNSUPPORTED;
     }
     if (is_f64)
-        prepare_rows_kernel<double><<<(unsigned)blocks, threads, 0, st>>>((const double *)x, n, dim, shift, inv_scale, X);
+        prepare_rows_kernel<double><<<(unsigned)blocks, threads, 0, st>>>((const double *)x, n, dim, shift, inv_scale, X, h->dev_counters + PC_CNT_CLAMPED);
     else
-        prepare_rows_kernel<float><<<(unsigned)blocks, threads, 0, st>>>((const float *)x, n, dim, shift, inv_scale, X);
+        prepare_rows_kernel<float><<<(unsigned)blocks, threads, 0, st>>>((const float *)x, n, dim, shift, inv_scale, X, h->dev_counters + PC_CNT_CLAMPED);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -262,9 +268,9 @@ int launch_prepare_frames(pc_handle h, const CorpusView &cv, const void *x, int 
         return PC_ERR_UNSUPPORTED;
     }
     if (is_f64)
-        prepare_frames_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(cv, (const double *)x, dim, shift, inv_scale, X, xtile_lo, xtile_hi);
+        prepare_frames_kernel<double><<<(unsigned)blocks, threads, 0, st>>>(cv, (const double *)x, dim, shift, inv_scale, X, xtile_lo, xtile_hi, h->dev_counters + PC_CNT_CLAMPED);
     else
-        prepare_frames_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(cv, (const float *)x, dim, shift, inv_scale, X, xtile_lo, xtile_hi);
+        prepare_frames_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(cv, (const float *)x, dim, shift, inv_scale, X, xtile_lo, xtile_hi, h->dev_counters + PC_CNT_CLAMPED);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;

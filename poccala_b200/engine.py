@@ -281,6 +281,11 @@ class EStep:
             self.shift = mu.contiguous()
             self.inv_scale = (1.0 / sd).contiguous()
         self.corpus.X = self.engine.prepare_frames(self.corpus, x, self.shift, self.inv_scale, out=self.corpus.X)
+        clamped = self.engine.get_option("clamped")  # synchronises: once per corpus
+        if clamped:
+            raise ValueError("%d feature values lie more than 240 standard units from the shift and were clamped: "
+                             "standardise the frames (EStep(standardise=True)) or pass matching shift / inv_scale"
+                             % clamped)
         return self.corpus.X
 
     # kernels ------------------------------------------------------------------------------
@@ -428,16 +433,77 @@ def host_log_bands(transmat, device):
     return (torch.as_tensor(np.ascontiguousarray(ls)).to(device), torch.as_tensor(np.ascontiguousarray(ln)).to(device))
 
 
-def em_iteration_host(engine, corpus, frames, mean, var, alpha, transmat, c_covariance=1e-3, fix_code=0):
-    """pc_em_iteration_host: host numpy buffers in, parameters updated in place, returns sum logP."""
+def frame_moments_host(engine, frames, group=None):
+    """Standardisation constants of a corpus held in host memory (pc_frame_moments_host): per-dimension
+    mean and 1/std as fp64 numpy arrays.  With a process group the moments of all ranks are added first,
+    so every rank maps its frames - and its accumulators, which live in the standardised space - the
+    same way."""
+    frames = np.ascontiguousarray(frames, dtype=np.float32)
+    n, D = frames.shape
+    s, q = np.zeros(D), np.zeros(D)
+    nat.call("pc_frame_moments_host", engine.h, _p(frames), n, D, _p(s), _p(q), _stream())
+    mom = np.concatenate([s, q, [float(n)]])
+    if group is not None:
+        t = torch.as_tensor(mom).to(engine.device)
+        torch.distributed.all_reduce(t, group=group)
+        mom = t.cpu().numpy()
+    cnt = mom[-1]
+    mu = mom[:D] / cnt
+    sd = np.sqrt(np.maximum(mom[D:2 * D] / cnt - mu * mu, 0.0))
+    return np.ascontiguousarray(mu), np.ascontiguousarray(1.0 / np.maximum(sd, 1e-12))
+
+
+class HostReduceHook:
+    """NCCL side of pc_em_iteration_host at world size > 1 (pc_set_reduce_hook): the exchange buffers
+    are torch tensors; the library calls back between its launches, op 0 = all-reduce MAX of the
+    transition maxima, op 1 = all-reduce SUM of [GMM statistics | transition sums], each queued on the
+    stream it names."""
+
+    def __init__(self, engine, n_units, n_gauss, group):
+        self.engine, self.group = engine, group
+        self.tmax = engine.empty((n_units, SLOTS), torch.float64)
+        self.flat = engine.empty((n_gauss * KA + n_units * SLOTS,), torch.float64)
+        self.error = None
+
+        def _hook(user, op, stream):
+            try:
+                ext = torch.cuda.ExternalStream(int(stream or 0), device=engine.device)
+                with torch.cuda.stream(ext):
+                    if op == 0:
+                        torch.distributed.all_reduce(self.tmax, op=torch.distributed.ReduceOp.MAX, group=self.group)
+                    else:
+                        torch.distributed.all_reduce(self.flat, group=self.group)
+                return 0
+            except Exception as e:  # never let an exception cross the C boundary
+                self.error = e
+                return 1
+
+        self._cb = nat.REDUCE_HOOK(_hook)  # keep the trampoline alive
+        nat.call("pc_set_reduce_hook", engine.h, C.cast(self._cb, C.c_void_p), None, _p(self.tmax), _p(self.flat),
+                 self.flat.numel())
+
+    def remove(self):
+        nat.call("pc_set_reduce_hook", self.engine.h, None, None, None, None, 0)
+
+
+def em_iteration_host(engine, corpus, frames, mean, var, alpha, transmat, c_covariance=1e-3, fix_code=0,
+                      shift=None, inv_scale=None):
+    """pc_em_iteration_host: host numpy buffers in, parameters updated in place, returns sum logP.
+    shift / inv_scale: the corpus' standardisation constants (frame_moments_host); None = computed
+    from `frames` inside the call."""
     frames = np.ascontiguousarray(frames, dtype=np.float32)
     for a in (mean, var, alpha, transmat):
         if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
             raise TypeError("parameters must be C-contiguous float64 numpy arrays (updated in place)")
+    if (shift is None) != (inv_scale is None):
+        raise ValueError("shift and inv_scale go together")
+    if shift is not None:
+        shift = np.ascontiguousarray(shift, dtype=np.float64)
+        inv_scale = np.ascontiguousarray(inv_scale, dtype=np.float64)
     U, _, M, D = mean.shape
     out = C.c_double(0.0)
     nat.call("pc_em_iteration_host", engine.h, corpus.c, _p(frames), D, U, M, _p(mean), _p(var), _p(alpha),
-             _p(transmat), float(c_covariance), int(fix_code), C.byref(out), _stream())
+             _p(transmat), _p(shift), _p(inv_scale), float(c_covariance), int(fix_code), C.byref(out), _stream())
     return out.value
 
 

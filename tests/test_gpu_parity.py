@@ -126,12 +126,19 @@ def test_scores_tensor_core_dead_and_scaled_rows(eng):
         assert _relerr(b_tc, b_ref) < REL
 
 
-def test_forward_backward_matches_oracle(eng):
-    init, labels, utts, n_units = _ragged(cfg_seed=4, n_utt=20, T=90, L=5)
+@pytest.mark.parametrize("k2_kernel,L", [(1, 5), (0, 5), (1, 14), (0, 14)])
+def test_forward_backward_matches_oracle(eng, k2_kernel, L):
+    """Both forward-backward kernels (one warp per utterance with the likelihood as normaliser; three
+    warps with a per-frame normaliser), one and two states per lane."""
+    init, labels, utts, n_units = _ragged(cfg_seed=4, n_utt=20, T=90, L=L)
     corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
     es.score()
-    es.forward_backward()
-    torch.cuda.synchronize()
+    eng.set_option("k2_kernel", k2_kernel)
+    try:
+        es.forward_backward()
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("k2_kernel", 1)
     logp = es.utt_logp.cpu().numpy()
     iters = es.utt_iters.cpu().numpy()
     pt = es.pair_trans.cpu().numpy()
@@ -253,22 +260,92 @@ def test_em_iteration_matches_executed_reference(eng):
 
 
 def test_host_entry_point_matches_device_path(eng):
-    from poccala_b200.engine import em_iteration_host
+    """pc_em_iteration_host standardises like EStep.load_frames does (its own device reduction of the
+    moments when no constants are passed), so both paths run the same arithmetic."""
+    from poccala_b200.engine import em_iteration_host, frame_moments_host
 
     init, labels, utts, n_units = _ragged(cfg_seed=6, n_utt=10, T=50, L=3, n_units=4)
-    corpus, model, es, om = _setup(eng, init, labels, utts, n_units, standardise=False)
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
     es.em_iteration(c_covariance=1e-6)
     torch.cuda.synchronize()
+    m2, v2, a2, t2 = model.numpy()
+    frames = np.concatenate(utts).astype(np.float32)
+    shift, inv_scale = frame_moments_host(eng, frames)
+    assert np.allclose(shift, es.shift.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert np.allclose(inv_scale, es.inv_scale.cpu().numpy(), rtol=1e-6)
+    for consts in ((None, None), (shift, inv_scale)):
+        mean, var, alpha = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init]
+        tm = synth.default_transmat(n_units).copy()
+        slp = em_iteration_host(eng, corpus, frames, mean, var, alpha, tm, c_covariance=1e-6,
+                                shift=consts[0], inv_scale=consts[1])
+        assert abs(slp - float(es.utt_logp.sum())) < 1e-6 * abs(slp)
+        assert np.allclose(mean, m2, rtol=1e-5, atol=1e-6)
+        assert np.allclose(var, v2, rtol=1e-4, atol=1e-7)
+        assert np.allclose(alpha, a2, rtol=1e-5)
+        assert np.allclose(tm, t2, rtol=1e-5, atol=1e-9)
+
+
+def _offset_problem(cfg_seed, n_utt, T, L, n_units, mix=4):
+    """Features far from the origin and on very different scales (dimension 0 sits at +50, every
+    third dimension is stretched x12, |x| < 100 for the reference's +100 bias, Q7): the expanded
+    quadratic of the scoring contraction only survives this through the standardisation."""
+    truth, init, labels, utts = synth.make_corpus(n_utt, T, L, n_units, mix, cfg_seed, ragged=True)
+    D = init[0].shape[-1]
+    scale = np.ones(D)
+    scale[2::3] = 12.0
+    offset = np.zeros(D)
+    offset[0], offset[5] = 50.0, -35.0
+    utts = [x * scale + offset for x in utts]
+    init = (init[0] * scale + offset, init[1] * scale * scale, init[2])
+    assert max(np.abs(x).max() for x in utts) < 100.0
+    return init, labels, utts
+
+
+def test_host_entry_point_offset_data_matches_oracle(eng):
+    """The end-to-end entry point (the call bench.py times as `e2e`) against the fp64 oracle on data
+    with a large mean offset: log-likelihoods and re-estimated parameters within 1e-4."""
+    from poccala_b200.engine import em_iteration_host, frame_moments_host
+
+    n_units = 4
+    init, labels, utts = _offset_problem(31, 12, 60, 3, n_units)
+    corpus = _corpus(eng, labels, utts, n_units)
+    tm0 = synth.default_transmat(n_units)
+    om = fast.Model(*init, tm0)
+    stats, info = fast.estep_corpus(om, labels, utts)
+    new = fast.mstep(om, stats, c_covariance=1e-6)
+    frames = np.concatenate(utts).astype(np.float32)
+    shift, inv_scale = frame_moments_host(eng, frames)
+    for consts in ((None, None), (shift, inv_scale)):
+        mean, var, alpha = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init]
+        tm = tm0.copy()
+        slp = em_iteration_host(eng, corpus, frames, mean, var, alpha, tm, c_covariance=1e-6,
+                                shift=consts[0], inv_scale=consts[1])
+        assert abs(slp - float(np.sum(info["logp"]))) <= 1e-5 * abs(slp)
+        ok = stats.occ >= OCC_MIN
+        assert ok.sum() >= 0.75 * ok.size
+        assert _relerr(alpha, new.alpha, floor=1e-3) < REL
+        sd = np.sqrt(new.var)
+        assert np.all(np.abs(mean - new.mean)[ok] <= (REL * np.maximum(np.abs(new.mean - shift), sd))[ok])
+        assert _var_close(var[ok], new.var[ok], utts)
+        assert np.all(np.abs(tm - new.transmat) <= REL * np.maximum(new.transmat, 1e-2))
+
+
+def test_host_entry_point_reports_unstandardised_frames(eng):
+    """Constants that do not describe the frames push standardised values past +-240: the call fails
+    instead of saturating silently."""
+    from poccala_b200._native import NativeError
+    from poccala_b200.engine import em_iteration_host
+
+    n_units = 4
+    init, labels, utts = _offset_problem(32, 6, 40, 2, n_units)
+    corpus = _corpus(eng, labels, utts, n_units)
     mean, var, alpha = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init]
     tm = synth.default_transmat(n_units).copy()
-    slp = em_iteration_host(eng, corpus, np.concatenate(utts).astype(np.float32), mean, var, alpha, tm,
-                            c_covariance=1e-6)
-    m2, v2, a2, t2 = model.numpy()
-    assert abs(slp - float(es.utt_logp.sum())) < 1e-6 * abs(slp)
-    assert np.allclose(mean, m2, rtol=1e-5, atol=1e-6)
-    assert np.allclose(var, v2, rtol=1e-4, atol=1e-7)
-    assert np.allclose(alpha, a2, rtol=1e-5)
-    assert np.allclose(tm, t2, rtol=1e-5, atol=1e-9)
+    D = mean.shape[-1]
+    with pytest.raises(NativeError, match="clamped"):
+        em_iteration_host(eng, corpus, np.concatenate(utts).astype(np.float32), mean, var, alpha, tm,
+                          c_covariance=1e-6, shift=np.zeros(D), inv_scale=np.full(D, 10.0))
+    assert eng.get_option("clamped") == 0  # reported once
 
 
 def _viterbi_check(eng, labels, utts, init, n_units, transmat=None, emissions64=None):
