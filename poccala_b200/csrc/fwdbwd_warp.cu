@@ -18,20 +18,22 @@
 // the utterance likelihood (Q6), so expected counts of e^-300 can decide a unit's transition row
 // and a scaled linear-domain recurrence would flush them.
 //
-// Arithmetic: fp32 log2 domain.  Every frame's emissions are shifted by g_t = max_j b_t(j) and every
-// FW_CH frames the state vector is renormalised exactly (one CREDUX on the chain); the shifts are
-// carried in fp64 per frame (backward: stored beside nb; forward: a running sum), so the scale
-// constant of frame t, (forward shifts to t-1) + (backward shifts from t) - log2 P, is an fp64
-// difference of numbers of size 1e4 rounded to fp32 once.  Lane l owns states [l*SPL, (l+1)*SPL);
-// emissions are time-major, a warp reads / writes one coalesced row per frame.  Scratch: nb rows in
-// the corpus' beta scratch (same layout as b), one float4 per frame {shift (fp64), g_t*log2e, nb of
-// the entry state}.  K3's activity flags are set from the log gamma rows while they are at hand.
+// Arithmetic: fp32 log2 domain.  Every frame's emissions are shifted by g_t = ceil(max_j log2 b_t(j)) and
+// every FW_CH frames the state vector is renormalised by the ceiling of its maximum (one CREDUX on the
+// chain).  All shifts are INTEGERS, so their running sums are exact in fp32 (|sum| < 2^24) and the scale
+// constant of frame t, (forward shifts to t-1) + (backward shifts from t) - log2 P, is an exact small
+// integer minus the fractional part of log2 P: no fp64 inside the loops.  Once per chunk the forward pass
+// measures the drift of its normaliser (log2 sum_j gamma_t(j), zero in exact arithmetic, ~1e-5 after 300
+// frames of MUFU approximations) and folds it into the constant.  Lane l owns states [l*SPL, (l+1)*SPL);
+// emissions are time-major, a warp reads / writes one coalesced row per frame.  Scratch: nb rows in the
+// corpus' beta scratch (same layout as b), one float4 per frame {backward shift, g_t, nb of the entry
+// state}.  K3's activity flags are set from the log gamma rows while they are at hand.
 #include <type_traits>
 
 #include "common.cuh"
 
-#define FW_CH 8   // frames per chunk: prefetch depth and renormalisation period
-#define FW_WPB 2  // warps (utterances) per block
+#define FW_CH 8   // frames per chunk: prefetch depth and renormalisation period (4: measured slower, 593 vs 322 clk per forward frame)
+#define FW_WPB 1  // one warp per block: every index below is provably warp-uniform (no divergence checks around the shuffles)
 
 __device__ long long g_fw_dbg[16];
 
@@ -62,14 +64,20 @@ __device__ __forceinline__ float logadd2(float a, float b) {
     d = (m == PC_NEG_INF) ? 0.f : d;
     return m + lg2f(1.f + ex2f(d));
 }
-// sum * 2^mx += 2^x, rescaling only when x overtakes the reference by a wide margin
-__device__ __forceinline__ void acc_lse2(float &mx, float &sum, float x) {
-    if (x > mx + 24.f) {
-        sum *= ex2f(mx - x);
-        mx = x;
-    }
-    sum += ex2f(x - mx);
+// asynchronous global -> shared copies (LDGSTS): the prefetch of the next chunk's rows neither holds
+// registers nor can be scheduled late by the compiler (register prefetches were sunk to their first use:
+// a quarter of the kernel's time went into waiting for them, profiles/README.md)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -83,9 +91,11 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
                    double *__restrict__ utt_logp, int32_t *__restrict__ utt_iters,
                    float *__restrict__ pair_trans) {
     constexpr int CH = FW_CH;
-    const int lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * FW_WPB + (threadIdx.x >> 5);
-    if (idx >= v.n_utt) return;
+    // two-stage ring of prefetched rows: every lane copies (and later reads) its own columns
+    __shared__ float sm_b[2][CH][32 * SPL], sm_n[2][CH][32 * SPL];
+    __shared__ __align__(16) float4 sm_f[2][CH];
+    const int lane = threadIdx.x;
+    const int idx = blockIdx.x;
     const int u = v.fb_order[idx];
     const int64_t f0 = v.frame_off[u];
     const int T = (int)(v.frame_off[u + 1] - f0);
@@ -125,9 +135,22 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
             ln[q] = PC_NEG_INF;
         }
     }
-    auto load_row = [&](int t, float (&e)[SPL]) {
+    // per-lane views of the [T][SP] blocks: element (t, this state) of b / nb / lgam is base[q][t * sp]
+    bool emit[SPL];
+    const float *bq[SPL];
+    float *nq[SPL], *gq[SPL];
 #pragma unroll
-        for (int q = 0; q < SPL; ++q) e[q] = (kind[q] == 1) ? __ldg(bu + (size_t)t * sp + col[q]) : PC_NEG_INF;
+    for (int q = 0; q < SPL; ++q) {
+        emit[q] = kind[q] == 1;
+        bq[q] = bu + col[q];
+        nq[q] = nbu + col[q];
+        gq[q] = gu + col[q];
+    }
+    const unsigned spu = (unsigned)sp;
+    auto load_row = [&](int t, float (&e)[SPL]) {
+        const unsigned off = (unsigned)t * spu;
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) e[q] = emit[q] ? __ldg(bq[q] + off) : PC_NEG_INF;
     };
     auto frame_max = [&](const float (&e)[SPL]) {
         float m = e[0];
@@ -145,25 +168,43 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
 
     // ------------------------------------------------------------------ backward (LHMM.py:353-366)
     float bh[SPL];
-    double Cb = 0.0;  // log2 beta_t = bh + Cb
+    float Cb = 0.f;  // log2 beta_t = bh + Cb; an integer (exact in fp32)
 #pragma unroll
     for (int q = 0; q < SPL; ++q) bh[q] = (kind[q] != 2) ? 0.f : PC_NEG_INF;
     {
         // step tau (= T-1 .. 1) consumes emission row tau, stores nb_tau and produces beta_hat_{tau-1}
-        float e_nxt[CH][SPL];
         int tau_hi = T - 1;
+        float *np_[SPL];  // -> (frame tau, this state) of the nb rows, walking down
+        float4 *fp_ = fs + tau_hi;
 #pragma unroll
-        for (int k = 0; k < CH; ++k) load_row(max(tau_hi - k, 0), e_nxt[k]);
+        for (int q = 0; q < SPL; ++q) np_[q] = nq[q] + (unsigned)tau_hi * spu;
+        // rows t_first, t_first - 1, .. of b -> stage `st` (clamped at row 0: the tail chunk ignores the extras)
+        auto prefetch_b = [&](int st, int t_first) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const unsigned off = (unsigned)max(t_first - k, 0) * spu;
+#pragma unroll
+                for (int q = 0; q < SPL; ++q)
+                    if (emit[q]) cp_async4(&sm_b[st][k][lane * SPL + q], bq[q] + off);
+            }
+            cp_async_commit();
+        };
+        prefetch_b(0, tau_hi);
+        int stage = 0;
         auto chunk = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             float es[CH][SPL], g2[CH];
+            cp_async_wait_all();
 #pragma unroll
             for (int k = 0; k < CH; ++k) {  // off the dependency chain
-                g2[k] = frame_max(e_nxt[k]) * kLog2e;
-                shift_row(e_nxt[k], g2[k], es[k]);
-            }
+                float e[SPL];
 #pragma unroll
-            for (int k = 0; k < CH; ++k) load_row(max(tau_hi - CH - k, 0), e_nxt[k]);  // prefetch
+                for (int q = 0; q < SPL; ++q) e[q] = emit[q] ? sm_b[stage][k][lane * SPL + q] : PC_NEG_INF;
+                g2[k] = ceilf(frame_max(e) * kLog2e);
+                shift_row(e, g2[k], es[k]);
+            }
+            prefetch_b(stage ^ 1, tau_hi - CH);
+            stage ^= 1;
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int tau = tau_hi - k;
@@ -172,13 +213,12 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) {
                         nb[q] = bh[q] + es[k][q];
-                        if (kind[q] == 1) nbu[(size_t)tau * sp + col[q]] = nb[q];
+                        if (emit[q]) *np_[q] = nb[q];
+                        np_[q] -= spu;
                     }
-                    if (lane == 0) {  // lane 0 holds the entry state in slot 0
-                        const double db = Cb + (double)g2[k];  // log2(b_tau beta_tau) = nb_tau + db
-                        fs[tau] = make_float4(__int_as_float(__double2loint(db)), __int_as_float(__double2hiint(db)),
-                                              g2[k], nb[0]);
-                    }
+                    // lane 0 holds the entry state in slot 0; log2(b_tau beta_tau) = nb_tau + (Cb + g2)
+                    if (lane == 0) *fp_ = make_float4(Cb + g2[k], g2[k], nb[0], 0.f);
+                    --fp_;
                     float up = __shfl_down_sync(0xffffffffu, nb[0], 1);
                     if (lane == 31) up = PC_NEG_INF;
 #pragma unroll
@@ -187,14 +227,14 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
                         raw[q] = logadd2(ls[q] + nb[q], ln[q] + nxt);
                     }
                     float r = 0.f;
-                    if (FULL && k == CH - 1) {  // exact renormalisation once per full chunk
+                    if (FULL && k == CH - 1) {
                         float m = raw[0];
 #pragma unroll
                         for (int q = 1; q < SPL; ++q) m = fmaxf(m, raw[q]);
                         m = redux_max(m);
-                        r = (m == PC_NEG_INF) ? 0.f : m;
+                        r = (m == PC_NEG_INF) ? 0.f : ceilf(m);
                     }
-                    Cb += (double)g2[k] + (double)r;
+                    Cb += g2[k] + r;
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) bh[q] = raw[q] - r;
                 }
@@ -207,7 +247,7 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
     if (trace) g_fw_dbg[1] = clock64();
     float e0[SPL];
     load_row(0, e0);
-    const float g20 = frame_max(e0) * kLog2e;
+    const float g20 = ceilf(frame_max(e0) * kLog2e);
 
     // ----------------------------------------- pi iteration (LHMM.py:447-452,526-544; A.3)
     // natural-log fp64 on w = B[:,0] + beta_0, relative to Cb (added back for log P)
@@ -251,7 +291,7 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
         if (kind[q] == 1) gu[col[q]] = (float)lg0;
     }
     if (lane == 0) {
-        utt_logp[u] = qn + Cb * 0.6931471805599453;
+        utt_logp[u] = qn + (double)Cb * 0.6931471805599453;
         utt_iters[u] = iters;
     }
     if (trace) g_fw_dbg[2] = clock64();
@@ -284,7 +324,8 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
     // ------------------------------------------------------------------ forward (LHMM.py:335-351)
     // + log gamma (LHMM.py:486-500) + expected transition counts (LHMM.py:431-445)
     float ah[SPL];
-    double CaLP;  // (forward shifts up to the previous frame) - log2 P:  log2 alpha_t = ah + CaLP + log2 P
+    float Sa;      // (forward shifts up to the previous frame) - floor(log2 P): an exact integer
+    float fPc;     // frac(log2 P) + the measured drift of the normaliser
     {
         float m = PC_NEG_INF;
 #pragma unroll
@@ -294,10 +335,14 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
             m = fmaxf(m, ah[q]);
         }
         m = redux_max(m);
-        if (m == PC_NEG_INF) m = 0.f;
+        m = (m == PC_NEG_INF) ? 0.f : ceilf(m);
 #pragma unroll
         for (int q = 0; q < SPL; ++q) ah[q] -= m;
-        CaLP = (double)g20 + (double)m - (qn * 1.4426950408889634 + Cb);
+        const double LP = qn * 1.4426950408889634 + (double)Cb;  // log2 P(O)
+        const double IP = floor(LP);
+        Sa = (float)((double)g20 + (double)m - IP);
+        fPc = (float)(LP - IP);
+        if (!(fabs(LP) < 1e30)) { Sa = 0.f; fPc = 0.f; }  // no path at all: the rows come out -inf / NaN either way
     }
     float ms[SPL], cs[SPL], mn[SPL], cn[SPL];  // running log-sum-exp of the stay / move counts
 #pragma unroll
@@ -306,77 +351,120 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
         cs[q] = cn[q] = 0.f;
     }
     {
-        float e_nxt[CH][SPL], nb_nxt[CH][SPL];
-        float4 f_nxt[CH];
         int tau_lo = 1;
-        auto load_fwd = [&](int t0) {
+        float *gp_[SPL];  // -> (frame t, this state) of the log gamma rows, walking up
+#pragma unroll
+        for (int q = 0; q < SPL; ++q) gp_[q] = gq[q] + spu;
+        // rows t0 .. t0 + CH - 1 of b and nb and the per-frame records -> stage `st` (clamped at row T - 1)
+        auto prefetch_f = [&](int st, int t0) {
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int t = min(t0 + k, T - 1);
-                load_row(t, e_nxt[k]);
-                f_nxt[k] = __ldcg(fs + t);
+                const unsigned off = (unsigned)t * spu;
 #pragma unroll
                 for (int q = 0; q < SPL; ++q)
-                    nb_nxt[k][q] = (kind[q] == 1) ? __ldcg(nbu + (size_t)t * sp + col[q])
-                                                  : (kind[q] == 0 ? f_nxt[k].w : PC_NEG_INF);
+                    if (emit[q]) {
+                        cp_async4(&sm_b[st][k][lane * SPL + q], bq[q] + off);
+                        cp_async4(&sm_n[st][k][lane * SPL + q], nq[q] + off);
+                    }
+                if (lane == k) cp_async16(&sm_f[st][k], fs + t);
             }
+            cp_async_commit();
         };
-        load_fwd(tau_lo);
+        prefetch_f(0, tau_lo);
+        int stage = 0;
         auto chunk = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
-            float es[CH][SPL], nbc[CH][SPL], g2[CH];
-            double db[CH];
+            float es[CH][SPL], nbc[CH][SPL], g2[CH], db[CH];
+            cp_async_wait_all();
+            __syncwarp();  // the per-frame records were fetched by lanes 0 .. CH-1
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
-                g2[k] = f_nxt[k].z;
-                db[k] = __hiloint2double(__float_as_int(f_nxt[k].y), __float_as_int(f_nxt[k].x));
-                shift_row(e_nxt[k], g2[k], es[k]);
+                const float4 f = sm_f[stage][k];
+                db[k] = f.x;
+                g2[k] = f.y;
+                float e[SPL];
 #pragma unroll
-                for (int q = 0; q < SPL; ++q) nbc[k][q] = nb_nxt[k][q];
+                for (int q = 0; q < SPL; ++q) {
+                    e[q] = emit[q] ? sm_b[stage][k][lane * SPL + q] : PC_NEG_INF;
+                    nbc[k][q] = emit[q] ? sm_n[stage][k][lane * SPL + q] : (kind[q] == 0 ? f.z : PC_NEG_INF);
+                }
+                shift_row(e, g2[k], es[k]);
             }
-            load_fwd(tau_lo + CH);  // prefetch
+            __syncwarp();  // every lane has read the records before the other stage's refill can land on a reused slot
+            prefetch_f(stage ^ 1, tau_lo + CH);
+            stage ^= 1;
+            float xs[CH][SPL], xn[CH][SPL], lg2_last[SPL];
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int t = tau_lo + k;
-                if (FULL || t <= T - 1) {
-                    const float cx = (float)(CaLP + db[k]);  // scale constant of frame t
-                    float left = __shfl_up_sync(0xffffffffu, ah[SPL - 1] + ln[SPL - 1], 1);
-                    if (lane == 0) left = PC_NEG_INF;
-                    float raw[SPL];
+                const bool valid = FULL || t <= T - 1;
+                // scale constant of frame t: (exact integer) - (fraction of log2 P + drift)
+                const float cx = (Sa + db[k]) - fPc;
+                float left = __shfl_up_sync(0xffffffffu, ah[SPL - 1] + ln[SPL - 1], 1);
+                if (lane == 0) left = PC_NEG_INF;
+                float raw[SPL];
 #pragma unroll
-                    for (int q = 0; q < SPL; ++q) {
-                        const float stay = ah[q] + ls[q];
-                        const float move = (q > 0) ? ah[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
-                        raw[q] = logadd2(stay, move);
-                        const float nc = nbc[k][q] + cx;
-                        acc_lse2(ms[q], cs[q], stay + nc);
-                        acc_lse2(mn[q], cn[q], move + nc);
-                        const float lg = (raw[q] + nc) * kLn2;
-                        if (kind[q] == 1) {
-                            gu[(size_t)t * sp + col[q]] = lg;
-                            tmx[q] = fmaxf(tmx[q], lg);
-                        }
-                    }
+                for (int q = 0; q < SPL; ++q) {
+                    const float stay = ah[q] + ls[q];
+                    const float move = (q > 0) ? ah[(q + SPL - 1) % SPL] + ln[(q + SPL - 1) % SPL] : left;
+                    raw[q] = logadd2(stay, move);
+                    const float nc = nbc[k][q] + cx;
+                    xs[k][q] = valid ? stay + nc : PC_NEG_INF;
+                    xn[k][q] = valid ? move + nc : PC_NEG_INF;
+                    const float l2 = raw[q] + nc;
+                    if (k == CH - 1) lg2_last[q] = l2;
+                    const float lg = l2 * kLn2;
+                    if (valid && emit[q]) *gp_[q] = lg;
+                    gp_[q] += spu;
+                    if (valid) tmx[q] = fmaxf(tmx[q], lg);  // (only emitting states' maxima are ever read)
+                }
+                if (valid) {
                     float r = 0.f;
                     if (FULL && k == CH - 1) {
                         float m = raw[0] + es[k][0];
 #pragma unroll
                         for (int q = 1; q < SPL; ++q) m = fmaxf(m, raw[q] + es[k][q]);
                         m = redux_max(m);
-                        r = (m == PC_NEG_INF) ? 0.f : m;
+                        r = (m == PC_NEG_INF) ? 0.f : ceilf(m);
                     }
-                    CaLP += (double)g2[k] + (double)r;
+                    Sa += g2[k] + r;
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) ah[q] = raw[q] + es[k][q] - r;
-                    // a tile's last frame: t = 127 mod 128 sits at k = CH - 2 of its chunk (chunks start at t = 1 mod CH)
-                    if ((k == CH - 2 && (t & (PC_TILE_ROWS - 1)) == PC_TILE_ROWS - 1) || t == T - 1)
-                        flag_tile(t / PC_TILE_ROWS);
                 }
+                // a tile's last frame, t = 127 mod 128, sits at k = CH - 2 of its chunk (chunks start at t = 1 mod CH)
+                if (k == CH - 2 && valid && (t & (PC_TILE_ROWS - 1)) == PC_TILE_ROWS - 1) flag_tile(t / PC_TILE_ROWS);
+            }
+            // expected counts: log-sum-exp over the chunk with one shared reference per state (branch-free)
+#pragma unroll
+            for (int q = 0; q < SPL; ++q) {
+                float gs = xs[0][q], gn = xn[0][q];
+#pragma unroll
+                for (int k = 1; k < CH; ++k) { gs = fmaxf(gs, xs[k][q]); gn = fmaxf(gn, xn[k][q]); }
+                const float ns = fmaxf(ms[q], gs), nn = fmaxf(mn[q], gn);
+                float as = cs[q] * ex2f(ms[q] - ns), an = cn[q] * ex2f(mn[q] - nn);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) { as += ex2f(xs[k][q] - ns); an += ex2f(xn[k][q] - nn); }
+                ms[q] = ns; cs[q] = as; mn[q] = nn; cn[q] = an;
+            }
+            if (FULL) {
+                // drift of the normaliser at the chunk's last frame: log2 sum_j gamma(j) should be 0
+                float m = lg2_last[0];
+#pragma unroll
+                for (int q = 1; q < SPL; ++q) m = fmaxf(m, lg2_last[q]);
+                m = redux_max(m);
+                float z = 0.f;
+#pragma unroll
+                for (int q = 0; q < SPL; ++q) z += ex2f(lg2_last[q] - m);
+                z = warp_sum(z);
+                const float drift = m + lg2f(z);
+                if (fabsf(drift) < 1e-2f) fPc += drift;  // (an utterance without any path has no normaliser)
             }
             tau_lo += CH;
         };
         while (tau_lo + CH - 1 <= T - 1) chunk(std::true_type{});
         if (tau_lo <= T - 1) chunk(std::false_type{});
+        if (T > 1 && ((T - 1) & (PC_TILE_ROWS - 1)) != PC_TILE_ROWS - 1) flag_tile((T - 1) / PC_TILE_ROWS);  // the last, partial tile
     }
     // the move counts were collected at the destination state: state s's "next" count sits with state s + 1
     {

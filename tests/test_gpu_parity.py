@@ -265,6 +265,7 @@ def test_host_entry_point_matches_device_path(eng):
     from poccala_b200.engine import em_iteration_host, frame_moments_host
 
     init, labels, utts, n_units = _ragged(cfg_seed=6, n_utt=10, T=50, L=3, n_units=4)
+    utts = [x.astype(np.float32).astype(np.float64) for x in utts]  # the same fp32 frames on both paths
     corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
     es.em_iteration(c_covariance=1e-6)
     torch.cuda.synchronize()
@@ -292,12 +293,12 @@ def _offset_problem(cfg_seed, n_utt, T, L, n_units, mix=4):
     truth, init, labels, utts = synth.make_corpus(n_utt, T, L, n_units, mix, cfg_seed, ragged=True)
     D = init[0].shape[-1]
     scale = np.ones(D)
-    scale[2::3] = 12.0
+    scale[2::3] = 8.0
     offset = np.zeros(D)
     offset[0], offset[5] = 50.0, -35.0
     utts = [x * scale + offset for x in utts]
     init = (init[0] * scale + offset, init[1] * scale * scale, init[2])
-    assert max(np.abs(x).max() for x in utts) < 100.0
+    assert max(np.abs(x).max() for x in utts) < 100.0, "Q7: the reference adds 100 before taking logs"
     return init, labels, utts
 
 
@@ -320,14 +321,18 @@ def test_host_entry_point_offset_data_matches_oracle(eng):
         tm = tm0.copy()
         slp = em_iteration_host(eng, corpus, frames, mean, var, alpha, tm, c_covariance=1e-6,
                                 shift=consts[0], inv_scale=consts[1])
-        assert abs(slp - float(np.sum(info["logp"]))) <= 1e-5 * abs(slp)
+        assert abs(slp - float(np.sum(info["logp"]))) <= 1e-5 * abs(slp), (slp, float(np.sum(info["logp"])))
         ok = stats.occ >= OCC_MIN
         assert ok.sum() >= 0.75 * ok.size
-        assert _relerr(alpha, new.alpha, floor=1e-3) < REL
+        assert _relerr(alpha, new.alpha, floor=1e-3) < REL, _relerr(alpha, new.alpha, floor=1e-3)
         sd = np.sqrt(new.var)
-        assert np.all(np.abs(mean - new.mean)[ok] <= (REL * np.maximum(np.abs(new.mean - shift), sd))[ok])
-        assert _var_close(var[ok], new.var[ok], utts)
-        assert np.all(np.abs(tm - new.transmat) <= REL * np.maximum(new.transmat, 1e-2))
+        merr = (np.abs(mean - new.mean) / np.maximum(np.abs(new.mean - shift), sd))[ok].max()
+        assert merr <= REL, merr
+        gvar = np.concatenate(utts, axis=0).var(axis=0)
+        verr = (np.abs(var - new.var) / np.maximum(new.var, 1e-2 * gvar))[ok].max()
+        assert verr <= REL, verr
+        terr = (np.abs(tm - new.transmat) / np.maximum(new.transmat, 1e-2)).max()
+        assert terr <= REL, terr
 
 
 def test_host_entry_point_reports_unstandardised_frames(eng):
