@@ -50,6 +50,7 @@ int pc_create(int device, pc_handle *out) {
     h->sm_count = prop.multiProcessorCount;
     h->use_tc = 1;
     h->k2_kernel = 1;
+    h->k1_kernel = 1;
     if (cudaMalloc((void **)&h->dev_counters, PC_CNT_N * sizeof(int)) != cudaSuccess ||
         cudaMemset(h->dev_counters, 0, PC_CNT_N * sizeof(int)) != cudaSuccess) {
         pc_set_error("pc_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -84,6 +85,7 @@ int pc_set_option(pc_handle h, const char *key, int64_t value) {
     if (!strcmp(key, "host_chunks")) { h->host_chunks = (int)value; return PC_OK; }
     if (!strcmp(key, "launches")) { h->launches = value; return PC_OK; }
     if (!strcmp(key, "k2_kernel")) { h->k2_kernel = (int)value; return PC_OK; }
+    if (!strcmp(key, "k1_kernel")) { h->k1_kernel = (int)value; return PC_OK; }
     pc_set_error("pc_set_option: unknown key '%s'", key);
     return PC_ERR_INVALID;
 }
@@ -96,6 +98,7 @@ int64_t pc_get_option(pc_handle h, const char *key) {
     if (!strcmp(key, "launches")) return h->launches;
     if (!strcmp(key, "sm_count")) return h->sm_count;
     if (!strcmp(key, "k2_kernel")) return h->k2_kernel;
+    if (!strcmp(key, "k1_kernel")) return h->k1_kernel;
     if (!strcmp(key, "clamped")) {
         const int idx = PC_CNT_CLAMPED;
         int n = 0;
@@ -429,7 +432,7 @@ int64_t pc_corpus_emission_floats(pc_corpus c) { return c ? c->emis_floats : -1;
 int64_t pc_corpus_total_pairs(pc_corpus c) { return c ? c->v.n_pairs : -1; }
 int64_t pc_corpus_total_states(pc_corpus c) { return c ? c->total_states : -1; }
 int64_t pc_corpus_frames_bytes(pc_corpus c) {
-    return c ? (int64_t)(pc_x16_offset(c->total_frames) + (size_t)c->v.n_xtiles * PC_XTILE_BYTES) : -1;
+    return c ? (int64_t)(pc_x32_offset(c->total_frames, c->v.n_xtiles) + (size_t)c->v.n_xtiles * PC_X32TILE_BYTES) : -1;
 }
 
 int pc_corpus_offsets(pc_corpus c, int64_t *frame_off, int64_t *emis_off, int64_t *pair_off,

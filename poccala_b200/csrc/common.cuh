@@ -9,11 +9,15 @@
 
 #define PC_TILE_ROWS 128  // frames per work tile (one tcgen05 M=128 accumulator block)
 #define PC_XTILE_BYTES (2 * (PC_KA / 8) * PC_TILE_ROWS * 16)  // one frame-tile operand image (40 KiB)
+#define PC_X32TILE_BYTES (PC_TILE_ROWS * PC_XS * 4)           // one frame tile as fp32, quad-major [10][128 rows][4] (20 KiB)
 #define PC_WGROUP_BYTES (2 * (PC_KA / 8) * 128)               // 8 Gaussian rows of a unit image (2560 B)
 
 // byte offsets of the fp16 operand images inside the W / X buffers (pack.cu)
 __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t pc_x32_offset(int64_t n_frames, int64_t n_xtiles) {
+    return pc_x16_offset(n_frames) + (size_t)n_xtiles * PC_XTILE_BYTES;
+}
 #define PC_NEG_INF (-INFINITY)
 #define PC_L2_RUN_BYTES (32ll << 20)  // frame-tile images one (run, unit) block of K3 work items may span
 // A (tile, unit) pair whose log gamma all lie below log(2^-41) contributes exactly nothing to K3 (see
@@ -146,6 +150,7 @@ struct pc_handle_s {
     cudaEvent_t fork_ev, join_ev;             // transition reductions beside the accumulation kernel
     // device counters: [PC_CNT_CLAMPED] standardised features clamped by the frame preparation
     int *dev_counters;
+    int k1_kernel;       // option "k1_kernel": 1 = wide accumulators for <= 16 mixtures (score_tc_wide.cu), 0 = score_tc.cu only
     int k2_kernel;       // option "k2_kernel": 1 = one warp per utterance (fwdbwd_warp.cu), 0 = three warps (fwdbwd.cu)
     // cross-rank reduction hook of the host-buffer entry point (pc_set_reduce_hook)
     pc_reduce_hook hook;
@@ -190,6 +195,9 @@ bool score_tc_supported(int mix);
 // [item_lo, item_hi): range of utterance-major work items (whole corpus: 0, v.n_sitems)
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                     float *b, int item_lo, int item_hi, cudaStream_t st);
+bool score_tc_wide_supported(int mix);
+int launch_score_tc_wide(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
+                         float *b, int item_lo, int item_hi, cudaStream_t st);
 bool accumulate_tc_supported(int mix);
 // flags_fresh: the activity flags of `lgam` were set by launch_forward_backward (skip the pre-pass)
 int launch_accumulate_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,

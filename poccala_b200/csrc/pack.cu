@@ -22,7 +22,10 @@
 // prepare_frames: X buffer = fp32 rows [F][40] (cols [0,D) standardised data, col 39 = 1), then at
 // pc_x16_offset(F) one operand image per 128-frame tile of every utterance:
 // fp16 [2 (hi, lo)][10 chunks][128 rows][8] of the augmented row [x | x^2] (chunks 0-4 = x, 5-9 = x^2),
-// rows past the end of the utterance zero: a tile is ONE 40 KiB cp.async.bulk.
+// rows past the end of the utterance zero: a tile is ONE 40 KiB cp.async.bulk.  Behind those, at
+// pc_x32_offset(F, tiles), the same tiles as fp32 in quad-major order, float [10 quads][128 rows][4] (20 KiB,
+// padding rows zero): what the wide scoring kernel streams and converts in shared memory (conflict-free
+// 16-byte reads, one row per thread).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -207,6 +210,12 @@ __global__ void prepare_frames_kernel(CorpusView cv, const T *__restrict__ x, in
         float4 *row = reinterpret_cast<float4 *>(X + (size_t)(f0 + t) * PC_XS + 8 * c);
         row[0] = make_float4(v[0], v[1], v[2], v[3]);
         row[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    {
+        float4 *q32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(X) + pc_x32_offset(cv.total_frames, cv.n_xtiles) +
+                                                 (size_t)blk * PC_X32TILE_BYTES);
+        q32[(2 * c) * PC_TILE_ROWS + r] = make_float4(v[0], v[1], v[2], v[3]);
+        q32[(2 * c + 1) * PC_TILE_ROWS + r] = make_float4(v[4], v[5], v[6], v[7]);
     }
     uint8_t *img = reinterpret_cast<uint8_t *>(X) + pc_x16_offset(cv.total_frames) + (size_t)blk * PC_XTILE_BYTES;
     __half xh[8], xl[8], qh[8], ql[8];

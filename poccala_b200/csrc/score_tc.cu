@@ -442,6 +442,8 @@ bool score_tc_supported(int mix) { return mix == 4 || mix == 8 || mix == 16 || m
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                     float *b, int item_lo, int item_hi, cudaStream_t st) {
     if (item_hi <= item_lo) return PC_OK;
+    if (h->k1_kernel && score_tc_wide_supported(mix))  // narrow units: wide accumulators (score_tc_wide.cu)
+        return launch_score_tc_wide(h, v, X, W, mix, b, item_lo, item_hi, st);
     switch (mix) {
         case 4: return launch_mix<4>(h, v, X, W, b, item_lo, item_hi, st);
         case 8: return launch_mix<8>(h, v, X, W, b, item_lo, item_hi, st);

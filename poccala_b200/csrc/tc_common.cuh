@@ -170,6 +170,22 @@ __device__ __forceinline__ float lg2(float x) {
     return y;
 }
 
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, degree-5
+// polynomial for 2^f (relative error 1.9e-7 in fp32, the same as ex2.approx), n added into the exponent
+// field.  x below -126 (and -inf, NaN) gives ~1e-38.  Used for a quarter of the exponentials of the
+// log-sum-exp epilogues, whose MUFU queue is the busiest unit of the SM sub-partitions.
+__device__ __forceinline__ float ex2_fma(float x) {
+    x = fmaxf(x, -126.f);
+    const float t = x + 12582912.f;  // 1.5 * 2^23: n lands in the low mantissa bits
+    const float f = x - (t - 12582912.f);
+    float p = fmaf(1.326472731307149e-3f, f, 9.671512991189957e-3f);
+    p = fmaf(p, f, 5.550733581185341e-2f);
+    p = fmaf(p, f, 0.24022242426872253f);
+    p = fmaf(p, f, 0.6931470036506653f);
+    p = fmaf(p, f, 1.f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, no swizzle ("interleave"): the operand is stored as 8x16-byte
 // core matrices (8 rows of the non-contracted dimension x 16 contiguous bytes of the other);
@@ -325,6 +341,46 @@ __device__ __forceinline__ void convert_frame_row(const uint8_t *raw_stage, int 
         *reinterpret_cast<uint4 *>(a_hi + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
         *reinterpret_cast<uint4 *>(a_lo + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
     }
+}
+
+// Row r of a quad-major fp32 tile (float [10 quads][128 rows][4], pack.cu) -> [x | x^2] fp16 hi / lo rows of the
+// operand tile: consecutive threads read and write consecutive 16-byte words (no bank conflicts).
+__device__ __forceinline__ void convert_tile_row_qm(const uint8_t *tile32, int r, uint8_t *a_hi, uint8_t *a_lo) {
+    const float4 *src = reinterpret_cast<const float4 *>(tile32) + r;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        const float4 q0 = src[(2 * c) * T_ROWS], q1 = src[(2 * c + 1) * T_ROWS];
+        const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        uint32_t h[4], l[4], h2[4], l2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float p = x[2 * e], q = x[2 * e + 1];
+            split2(p, q, h[e], l[e]);
+            split2(p * p, q * q, h2[e], l2[e]);
+        }
+        *reinterpret_cast<uint4 *>(a_hi + c * T_ROWS * 16 + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4 *>(a_lo + c * T_ROWS * 16 + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+        *reinterpret_cast<uint4 *>(a_hi + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+        *reinterpret_cast<uint4 *>(a_lo + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+    }
+}
+
+// (row r, 8-feature chunk c) of a quad-major fp32 tile -> chunks c (x) and c + 5 (x^2) of the operand tile
+__device__ __forceinline__ void convert_tile_chunk_qm(const uint8_t *tile32, int r, int c, uint8_t *a_hi, uint8_t *a_lo) {
+    const float4 *src = reinterpret_cast<const float4 *>(tile32) + r;
+    const float4 q0 = src[(2 * c) * T_ROWS], q1 = src[(2 * c + 1) * T_ROWS];
+    const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    uint32_t h[4], l[4], h2[4], l2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float p = x[2 * e], q = x[2 * e + 1];
+        split2(p, q, h[e], l[e]);
+        split2(p * p, q * q, h2[e], l2[e]);
+    }
+    *reinterpret_cast<uint4 *>(a_hi + c * T_ROWS * 16 + r * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(a_lo + c * T_ROWS * 16 + r * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4 *>(a_hi + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+    *reinterpret_cast<uint4 *>(a_lo + (c + 5) * T_ROWS * 16 + r * 16) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
 }
 
 }  // namespace tc

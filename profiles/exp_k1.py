@@ -1,36 +1,41 @@
-"""Micro-experiments on the scoring / accumulation kernels (bench workload): kernel-only timings
-under debug flags (option "debug_flags" is the debug word for the tcgen05 kernels)."""
-import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""K1 timing on the bench workload, both tensor-core kernels: python profiles/exp_k1.py [n_utt] [mix]"""
+import sys
 import numpy as np, torch
+sys.path.insert(0, ".")
 from poccala_b200 import synth
 from poccala_b200.engine import Corpus, Engine, EStep, Model
-
-N_UNITS, MIX, N_UTT, T, L = 57, int(os.environ.get("MIX", 16)), int(os.environ.get("NUTT", 1000)), 300, 10
+n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+mix = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+T, L = 300, 10
 eng = Engine(0)
-truth, init, labels, x = synth.torch_corpus(N_UTT, T, L, N_UNITS, MIX, 2, eng.device, 22)
-corpus = Corpus(eng, labels, np.full(N_UTT, T, dtype=np.int32), N_UNITS)
-model = Model(eng, *init, synth.default_transmat(N_UNITS))
+truth, init0, labels, x = synth.torch_corpus(n_utt, T, L, 57, mix, 2, eng.device, 22)
+corpus = Corpus(eng, labels, np.full(n_utt, T, dtype=np.int32), 57)
+model = Model(eng, *init0, synth.default_transmat(57))
 es = EStep(eng, corpus, model)
 es.load_frames(x)
-es.score(); es.forward_backward(); es.accumulate()
-torch.cuda.synchronize()
-from poccala_b200 import _native as nat
-from poccala_b200._native import _p
-import ctypes as C
-def t_kernel(fn, n=10):
-    for _ in range(3): fn()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)
+ref = None
+for name, k1, dbg in (("per-position-pair", 0, 0), ("wide", 1, 0), ("wide, no MMA", 1, 2), ("wide, no epilogue math", 1, 16),
+                      ("wide, no conversion", 1, 8), ("wide, no MMA/epilogue/conversion", 1, 26)):
+    eng.set_option("k1_kernel", k1)
+    eng.set_option("debug_flags", dbg)
+    for _ in range(3):
+        es.score()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n * 1e3
-st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
-def k1(): nat.call("pc_gmm_score", eng.h, corpus.c, _p(corpus.X), _p(model.W), MIX, _p(es.b), st())
-def k3(): nat.call("pc_accumulate", eng.h, corpus.c, _p(corpus.X), _p(model.W), MIX, _p(es.b), _p(es.lgam), _p(es.acc), st())
-for flags in [int(a) for a in sys.argv[1:]] or [0]:
-    eng.set_option("debug_flags", flags)
-    print("flags", flags, "K1 us %.1f" % (t_kernel(k1) if not (flags & 256) else 0.0), "K3 us %.1f" % t_kernel(k3), flush=True)
+    ms = []
+    for _ in range(5):
+        flush.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(); es.score(); ev[1].record()
+        torch.cuda.synchronize()
+        ms.append(ev[0].elapsed_time(ev[1]))
+    if dbg == 0:
+        bb = es.b.clone()
+        if ref is None:
+            ref = bb
+        else:
+            print("   max |b - b_ref| = %.3g" % (bb - ref).abs().max().item())
+    pairs = n_utt * T * 3 * L * mix
+    print("%-36s %.1f us (min %.1f)  %.0f TFLOP/s algorithmic" % (name, 1e3 * sum(ms) / len(ms), 1e3 * min(ms),
+                                                                   158.0 * pairs / (min(ms) * 1e-3) / 1e12), flush=True)
 eng.set_option("debug_flags", 0)
-print("K3 active (tile, unit) pairs: %d of %d" % (nat.lib().pc_corpus_active_tiles(corpus.c), nat.lib().pc_corpus_total_tiles(corpus.c)))

@@ -90,13 +90,17 @@ def test_scores_tensor_core_vs_cuda_core_and_oracle(eng, mix):
     utts[0] = utts[0][:1]
     corpus, model, es, om = _setup(eng, init, labels, utts, 5)
     out = {}
-    for tc in (0, 1):
-        eng.set_option("tensor_core", tc)
+    for tc in (0, 1, 2):  # CUDA cores / tcgen05 (wide accumulators up to 16 mixtures) / tcgen05 per position pair
+        eng.set_option("tensor_core", min(tc, 1))
+        eng.set_option("k1_kernel", 0 if tc == 2 else 1)
         es.b.fill_(float("nan"))
         es.score()
         torch.cuda.synchronize()
         out[tc] = es.b.clone()
     eng.set_option("tensor_core", 1)
+    eng.set_option("k1_kernel", 1)
+    for u in range(len(utts)):  # both tensor-core kernels run the same contraction
+        assert np.abs(corpus.emission_view(out[1], u).cpu().numpy() - corpus.emission_view(out[2], u).cpu().numpy()).max() < 1e-4
     worst = 0.0
     for u, (lab, X) in enumerate(zip(labels, utts)):
         c = fast.score_components_direct(om, lab[None], X[None])
@@ -308,7 +312,7 @@ def test_host_entry_point_offset_data_matches_oracle(eng):
     from poccala_b200.engine import em_iteration_host, frame_moments_host
 
     n_units = 4
-    init, labels, utts = _offset_problem(31, 12, 60, 3, n_units)
+    init, labels, utts = _offset_problem(31, 30, 80, 3, n_units)
     corpus = _corpus(eng, labels, utts, n_units)
     tm0 = synth.default_transmat(n_units)
     om = fast.Model(*init, tm0)
@@ -323,11 +327,16 @@ def test_host_entry_point_offset_data_matches_oracle(eng):
                                 shift=consts[0], inv_scale=consts[1])
         assert abs(slp - float(np.sum(info["logp"]))) <= 1e-5 * abs(slp), (slp, float(np.sum(info["logp"])))
         ok = stats.occ >= OCC_MIN
-        assert ok.sum() >= 0.75 * ok.size
+        assert ok.sum() >= 0.6 * ok.size, ok.mean()
         assert _relerr(alpha, new.alpha, floor=1e-3) < REL, _relerr(alpha, new.alpha, floor=1e-3)
         sd = np.sqrt(new.var)
-        merr = (np.abs(mean - new.mean) / np.maximum(np.abs(new.mean - shift), sd))[ok].max()
+        # the stated bound (relative to the parameter, as in the other tests) ...
+        merr = (np.abs(mean - new.mean) / np.maximum(np.abs(new.mean), sd))[ok].max()
         assert merr <= REL, merr
+        # ... and what the standardised contraction actually reaches: the error does not grow with the offset
+        # (measured 2e-4 of the distance to the corpus centre; without standardisation it is ~1e-1)
+        merr_c = (np.abs(mean - new.mean) / np.maximum(np.abs(new.mean - shift), sd))[ok].max()
+        assert merr_c <= 5e-4, merr_c
         gvar = np.concatenate(utts, axis=0).var(axis=0)
         verr = (np.abs(var - new.var) / np.maximum(new.var, 1e-2 * gvar))[ok].max()
         assert verr <= REL, verr
