@@ -5,10 +5,14 @@ HMMs, 16-mix GMMs, 1k synthetic utterances x 300 frames x 10 units, one embedded
 iteration per step.  Weak scaling: every rank owns its own 1k utterances; the only exchange step
 is the NCCL allreduce of the accumulators.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--check] [--cfg5-utt U]
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` the same iteration
-through the host-buffer C-ABI entry point (pc_em_iteration_host) with pinned host inputs.
+through the host-buffer C-ABI entry point (pc_em_iteration_host) with pinned host inputs (at N > 1 with
+the two NCCL collectives inside the call).  Further legs in the same line: `cfg5` = BASELINE.json
+configs[4] (100k utterances over the N ranks, 64-mix, k-means init + 5 EM iterations), at N = 1 also
+`viterbi` (configs[3]) and `scoring_sweep` (configs[2] at 10M frames x 4 096 and 65 536 Gaussians).
+`--check`: the same 2 000 utterances on one rank and on N ranks, models compared (no timing).
 `--impl reference` times the CPU port of the reference (oracle/ref_port.py, the reference's own
 cost structure: /root/reference does not exist on the GPU box) on all host cores.
 """
@@ -65,10 +69,11 @@ def ncu_traffic(stage):
 _CPU = {}
 
 
-def _cpu_init(seed):
+def _cpu_init(seed, mix=None):
     from oracle import ref_port as rp
     from poccala_b200 import synth
 
+    MIX = mix or globals()["MIX"]
     truth = synth.make_truth(N_UNITS, MIX, 1000 * seed + 7)
     init = synth.perturb(*truth, seed=1000 * seed + 11)
     names = [str(i) for i in range(N_UNITS)]
@@ -91,13 +96,13 @@ def _cpu_task(i):
     return time.perf_counter() - t0, float(r["logp"])
 
 
-def cpu_arm(n_utt_sample, cores, seed=2, steps=1):
+def cpu_arm(n_utt_sample, cores, seed=2, steps=1, mix=None):
     """E-step of the reference's CPU path on `n_utt_sample` utterances of the bench workload per
     step, one utterance per task on `cores` processes (AcousticModel.py:861-870).
     Returns (frames/s over all steps, [wall seconds per step])."""
     ctx = mp.get_context("spawn")
     walls = []
-    with ctx.Pool(cores, initializer=_cpu_init, initargs=(seed,)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(seed, mix)) as pool:
         pool.map(_cpu_task, range(cores))  # warm-up: imports, page-in (1 utterance per core)
         for k in range(steps):
             t0 = time.perf_counter()
@@ -201,6 +206,126 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def _init_group(world, local):
+    """NCCL process group of the launch (torchrun environment), or None at world size 1."""
+    import torch
+    import torch.distributed as dist
+
+    if world <= 1:
+        return None
+    # the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout: rank 0 must print ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # ... and whatever NCCL still writes while the communicator comes up goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group = dist.group.WORLD
+        warm = torch.zeros(1, device=torch.device("cuda", local))
+        dist.all_reduce(warm, group=group)
+        dist.all_reduce(warm, op=dist.ReduceOp.MAX, group=group)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return group
+
+
+def run_check(args):
+    """`--check`: the same 2 000 utterances (configs[1] shape) trained for two EM iterations (a) on every
+    rank alone, whole corpus, and (b) sharded over the N ranks (utterance u -> rank u mod N) with the NCCL
+    reductions - through the device-resident path and through the host-buffer entry point with its reduce
+    hook.  Asserts: replicas bit-identical, sharded == single-rank model within 1e-6 relative.  Prints one
+    JSON line; exit code 1 on failure."""
+    import torch
+    import torch.distributed as dist
+
+    from poccala_b200 import synth
+    from poccala_b200.engine import (Corpus, Engine, EStep, HostReduceHook, Model, em_iteration_host,
+                                     frame_moments_host)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    group = _init_group(world, local)
+    eng = Engine(local)
+    dev = eng.device
+    n_all, iters = 2000, 2
+    truth, init0, labels, x = synth.torch_corpus(n_all, T, L, N_UNITS, MIX, 2, dev, N_INITIALS)  # identical on every rank
+    tm0 = synth.default_transmat(N_UNITS)
+
+    def train(sel, grp):
+        xs = x.view(n_all, T, DIM)[sel].reshape(-1, DIM).contiguous()
+        corpus = Corpus(eng, labels[sel], np.full(len(sel), T, dtype=np.int32), N_UNITS)
+        model = Model(eng, init0[0], init0[1], init0[2], tm0)
+        es = EStep(eng, corpus, model)
+        es.load_frames(xs, group=grp)
+        ll = []
+        for _ in range(iters):
+            es.em_iteration(c_covariance=1e-6, group=grp)
+            s_ll = es.utt_logp.sum().reshape(1)
+            if grp is not None:
+                dist.all_reduce(s_ll, group=grp)
+            ll.append(float(s_ll.item()))
+        torch.cuda.synchronize()
+        return [model.mean.clone(), model.var.clone(), model.alpha.clone(), model.transmat.clone()], ll, corpus, xs
+
+    single, ll1, _, _ = train(np.arange(n_all), None)
+    mine = np.arange(rank, n_all, world)
+    sharded, llN, corpus_s, xs = train(mine, group)
+
+    def rel(a, b, floor):
+        return float(((a - b).abs() / b.abs().clamp_min(floor)).max().item())
+
+    names, floors = ("mean", "var", "alpha", "transmat"), (1e-2, 1e-6, 1e-6, 1e-6)
+    diffs = {n: rel(a, b, f) for n, a, b, f in zip(names, sharded, single, floors)}
+    identical = True
+    if group is not None:
+        for t in sharded:
+            hi, lo = t.clone(), t.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            identical = identical and bool((hi == lo).all().item())
+    # host-buffer entry point, one iteration, with the collectives inside the call
+    host_x = xs.cpu().numpy()
+    shift, isc = frame_moments_host(eng, host_x, group=group)
+    hook = HostReduceHook(eng, N_UNITS, N_UNITS * 3 * MIX, group) if group is not None else None
+    hp = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init0] + [tm0.copy()]
+    em_iteration_host(eng, corpus_s, host_x, *hp, c_covariance=1e-6, shift=shift, inv_scale=isc)
+    if hook is not None:
+        if hook.error is not None:
+            raise hook.error
+        hook.remove()
+    # against the single-rank model after ONE iteration
+    model1 = Model(eng, init0[0], init0[1], init0[2], tm0)
+    c1 = Corpus(eng, labels, np.full(n_all, T, dtype=np.int32), N_UNITS)
+    e1 = EStep(eng, c1, model1)
+    e1.load_frames(x)
+    e1.em_iteration(c_covariance=1e-6)
+    torch.cuda.synchronize()
+    ref1 = [model1.mean, model1.var, model1.alpha, model1.transmat]
+    host_diffs = {n: rel(torch.as_tensor(a).to(dev), b, f) for n, a, b, f in zip(names, hp, ref1, floors)}
+    ok = identical and max(diffs.values()) <= 1e-6 and max(host_diffs.values()) <= 1e-5 and \
+        abs(llN[-1] - ll1[-1]) <= 1e-9 * abs(ll1[-1])
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    if group is not None:
+        dist.all_reduce(flag, group=group)
+    ok_all = int(flag.item()) == 0
+    if rank == 0:
+        print(json.dumps({"check": "ok" if ok_all else "FAILED", "n_gpus": world, "utterances": n_all, "iterations": iters,
+                          "replicas_bit_identical": identical, "max_rel_diff_vs_single_rank": diffs,
+                          "host_entry_max_rel_diff_vs_single_rank": host_diffs,
+                          "sum_logp_single": ll1, "sum_logp_sharded": llN}), flush=True)
+    if group is not None:
+        dist.destroy_process_group()
+    if not ok_all:
+        raise SystemExit(1)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -214,26 +339,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the engine has no CPU fallback")
     torch.cuda.set_device(local)
-    group = None
-    if world > 1:
-        # the image exports NCCL_DEBUG=VERSION, whose banner goes to stdout: rank 0 must print ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        # ... and whatever NCCL still writes while the communicator comes up goes to stderr
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            group = dist.group.WORLD
-            warm = torch.zeros(1, device=torch.device("cuda", local))
-            dist.all_reduce(warm, group=group)
-            dist.all_reduce(warm, op=dist.ReduceOp.MAX, group=group)
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+    group = _init_group(world, local)
     eng = Engine(local)
     dev = eng.device
     # every rank starts from the SAME model (replicated parameters) and owns its own utterances
@@ -344,21 +450,32 @@ def run_gpu(args):
     c1.record()
     torch.cuda.synchronize()
     h2d_gbs = 3 * frames * DIM * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    del dst
+    del dst, host_x
+    pk, pk_src = peaks()
+    kern_ms = {"K1_score": statistics.mean(k1), "K2_forward_backward": statistics.mean(k2),
+               "K3_accumulate": statistics.mean(k3)}
+    del es, model, corpus, x
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[4]: every rank takes part (the job is split over the ranks)
+    cfg5 = None
+    if args.cfg5_utt > 0:
+        cfg5 = cfg5_leg(eng, pk, group, world, rank, args.cfg5_utt, sync_all)
 
     if rank != 0:
         if group is not None:
             dist.destroy_process_group()
         return
-    pk, pk_src = peaks()
-    vit = viterbi_leg(eng, pk)
-    sweep = scoring_sweep_leg(eng, pk)
+    vit = sweep = None
+    if world == 1:  # single-GPU configurations of BASELINE.json
+        vit = viterbi_leg(eng, pk)
+        sweep = [scoring_sweep_leg(eng, pk, F=10_000_000, G=g) for g in (4096, 65536)]
     # dominant kernel and its roofline: K1/K3 are contractions, 158 flops per
     # (frame, Gaussian) pair; K2 moves 8 B per (emitting state, frame)
     pairs = frames * 3 * L * MIX
-    kern = {"K1_score": (statistics.mean(k1), "tensor", 158.0 * pairs),
-            "K2_forward_backward": (statistics.mean(k2), "hbm", 8.0 * frames * 3 * L),
-            "K3_accumulate": (statistics.mean(k3), "tensor", 158.0 * pairs)}
+    kern = {"K1_score": (kern_ms["K1_score"], "tensor", 158.0 * pairs),
+            "K2_forward_backward": (kern_ms["K2_forward_backward"], "hbm", 8.0 * frames * 3 * L),
+            "K3_accumulate": (kern_ms["K3_accumulate"], "tensor", 158.0 * pairs)}
     dom = max(kern, key=lambda k: kern[k][0])
     ms, bound, work = kern[dom]
     if bound == "tensor":
@@ -373,10 +490,20 @@ def run_gpu(args):
                          "(K1 stage includes the model packing launch; the 3-product fp16 split executes 3x these "
                          "flops on the tensor pipe); K3 contracts only (tile, unit) pairs with posterior mass: "
                          "%d of %d active" % (active_tiles, total_tiles))}
+    roofline["all_frac"] = {k: (v[2] / (v[0] * 1e-3) / (1e12 * float(pk["bf16_tflops_sustained"]) if v[1] == "tensor"
+                                                       else 1e9 * float(pk["hbm_gbs"]))) for k, v in kern.items()}
     cores = os.cpu_count() or 1
-    n_sample = 2 * cores
-    cpu_v, cpu_walls = cpu_arm(n_sample, cores)
-    cpu_wall = sum(cpu_walls)
+    cpu = {}
+    if world == 1 and not os.environ.get("PC_BENCH_NO_CPU"):
+        n_sample = 2 * cores
+        cpu_v, cpu_walls = cpu_arm(n_sample, cores)
+        cpu = {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d utterances x %d frames of the same workload (E-step), %.1f s" % (n_sample, T, sum(cpu_walls))}
+        if cfg5 is not None:  # the reference CPU path at the configs[4] shape (64 mixtures), for the north-star ratio
+            c5_v, c5_walls = cpu_arm(cores, cores, mix=64)
+            cfg5["cpu_baseline"] = {"value": c5_v, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": "%d utterances x %d frames, 64-mix (E-step), %.1f s" % (cores, T, sum(c5_walls))}
+            cfg5["speedup_vs_cpu"] = cfg5["value"] / c5_v
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -390,20 +517,21 @@ def run_gpu(args):
                 "collectives_inside": world > 1},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "cfg5": cfg5,
         "viterbi": vit,
         "scoring_sweep": sweep,
-        "cpu_baseline": {"value": cpu_v, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d utterances x %d frames of the same workload (E-step), %.1f s" % (n_sample, T, cpu_wall)},
+        "cpu_baseline": cpu or None,
     }
     print(json.dumps(line), flush=True)
     if group is not None:
         dist.destroy_process_group()
 
 
-def scoring_sweep_leg(eng, pk, F=2_000_000, G=4096, mix=64):
-    """BASELINE.json configs[2] (GMM scoring sweep) on one GPU at a bounded size: F frames x G
-    39-dim diagonal Gaussians, 64 mixtures per state, through the tcgen05 scoring kernel
-    (Engine.score_dense_tc's layout; profiles/bench_cfg3.py runs the full 4k-64k sweep).
+def scoring_sweep_leg(eng, pk, F=10_000_000, G=4096, mix=64, slab=2_500_000):
+    """BASELINE.json configs[2] (GMM scoring sweep) on one GPU: F frames x G 39-dim diagonal Gaussians, 64
+    mixtures per state, through the tcgen05 scoring kernel (Engine.score_dense_tc's layout), in slabs of
+    `slab` frames so that the emission buffer stays bounded (F x G / 64 floats: 41 GB at 65 536 Gaussians).
+    Every slab's frames are prepared before its timed launch (inputs resident in HBM, larger than L2).
     Tensor roofline: 158 flop per (frame, Gaussian) pair against the measured bf16 peak (the 3-product
     fp16 split executes 3x these flops)."""
     import torch
@@ -414,7 +542,6 @@ def scoring_sweep_leg(eng, pk, F=2_000_000, G=4096, mix=64):
     dev = eng.device
     gen = torch.Generator(device=dev)
     gen.manual_seed(3)
-    x = torch.randn((F, DIM), generator=gen, device=dev, dtype=torch.float32)
     mean = torch.randn((G, DIM), generator=gen, device=dev, dtype=torch.float64)
     var = torch.rand((G, DIM), generator=gen, device=dev, dtype=torch.float64) + 0.5
     alpha = torch.full((G,), 1.0 / mix, device=dev, dtype=torch.float64)
@@ -424,32 +551,148 @@ def scoring_sweep_leg(eng, pk, F=2_000_000, G=4096, mix=64):
         mean = torch.cat([mean, torch.zeros((pad, DIM), dtype=mean.dtype, device=dev)])
         var = torch.cat([var, torch.ones((pad, DIM), dtype=var.dtype, device=dev)])
         alpha = torch.cat([alpha, torch.zeros((pad,), dtype=alpha.dtype, device=dev)])
-    n_frames = np.full((F + 383) // 384, 384, dtype=np.int32)
-    if F % 384:
-        n_frames[-1] = F % 384
+    slab = min(slab, F)
+    n_slabs = (F + slab - 1) // slab
+    n_frames = np.full((slab + 383) // 384, 384, dtype=np.int32)
+    if slab % 384:
+        n_frames[-1] = slab % 384
     labels = np.ascontiguousarray(np.broadcast_to(np.arange(U, dtype=np.int32), (len(n_frames), U)))
     corpus = Corpus(eng, labels, n_frames, U)
     W = eng.pack_gmm(mean, var, alpha, mix=mix)
-    X = eng.prepare_frames(corpus, x)
     b = eng.empty((corpus.emis_floats,), torch.float32)
-
-    def run():
+    X = None
+    total_ms = 0.0
+    for k in range(n_slabs + 1):  # slab 0 runs twice: the first pass is the warm-up
+        x = torch.randn((slab, DIM), generator=gen, device=dev, dtype=torch.float32)
+        X = eng.prepare_frames(corpus, x, out=X)
+        del x
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         nat.call("pc_gmm_score", eng.h, corpus.c, _p(X), _p(W), mix, _p(b), _stream())
+        e1.record()
+        torch.cuda.synchronize()
+        if k > 0:
+            total_ms += e0.elapsed_time(e1)
+    frames = n_slabs * slab
+    tf = 158.0 * frames * G / (total_ms * 1e-3) / 1e12
+    peak = float(pk["bf16_tflops_sustained"])
+    del corpus, W, X, b
+    torch.cuda.empty_cache()
+    return {"value": frames / (total_ms * 1e-3), "unit": "frames/s", "ms": total_ms,
+            "workload": "cfg3: %d frames x %d Gaussians (39-dim diag, %d-mix) in %d launches of %d frames, inputs larger "
+                        "than L2" % (frames, G, mix, n_slabs, slab),
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak}}
 
-    run()
+
+def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=64, em_iters=5, kmeans_points=4096):
+    """BASELINE.json configs[4]: data-parallel EM on `n_total` synthetic utterances (100k) split over the
+    ranks, 64-mix IF HMMs: uniform segmentation -> per-state k-means (K = 64, the 171 states sharded over the
+    ranks, parameters all-gathered) -> 5 Baum-Welch iterations with the NCCL accumulator all-reduce.  The
+    k-means runs on the first `kmeans_points` frames of every state pooled over the ranks: the reference's
+    greedy algorithm (and the bit-exact device kernel) costs O(N^2 / K) per state, 175k frames per state
+    would take minutes - the cap is part of the workload string.  Device times, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from poccala_b200 import _native as nat
+    from poccala_b200 import synth
+    from poccala_b200.engine import (EMIT, Corpus, EStep, Model, gather_state_data, group_frames, kmeans_states,
+                                     segment_keys)
+
+    dev = eng.device
+    n_utt = n_total // world
+    truth, _, labels, x = synth.torch_corpus(n_utt, T5, L5, N_UNITS, mix, 5, dev, N_INITIALS, data_seed=5 + rank)
+    corpus = Corpus(eng, labels, np.full(n_utt, T5, dtype=np.int32), N_UNITS)
+    S = N_UNITS * EMIT
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if group is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        return float(t.item())
+
+    # ---- initialisation (AcousticModel.process_data(mode=1, init=True) + __cal_gmm's k-means)
+    sync_all()
+    t0 = time.perf_counter()
+    key, _ = segment_keys(eng, corpus, None)  # uniform segmentation, three-way split
+    grouped = group_frames(eng, key, S, x.double())
+    data, key_off = gather_state_data(eng, grouped["data"], grouped["key_off"], group, max_points=kmeans_points)
+    del grouped
     torch.cuda.synchronize()
+    t_seg = max_over_ranks(time.perf_counter() - t0)
+    sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
-    for _ in range(3):
-        run()
+    km = kmeans_states(eng, data, key_off, mix, group)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    tf = 158.0 * F * G / (ms * 1e-3) / 1e12
-    peak = float(pk["bf16_tflops_sustained"])
-    return {"value": F / (ms * 1e-3), "unit": "frames/s", "ms": ms,
-            "workload": "cfg3 shape: %d frames x %d Gaussians (39-dim diag, %d-mix), inputs larger than L2" % (F, G, mix),
-            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak}}
+    t_km = max_over_ranks(time.perf_counter() - t0)
+    km_dev_ms = max_over_ranks(e0.elapsed_time(e1))  # includes the host-side seeding draws between the launches
+    pts = np.diff(key_off)
+    passes = km["passes"].cpu().numpy()
+    # K5 traffic: every pass runs up to K masked arg-mins over the state's points, 8 B coordinate + 1 B owner each
+    scan_bytes = float(np.sum(passes[km["states"]] * mix * pts[km["states"]] * 9.0)) if km["states"] else 0.0
+    mean = km["mean"].cpu().numpy().reshape(N_UNITS, EMIT, mix, -1)
+    var = np.maximum(km["var"].cpu().numpy().reshape(N_UNITS, EMIT, mix, -1), 1e-2)
+    alpha = km["alpha"].cpu().numpy().reshape(N_UNITS, EMIT, mix)
+    alpha = alpha / alpha.sum(-1, keepdims=True)
+    del data, km
+
+    # ---- EM
+    model = Model(eng, mean, var, alpha, synth.default_transmat(N_UNITS))
+    es = EStep(eng, corpus, model)
+    es.load_frames(x, group=group)
+    del x
+    es.em_iteration(c_covariance=1e-3, group=group)  # warm-up (first launches, NCCL buffers); its update is kept
+    ms, ll = [], []
+    for it in range(em_iters):
+        sync_all()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        es.em_iteration(c_covariance=1e-3, group=group)
+        a1.record()
+        torch.cuda.synchronize()
+        ms.append(max_over_ranks(a0.elapsed_time(a1)))
+        s_ll = es.utt_logp.sum().reshape(1)
+        if group is not None:
+            dist.all_reduce(s_ll, group=group)
+        ll.append(float(s_ll.item()))
+    # stage split of one more iteration (events on the launch stream)
+    sync_all()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record(); es.log_bands_async(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
+    es.reduce_transitions_async(group); es.accumulate(); ev[3].record()
+    es.reduce_statistics(group); es.mstep(c_covariance=1e-3); ev[4].record()
+    torch.cuda.synchronize()
+    stage = {"K1_score": ev[0].elapsed_time(ev[1]), "K2_forward_backward": ev[1].elapsed_time(ev[2]),
+             "K3_accumulate": ev[2].elapsed_time(ev[3]), "reduce_mstep": ev[3].elapsed_time(ev[4])}
+    stage = {k: max_over_ranks(v) for k, v in stage.items()}
+    active = nat.lib().pc_corpus_active_tiles(corpus.c) / max(nat.lib().pc_corpus_total_tiles(corpus.c), 1)
+    frames_rank = n_utt * T5
+    pairs = frames_rank * EMIT * L5 * mix
+    tpeak, hpeak = 1e12 * float(pk["bf16_tflops_sustained"]), 1e9 * float(pk["hbm_gbs"])
+    it_ms = statistics.mean(ms)
+    out = {
+        "workload": "cfg5: %d utterances x %d frames x %d IF units over %d GPU(s) (%d per rank), %d-mix, uniform "
+                    "segmentation + per-state k-means (K = %d, <= %d pooled frames per state, states sharded over the "
+                    "ranks) + %d EM iterations with NCCL all-reduce" % (n_utt * world, T5, L5, world, n_utt, mix, mix,
+                                                                        kmeans_points, em_iters),
+        "n_gpus": world, "value": world * frames_rank / (it_ms * 1e-3), "unit": "frames/s",
+        "ms_per_iteration": it_ms, "em_ms": ms, "stage_ms": stage,
+        "roofline_frac": {"K1_score": 158.0 * pairs / (stage["K1_score"] * 1e-3) / tpeak,
+                          "K2_forward_backward": 8.0 * frames_rank * EMIT * L5 / (stage["K2_forward_backward"] * 1e-3) / hpeak,
+                          "K3_accumulate": 158.0 * pairs / (stage["K3_accumulate"] * 1e-3) / tpeak},
+        "kmeans": {"wall_s": t_km, "device_ms": km_dev_ms, "states": S, "points": int(pts.sum()),
+                   "passes_max": int(passes.max()) if len(passes) else 0,
+                   "scan_gbs": scan_bytes / max(km_dev_ms * 1e-3, 1e-9) / 1e9,
+                   "bound": "latency: K dependent masked arg-mins per pass over shared-memory resident points"},
+        "segmentation_s": t_seg, "sum_logp": ll, "k3_active_pair_frac": active,
+    }
+    del es, model, corpus
+    torch.cuda.empty_cache()
+    return out
 
 
 def viterbi_leg(eng, pk, n_utt=10000, T_v=1000, L_v=20, reps=5):
@@ -515,9 +758,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--check", action="store_true", help="N-rank vs 1-rank model agreement instead of timing")
+    ap.add_argument("--cfg5-utt", type=int, default=int(os.environ.get("PC_BENCH_CFG5_UTT", "100000")),
+                    help="utterances of the configs[4] leg over all ranks (0 = skip the leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.check:
+        run_check(args)
     else:
         run_gpu(args)
 

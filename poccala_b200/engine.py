@@ -574,6 +574,84 @@ def kmeans_run(engine, x, point_off, k, seeds, max_passes=1 << 40):
     return out
 
 
+def gather_state_data(engine, data, key_off, group=None, max_points=None):
+    """Per-(unit, state) data sets across ranks.  Every rank has grouped the frames of ITS utterances by
+    state (`group_frames`); the reference pools the segments of all machines per unit on a shared file
+    system before k-means (AcousticModel.py:532-561, Controller.py:47-106).  Here every rank contributes
+    its first ceil(max_points / R) frames of each state and one all-gather hands every rank the pooled
+    (capped) sets, rank-major.  Returns (data [P, D] fp64 device tensor, key_off host int64 [S + 1])."""
+    key_off = np.asarray(key_off, dtype=np.int64)
+    S = len(key_off) - 1
+    R = 1 if group is None else torch.distributed.get_world_size(group)
+    counts = np.diff(key_off)
+    if max_points is None and R == 1:
+        return data, key_off
+    q = int(counts.max()) if max_points is None else int(-(-int(max_points) // R))
+    D = data.shape[1]
+    take = np.minimum(counts, q)
+    if R == 1:
+        sel = torch.cat([torch.arange(int(key_off[s]), int(key_off[s] + take[s]), device=data.device) for s in range(S)])
+        return data[sel].contiguous(), np.concatenate([[0], np.cumsum(take)]).astype(np.int64)
+    local = torch.zeros((S, q, D), dtype=data.dtype, device=data.device)
+    for s in range(S):
+        if take[s]:
+            local[s, :int(take[s])] = data[int(key_off[s]):int(key_off[s] + take[s])]
+    cnt = torch.as_tensor(take.astype(np.int64)).to(data.device)
+    all_cnt = torch.empty((R, S), dtype=torch.int64, device=data.device)
+    all_dat = torch.empty((R, S, q, D), dtype=data.dtype, device=data.device)
+    torch.distributed.all_gather_into_tensor(all_cnt, cnt, group=group)
+    torch.distributed.all_gather_into_tensor(all_dat, local, group=group)
+    all_cnt = all_cnt.cpu().numpy()
+    parts, off = [], [0]
+    for s in range(S):
+        n_s = 0
+        for r in range(R):
+            c = int(all_cnt[r, s])
+            if c:
+                parts.append(all_dat[r, s, :c])
+                n_s += c
+        off.append(off[-1] + n_s)
+    return torch.cat(parts).contiguous(), np.asarray(off, dtype=np.int64)
+
+
+def kmeans_states(engine, data, key_off, k, group=None, seed_rng=None):
+    """k-means initialisation of every (unit, state) data set (ClusterInitialization.kmeans(algorithm=1),
+    AcousticModel.py:553-554) with the STATES sharded over the ranks of `group` (state s -> rank s mod R:
+    the problems are independent) and the parameters summed into place on every rank (disjoint
+    supports: the all-reduce is an all-gather).  `data` / `key_off`: the pooled sets (`gather_state_data`),
+    identical on every rank.  seed_rng(s) -> the `random.Random` that draws state s's seeds (the reference
+    uses the module-level generator).  Returns dict(mean [S,k,D], var [S,k,D], alpha [S,k], passes [S])."""
+    import random as _random
+
+    key_off = np.asarray(key_off, dtype=np.int64)
+    S = len(key_off) - 1
+    D = data.shape[1]
+    R, rank = 1, 0
+    if group is not None:
+        R, rank = torch.distributed.get_world_size(group), torch.distributed.get_rank(group)
+    mine = [s for s in range(S) if s % R == rank and key_off[s + 1] - key_off[s] >= k]
+    dev = engine.device
+    mean = torch.zeros((S, k, D), dtype=torch.float64, device=dev)
+    var = torch.zeros((S, k, D), dtype=torch.float64, device=dev)
+    alpha = torch.zeros((S, k), dtype=torch.float64, device=dev)
+    passes = torch.zeros((S,), dtype=torch.int64, device=dev)
+    if mine:
+        sub = torch.cat([data[int(key_off[s]):int(key_off[s + 1])] for s in mine]).contiguous()
+        sub_off = np.concatenate([[0], np.cumsum([key_off[s + 1] - key_off[s] for s in mine])]).astype(np.int64)
+        x0 = sub[:, 0].cpu().numpy()
+        seeds = [kmeans_seed_points(np.ascontiguousarray(x0[sub_off[i]:sub_off[i + 1]]), k,
+                                    seed_rng(s) if seed_rng is not None else _random.Random(s))
+                 for i, s in enumerate(mine)]
+        out = kmeans_run(engine, sub, sub_off, k, np.array(seeds, dtype=np.int32))
+        idx = torch.as_tensor(np.asarray(mine, dtype=np.int64)).to(dev)
+        mean[idx], var[idx], alpha[idx] = out["mean"], out["var"], out["alpha"]
+        passes[idx] = out["passes"].to(torch.int64)
+    if group is not None:
+        for t in (mean, var, alpha, passes):
+            torch.distributed.all_reduce(t, group=group)
+    return dict(mean=mean, var=var, alpha=alpha, passes=passes, states=mine)
+
+
 # ---- alignment post-processing (SURVEY.md §8 f3) ------------------------------------------------
 def segment_keys(engine, corpus, path=None):
     """pc_segment_keys: per corpus frame the data set it joins, key = unit * 3 + emitting state, or -1.
