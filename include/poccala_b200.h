@@ -68,7 +68,8 @@ int pc_destroy(pc_handle h);
  * depth of pc_em_iteration_host (0 = 8); "debug_flags" is a tuning aid for the tcgen05 kernels (skip
  * stages, record block 0's phase clocks); "k1_kernel" 1 (default) = scoring kernel with wide accumulators
  * (several label positions per tcgen05 accumulator) for units of <= 16 mixtures, 0 = the per-position-pair
- * kernel for every mixture count; "k2_kernel" 1 (default) = one warp per utterance, posteriors
+ * kernel for every mixture count; "k3_kernel" 1 (default) = accumulation kernel with the Gaussians on the
+ * accumulator lanes and gathered 32-frame blocks, 0 = one (128-frame tile, unit) pair at a time; "k2_kernel" 1 (default) = one warp per utterance, posteriors
  * normalised by the utterance likelihood; 0 = three warps per utterance with a per-frame normaliser (the
  * tests cross-check both); read-only: "launches" (kernels launched), "sm_count", "clamped" (standardised
  * feature values the frame preparation had to clamp to +-240 since the counter was last read: synchronises

@@ -51,6 +51,7 @@ int pc_create(int device, pc_handle *out) {
     h->use_tc = 1;
     h->k2_kernel = 1;
     h->k1_kernel = 1;
+    h->k3_kernel = 1;
     if (cudaMalloc((void **)&h->dev_counters, PC_CNT_N * sizeof(int)) != cudaSuccess ||
         cudaMemset(h->dev_counters, 0, PC_CNT_N * sizeof(int)) != cudaSuccess) {
         pc_set_error("pc_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -86,6 +87,7 @@ int pc_set_option(pc_handle h, const char *key, int64_t value) {
     if (!strcmp(key, "launches")) { h->launches = value; return PC_OK; }
     if (!strcmp(key, "k2_kernel")) { h->k2_kernel = (int)value; return PC_OK; }
     if (!strcmp(key, "k1_kernel")) { h->k1_kernel = (int)value; return PC_OK; }
+    if (!strcmp(key, "k3_kernel")) { h->k3_kernel = (int)value; return PC_OK; }
     pc_set_error("pc_set_option: unknown key '%s'", key);
     return PC_ERR_INVALID;
 }
@@ -99,6 +101,7 @@ int64_t pc_get_option(pc_handle h, const char *key) {
     if (!strcmp(key, "sm_count")) return h->sm_count;
     if (!strcmp(key, "k2_kernel")) return h->k2_kernel;
     if (!strcmp(key, "k1_kernel")) return h->k1_kernel;
+    if (!strcmp(key, "k3_kernel")) return h->k3_kernel;
     if (!strcmp(key, "clamped")) {
         const int idx = PC_CNT_CLAMPED;
         int n = 0;
@@ -560,6 +563,8 @@ int pc_accumulate(pc_handle h, pc_corpus c, const float *X, const float *W, int3
     // gives; log gamma from anywhere else (or a second pass) goes through the pre-pass
     const bool fresh = c->flags_lgam == lgam && !(h->debug_flags & 2048);
     c->flags_lgam = nullptr;
+    if (h->use_tc && h->k3_kernel && accumulate_tcx_supported(mix))
+        return launch_accumulate_tcx(h, c->v, X, W, mix, b, lgam, acc, fresh, (cudaStream_t)stream);
     if (h->use_tc && accumulate_tc_supported(mix))
         return launch_accumulate_tc(h, c->v, X, W, mix, b, lgam, acc, fresh, (cudaStream_t)stream);
     return launch_accumulate_simt(h, c->v, X, W, mix, b, lgam, acc, (cudaStream_t)stream);
@@ -901,7 +906,9 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     PC_CUDA_TRY(cudaEventRecord(h->join_ev, h->copy_stream));
     if (!(fix_code & 2))
     {
-        if (h->use_tc && accumulate_tc_supported(mix)) {
+        if (h->use_tc && h->k3_kernel && accumulate_tcx_supported(mix)) {
+            if ((rc = launch_accumulate_tcx(h, c->v, X, W, mix, b, lg, acc, true, st))) return rc;
+        } else if (h->use_tc && accumulate_tc_supported(mix)) {
             if ((rc = launch_accumulate_tc(h, c->v, X, W, mix, b, lg, acc, true, st))) return rc;
         } else if ((rc = launch_accumulate_simt(h, c->v, X, W, mix, b, lg, acc, st))) {
             return rc;

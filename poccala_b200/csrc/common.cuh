@@ -8,8 +8,9 @@
 #include "../../include/poccala_b200.h"
 
 #define PC_TILE_ROWS 128  // frames per work tile (one tcgen05 M=128 accumulator block)
+#define PC_BLOCK_ROWS 32  // frames per activity block: K3 gathers the blocks of a tile that carry posterior mass
 #define PC_XTILE_BYTES (2 * (PC_KA / 8) * PC_TILE_ROWS * 16)  // one frame-tile operand image (40 KiB)
-#define PC_X32TILE_BYTES (PC_TILE_ROWS * PC_XS * 4)           // one frame tile as fp32, quad-major [10][128 rows][4] (20 KiB)
+#define PC_X32TILE_BYTES (PC_TILE_ROWS * PC_XS * 4)           // one frame tile as fp32, [4 blocks][10 quads][32 rows][4] (20 KiB)
 #define PC_WGROUP_BYTES (2 * (PC_KA / 8) * 128)               // 8 Gaussian rows of a unit image (2560 B)
 
 // byte offsets of the fp16 operand images inside the W / X buffers (pack.cu)
@@ -56,7 +57,7 @@ struct CorpusView {
     const int32_t *item_unit;     // [n_items]
     float *scratch0;              // [total_frames] float4 per frame (K2 scratch: beta_hat of the entry state)
     float *scratch1;              // [emission floats] K2 scratch: beta_hat rows, same layout as b / lgam
-    int32_t *tile_active;         // [n_tiles] K3 scratch: 1 = the tile carries posterior mass
+    int32_t *tile_active;         // [n_tiles] K3 scratch: bit k = the tile's 32-frame block k carries posterior mass
     const int32_t *tile_item;     // [n_tiles] work item of each unit-major tile
     int32_t *item_act;            // [n_items + 1] K3 scratch, directly behind tile_active: active tiles of the item; [n_items] = block ticket counter
     int32_t *item_order;          // [n_items] K3 scratch: items sorted by active tiles, heaviest first
@@ -151,6 +152,7 @@ struct pc_handle_s {
     // device counters: [PC_CNT_CLAMPED] standardised features clamped by the frame preparation
     int *dev_counters;
     int k1_kernel;       // option "k1_kernel": 1 = wide accumulators for <= 16 mixtures (score_tc_wide.cu), 0 = score_tc.cu only
+    int k3_kernel;       // option "k3_kernel": 1 = Gaussians on the accumulator lanes, gathered frame blocks (accumulate_tcx.cu), 0 = accumulate_tc.cu
     int k2_kernel;       // option "k2_kernel": 1 = one warp per utterance (fwdbwd_warp.cu), 0 = three warps (fwdbwd.cu)
     // cross-rank reduction hook of the host-buffer entry point (pc_set_reduce_hook)
     pc_reduce_hook hook;
@@ -202,6 +204,9 @@ bool accumulate_tc_supported(int mix);
 // flags_fresh: the activity flags of `lgam` were set by launch_forward_backward (skip the pre-pass)
 int launch_accumulate_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                          const float *b, const float *lgam, double *acc, bool flags_fresh, cudaStream_t st);
+bool accumulate_tcx_supported(int mix);
+int launch_accumulate_tcx(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
+                          const float *b, const float *lgam, double *acc, bool flags_fresh, cudaStream_t st);
 int launch_score_dense_simt(pc_handle h, const float *X, int64_t n, const float *W, int n_states,
                             int mix, float *out, cudaStream_t st);
 int launch_accumulate_simt(pc_handle h, const CorpusView &v, const float *X, const float *W,

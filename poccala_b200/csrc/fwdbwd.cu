@@ -426,7 +426,7 @@ fwdbwd_kernel(CorpusView v, const float *__restrict__ b, const double *__restric
                 if (kind[q] == 1 && col[q] % PC_EMIT == 0) {
                     const int s = lane * SPL + q;
                     const float m = fmaxf(fmaxf(sm->tmx_row[s], sm->tmx_row[s + 1]), sm->tmx_row[s + 2]);
-                    flag0[q][k_tile] = m > PC_ACTIVE_MIN_LGAM ? 1 : 0;
+                    flag0[q][k_tile] = m > PC_ACTIVE_MIN_LGAM ? 0xF : 0;  // (per-tile resolution: every 32-frame block)
                 }
                 tmx[q] = PC_NEG_INF;
             }

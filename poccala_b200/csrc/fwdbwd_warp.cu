@@ -296,8 +296,9 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
     }
     if (trace) g_fw_dbg[2] = clock64();
 
-    // K3's activity flags: every (tile, position) flag is written exactly once per run, 0 or 1, by the
-    // lane that holds the position's first state; the maxima of the position's other two states arrive by shuffle
+    // K3's activity flags: every (tile, position) flag is written exactly once per run by the lane that holds
+    // the position's first state (the maxima of the position's other two states arrive by shuffle): bit k =
+    // the 32-frame block k of the tile carries posterior mass (some log gamma above PC_ACTIVE_MIN_LGAM)
     int32_t *flag0[SPL];  // -> flag of (tile 0, this state's position); the pair's tiles are consecutive
 #pragma unroll
     for (int q = 0; q < SPL; ++q)
@@ -307,18 +308,27 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
 #pragma unroll
         for (int q = 0; q < SPL; ++q) y[q] = (q + 1 < SPL) ? x[(q + 1) % SPL] : up;
     };
-    auto flag_tile = [&](int k_tile) {
+    int tmask[SPL];
+#pragma unroll
+    for (int q = 0; q < SPL; ++q) tmask[q] = 0;
+    // end of the 32-frame block that holds frame t (t = 31 mod 32, or the utterance's last frame)
+    auto flag_block = [&](int t) {
         float m1[SPL], m2[SPL];
         next_state(tmx, m1);
         next_state(m1, m2);
+        const int bit = 1 << ((t / PC_BLOCK_ROWS) & (PC_TILE_ROWS / PC_BLOCK_ROWS - 1));
+        const bool tile_end = (t & (PC_TILE_ROWS - 1)) == PC_TILE_ROWS - 1 || t == T - 1;
 #pragma unroll
         for (int q = 0; q < SPL; ++q) {
-            if (kind[q] == 1 && col[q] % PC_EMIT == 0)
-                flag0[q][k_tile] = fmaxf(fmaxf(tmx[q], m1[q]), m2[q]) > PC_ACTIVE_MIN_LGAM ? 1 : 0;
+            if (fmaxf(fmaxf(tmx[q], m1[q]), m2[q]) > PC_ACTIVE_MIN_LGAM) tmask[q] |= bit;
             tmx[q] = PC_NEG_INF;
+            if (tile_end) {
+                if (kind[q] == 1 && col[q] % PC_EMIT == 0) flag0[q][t / PC_TILE_ROWS] = tmask[q];
+                tmask[q] = 0;
+            }
         }
     };
-    if (T == 1) flag_tile(0);
+    if (T == 1) flag_block(0);
     __syncwarp();  // lane 0's per-frame records are read by every lane below
 
     // ------------------------------------------------------------------ forward (LHMM.py:335-351)
@@ -432,8 +442,8 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
 #pragma unroll
                     for (int q = 0; q < SPL; ++q) ah[q] = raw[q] + es[k][q] - r;
                 }
-                // a tile's last frame, t = 127 mod 128, sits at k = CH - 2 of its chunk (chunks start at t = 1 mod CH)
-                if (k == CH - 2 && valid && (t & (PC_TILE_ROWS - 1)) == PC_TILE_ROWS - 1) flag_tile(t / PC_TILE_ROWS);
+                // a block's last frame, t = 31 mod 32, sits at k = CH - 2 of its chunk (chunks start at t = 1 mod CH)
+                if (k == CH - 2 && valid && (t & (PC_BLOCK_ROWS - 1)) == PC_BLOCK_ROWS - 1) flag_block(t);
             }
             // expected counts: log-sum-exp over the chunk with one shared reference per state (branch-free)
 #pragma unroll
@@ -464,7 +474,7 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
         };
         while (tau_lo + CH - 1 <= T - 1) chunk(std::true_type{});
         if (tau_lo <= T - 1) chunk(std::false_type{});
-        if (T > 1 && ((T - 1) & (PC_TILE_ROWS - 1)) != PC_TILE_ROWS - 1) flag_tile((T - 1) / PC_TILE_ROWS);  // the last, partial tile
+        if (T > 1 && ((T - 1) & (PC_BLOCK_ROWS - 1)) != PC_BLOCK_ROWS - 1) flag_block(T - 1);  // the last, partial block
     }
     // the move counts were collected at the destination state: state s's "next" count sits with state s + 1
     {

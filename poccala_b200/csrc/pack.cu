@@ -23,9 +23,10 @@
 // pc_x16_offset(F) one operand image per 128-frame tile of every utterance:
 // fp16 [2 (hi, lo)][10 chunks][128 rows][8] of the augmented row [x | x^2] (chunks 0-4 = x, 5-9 = x^2),
 // rows past the end of the utterance zero: a tile is ONE 40 KiB cp.async.bulk.  Behind those, at
-// pc_x32_offset(F, tiles), the same tiles as fp32 in quad-major order, float [10 quads][128 rows][4] (20 KiB,
-// padding rows zero): what the wide scoring kernel streams and converts in shared memory (conflict-free
-// 16-byte reads, one row per thread).
+// pc_x32_offset(F, tiles), the same tiles as fp32, float [4 blocks][10 quads][32 rows][4] (20 KiB, padding rows
+// zero): what the scoring kernel for narrow units and the accumulation kernel stream and convert in shared
+// memory (conflict-free 16-byte reads, one row per thread); a 32-row block is one contiguous 5 KiB piece, the
+// unit in which the accumulation kernel gathers the frames that carry posterior mass.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -214,8 +215,10 @@ __global__ void prepare_frames_kernel(CorpusView cv, const T *__restrict__ x, in
     {
         float4 *q32 = reinterpret_cast<float4 *>(reinterpret_cast<uint8_t *>(X) + pc_x32_offset(cv.total_frames, cv.n_xtiles) +
                                                  (size_t)blk * PC_X32TILE_BYTES);
-        q32[(2 * c) * PC_TILE_ROWS + r] = make_float4(v[0], v[1], v[2], v[3]);
-        q32[(2 * c + 1) * PC_TILE_ROWS + r] = make_float4(v[4], v[5], v[6], v[7]);
+        // [4 blocks of 32 rows][10 quads][32 rows][4 floats]: a 32-row block is one contiguous 5 KB piece
+        float4 *blk32 = q32 + (r / PC_BLOCK_ROWS) * (PC_BLOCK_ROWS * PC_XS / 4) + (r % PC_BLOCK_ROWS);
+        blk32[(2 * c) * PC_BLOCK_ROWS] = make_float4(v[0], v[1], v[2], v[3]);
+        blk32[(2 * c + 1) * PC_BLOCK_ROWS] = make_float4(v[4], v[5], v[6], v[7]);
     }
     uint8_t *img = reinterpret_cast<uint8_t *>(X) + pc_x16_offset(cv.total_frames) + (size_t)blk * PC_XTILE_BYTES;
     __half xh[8], xl[8], qh[8], ql[8];

@@ -343,13 +343,14 @@ __device__ __forceinline__ void convert_frame_row(const uint8_t *raw_stage, int 
     }
 }
 
-// Row r of a quad-major fp32 tile (float [10 quads][128 rows][4], pack.cu) -> [x | x^2] fp16 hi / lo rows of the
+// Row r of an fp32 tile (float [4 blocks][10 quads][32 rows][4], pack.cu) -> [x | x^2] fp16 hi / lo rows of the
 // operand tile: consecutive threads read and write consecutive 16-byte words (no bank conflicts).
 __device__ __forceinline__ void convert_tile_row_qm(const uint8_t *tile32, int r, uint8_t *a_hi, uint8_t *a_lo) {
-    const float4 *src = reinterpret_cast<const float4 *>(tile32) + r;
+    const float4 *src = reinterpret_cast<const float4 *>(tile32) + (r / PC_BLOCK_ROWS) * (PC_BLOCK_ROWS * PC_XS / 4) +
+                        (r % PC_BLOCK_ROWS);
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-        const float4 q0 = src[(2 * c) * T_ROWS], q1 = src[(2 * c + 1) * T_ROWS];
+        const float4 q0 = src[(2 * c) * PC_BLOCK_ROWS], q1 = src[(2 * c + 1) * PC_BLOCK_ROWS];
         const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         uint32_t h[4], l[4], h2[4], l2[4];
 #pragma unroll
@@ -365,10 +366,11 @@ __device__ __forceinline__ void convert_tile_row_qm(const uint8_t *tile32, int r
     }
 }
 
-// (row r, 8-feature chunk c) of a quad-major fp32 tile -> chunks c (x) and c + 5 (x^2) of the operand tile
+// (row r, 8-feature chunk c) of an fp32 tile -> chunks c (x) and c + 5 (x^2) of the operand tile
 __device__ __forceinline__ void convert_tile_chunk_qm(const uint8_t *tile32, int r, int c, uint8_t *a_hi, uint8_t *a_lo) {
-    const float4 *src = reinterpret_cast<const float4 *>(tile32) + r;
-    const float4 q0 = src[(2 * c) * T_ROWS], q1 = src[(2 * c + 1) * T_ROWS];
+    const float4 *src = reinterpret_cast<const float4 *>(tile32) + (r / PC_BLOCK_ROWS) * (PC_BLOCK_ROWS * PC_XS / 4) +
+                        (r % PC_BLOCK_ROWS);
+    const float4 q0 = src[(2 * c) * PC_BLOCK_ROWS], q1 = src[(2 * c + 1) * PC_BLOCK_ROWS];
     const float x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     uint32_t h[4], l[4], h2[4], l2[4];
 #pragma unroll

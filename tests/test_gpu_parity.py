@@ -210,18 +210,20 @@ def test_accumulate_tensor_core_vs_cuda_core_and_oracle(eng, mix):
     es.score()
     es.forward_backward()
     accs = {}
-    for tc in (0, 1):
-        eng.set_option("tensor_core", tc)
+    for tc in (0, 1, 2):  # CUDA cores / tcgen05 with the Gaussians on the lanes and gathered blocks / tcgen05 per tile
+        eng.set_option("tensor_core", min(tc, 1))
+        eng.set_option("k3_kernel", 0 if tc == 2 else 1)
         es.accumulate()
         torch.cuda.synchronize()
         accs[tc] = es.acc.cpu().numpy().reshape(n_units, 3, mix, 80)
     eng.set_option("tensor_core", 1)
+    eng.set_option("k3_kernel", 1)
     stats, _ = fast.estep_corpus(om, labels, utts)
     sh, isc = es.shift.cpu().numpy(), es.inv_scale.cpu().numpy()
     occ = stats.occ[..., None]
     sx_ref = (stats.sx - sh * occ) * isc
     sxx_ref = (stats.sxx - 2 * sh * stats.sx + sh * sh * occ) * isc * isc
-    for tc in (0, 1):
+    for tc in (0, 1, 2):
         a = accs[tc]
         assert np.all(np.abs(a[..., 39] - stats.occ) <= REL * np.maximum(stats.occ, 1e-2)), tc
         assert np.all(np.abs(a[..., 79] - stats.occ) <= REL * np.maximum(stats.occ, 1e-2)), tc
