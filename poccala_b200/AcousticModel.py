@@ -13,7 +13,7 @@ Two ways through the same kernels:
     `multi_embedded_training_2(unit, init, ...)` - used by the parity tests that replay the
     reference's own sequence of calls.
 Out of scope here: wav/MFCC front end, pickled data files, trainInfo resume files,
-mode-1 isolated-unit training (GMM.em), multiprocessing pools.
+multiprocessing pools.
 """
 from __future__ import annotations
 
@@ -62,7 +62,9 @@ class AcousticModel(object):
         self.__utterances = None
         self.__state_data = None  # per-(unit, state) data sets grouped by process_data(mode=1)
         self.__estep = None
+        self.__estep_group = None  # process group the resident frames were standardised with
         self.__model = None
+        self.__unit_data = {}      # unit -> list of [n, D] segments (multi_process_data: the reference's pickles)
         self.last_log_likelihood = None
         if state_num != 5:
             raise NotImplementedError("the kernels cover state_num = 5 (3 emitting states, init.py:33)")
@@ -189,7 +191,24 @@ class AcousticModel(object):
         self.__acc.pop(unit, None)
 
     def delete_trainInfo(self):
-        pass
+        """AcousticModel.py:432-441 removes trainInfo_<job>.csv (the resume list of trained units); training
+        state lives in memory here, so there is nothing to delete."""
+
+    @staticmethod
+    def init_audio(audiopath, labelpath):
+        """AcousticModel.py:443-461: generator over a corpus directory - first the number of audio files,
+        then (wav path, transcript path) pairs, each terminated by a newline like the reference's
+        pathInfo lines."""
+        import os
+
+        count = 0
+        for d in os.walk(audiopath):
+            count += len(d[2])
+        yield count
+        for d in os.walk(audiopath):
+            for file in d[2]:
+                name = file.split('.')[0]
+                yield audiopath + '/%s.wav\n' % name, labelpath + '/%s.wav.trn\n' % name
 
     # ---- sentence HMM assembly (AcousticModel.py:957-1014) ----------------------------------
     def embedded(self, label, hmm_list, data_index, alter=15):
@@ -296,9 +315,14 @@ class AcousticModel(object):
         if self.__model is None:
             self.__model = _eng.Model(self.engine, *self.get_parameters())
             self.__estep = None
+        if self.__estep is not None and group is not None and self.__estep_group is not group:
+            # the frames were standardised with another group's (or this rank's own) moments: the accumulators of
+            # the ranks would live in different coordinates - standardise again with the moments of `group`
+            self.__estep = None
         if self.__estep is None:
             self.__estep = _eng.EStep(self.engine, self.__corpus, self.__model)
             self.__estep.load_frames(self.__frames, group=group)
+            self.__estep_group = group
         return self.__estep
 
     def embedded_training(self, wwt_units=None, init=True, load_line=0, fix_code=0, show_q=False, show_a=False,
@@ -324,7 +348,7 @@ class AcousticModel(object):
 
     # ---- mode 1: segment -> per-state data sets -> k-means / GMM EM --------
     def process_data(self, mode=1, load_line=0, init=True, proportion=0.25, step=1, differentiation=True,
-                     coefficient=1):
+                     coefficient=1, group=None):
         """AcousticModel.py:681-733 over the resident corpus.  Mode 1: every utterance is cut
         uniformly over its units (init, `__eq_segment` mode 'e', :605-612) or along the forced
         alignment of the current models (multi_process_data, :736-764), each unit segment in three
@@ -342,12 +366,56 @@ class AcousticModel(object):
         path = None
         if not init:
             self.log.note("Viterbi Alignment...", cls="i")
-            _, path, _ = self.align()
+            _, path, _ = self.align(group)
         key, kept = _eng.segment_keys(self.engine, self.__corpus, path)
         frames = self.__frames if self.__frames.dtype == torch.float64 else self.__frames.double()
         self.__state_data = _eng.group_frames(self.engine, key, EMIT * len(self.__loaded_units), frames)
         self.__state_data["utt_kept"] = kept
         return self.__state_data
+
+    def multi_process_data(self, label, data, init, *args):
+        """AcousticModel.py:723-769, one utterance: cut `data` uniformly over the units of `label` (init,
+        `__eq_segment` mode 'e') or along the forced alignment of the current models (Viterbi on the
+        device; an utterance whose path visits fewer distinct units than its label holds is dropped,
+        :751-757; contiguous runs per unit, `discriminate`), and keep the segments per unit - what the
+        reference pickles with `__save_data`.  `multi_training` reads them when no corpus-wide grouping
+        (process_data) is at hand.  args = (current, total, fix_code), unused."""
+        data = np.asarray(data, dtype=np.float64)
+        label = list(label)
+        if init:
+            n = len(data) // len(label)
+            for i, u in enumerate(label):
+                self.__unit_data.setdefault(u, []).append(data[i * n:(i + 1) * n])
+            return True
+        hmm_list = []
+        for u in label:
+            hmm = self.init_unit(unit=u, new_log=init)
+            self.init_parameter(u, hmm=hmm)
+            hmm.cal_observation_pro([data], [len(data)])
+            hmm.clear_data()
+            hmm_list.append(hmm)
+        states, A, B, pi = self.embedded(label, hmm_list, 0, 15)
+        point, sequence = self.viterbi(states, A, B, pi)
+        if len(set(sequence)) < len(set(label)):
+            self.log.note("viterbi alignment failed: utterance dropped", cls="w")
+            return False
+        for u in set(label):
+            for loc in AcousticModel.discriminate(u, sequence):
+                self.__unit_data.setdefault(u, []).append(data[loc])
+        return True
+
+    def _state_rows_from_segments(self, unit):
+        """`__get_gmmdata` (AcousticModel.py:629-644) on the segments multi_process_data kept: every segment of n
+        frames is cut into 3 parts of n // 3 frames, the last taking the remainder; parts concatenate per state."""
+        segs = self.__unit_data.get(unit, [])
+        D = self.__vector_size
+        parts = [[] for _ in range(EMIT)]
+        for seg in segs:
+            n = len(seg) // EMIT
+            for r in range(EMIT):
+                parts[r].append(seg[r * n:(r + 1) * n] if r < EMIT - 1 else seg[r * n:])
+        dev = self.engine.device
+        return [torch.as_tensor(np.concatenate(p) if p else np.zeros((0, D))).to(dev) for p in parts]
 
     def multi_training(self, unit, init, *args):
         """AcousticModel.py:814-838 + `__cal_gmm` (:532-561): the unit's three state GMMs from their
@@ -361,14 +429,17 @@ class AcousticModel(object):
 
         show_q = args[0] if len(args) > 0 else False
         c_cov = args[2] if len(args) > 2 else 1e-3
-        if self.__state_data is None:
-            raise RuntimeError("process_data(mode=1) first")
+        if self.__state_data is None and not self.__unit_data:
+            raise RuntimeError("process_data(mode=1) or multi_process_data(...) first")
         hmm = self.init_unit(unit, new_log=init, fix_code=2)
         self.init_parameter(unit, hmm)
-        ui = self.__loaded_units.index(unit)
-        off, data = self.__state_data["key_off"], self.__state_data["data"]
         M = self.__mix_level
-        rows = [data[off[ui * EMIT + r]:off[ui * EMIT + r + 1]] for r in range(EMIT)]
+        if self.__state_data is not None:
+            ui = self.__loaded_units.index(unit)
+            off, data = self.__state_data["key_off"], self.__state_data["data"]
+            rows = [data[off[ui * EMIT + r]:off[ui * EMIT + r + 1]] for r in range(EMIT)]
+        else:
+            rows = self._state_rows_from_segments(unit)
         if sum(len(x) for x in rows) == 0:
             self.log.note("unit %s has no data" % unit, cls="w")
             self.__save_parameter(unit, hmm)
@@ -413,11 +484,12 @@ class AcousticModel(object):
         return self.embedded_training(units, init=init, show_q=show_q, show_a=show_a, load_line=load_line,
                                       fix_code=fix_code, c_covariance=c_covariance, group=group)
 
-    def align(self):
+    def align(self, group=None):
         """Forced alignment of the whole resident corpus (multi_process_data's Viterbi step,
         AcousticModel.py:736-764): returns (scores [U] fp64, state path, unit path) as device tensors
-        indexed by corpus frame."""
-        es = self._ensure_estep()
+        indexed by corpus frame.  `group`: the process group of a data-parallel run, so that the frames
+        are standardised once, with the moments of all ranks."""
+        es = self._ensure_estep(group)
         es.score()
         ls, ln = _eng.host_log_bands(self.get_parameters()[3], self.engine.device)
         n_lab = self.__corpus.n_labels

@@ -9,8 +9,8 @@ Differences a maintainer should know:
     log-domain views the reference exposes (`acc`, `alpha_acc`, `mean_acc`) are derived on access;
   * `covariance` is the reference's [M,D,D] stack of diagonal matrices; only the diagonal is used
     (the reference extracts `.diagonal()` in util.gaussian_function, util.py:20-36);
-  * the stand-alone `em()` / SMEM split-merge trainer (Clustering.py:483-651,695-719) is outside
-    the hot path and raises NotImplementedError.
+  * the stand-alone `em()` trainer (Clustering.py:583-651,695-719) runs its E-step on the device; the SMEM
+    split / merge search (Clustering.py:371-577) is host-side model selection over device-computed posteriors.
 """
 from __future__ import annotations
 
@@ -105,6 +105,49 @@ class Clustering(object):
             self.__alpha = np.load(path + '/GMM_weight.npy')
             # the reference hands ConfigParser.read() an open file object, so the .ini never parses
             # and mixture / dimension / bias keep their constructor values (Q15); same here
+
+        # ---- accumulator files (Clustering.py:257-283, 314-367): the reference's four log-domain arrays per
+        # save - acc [M] = log sum gamma(j,m), alpha_acc = log sum gamma(j), mean_acc [M,D] = log sum gamma (x + 100),
+        # covariance_acc [M,D] = log sum gamma (x - mu_old)^2 - derived from the linear statistics on save and
+        # folded back into them on load (log-sum-exp over files == sum of the linear values).
+        def save_acc(self, path):
+            import os
+
+            from .LHMM import LHMM
+
+            path = path + '/GMM_%d' % self.__gmm_id
+            dirs = [path, path + '/acc', path + '/alpha-acc', path + '/mean-acc', path + '/covariance-acc']
+            for d in dirs:
+                if not os.path.exists(d):
+                    os.mkdir(d)
+            np.save(LHMM._acc_file(dirs[1], 'GMM_acc'), self.acc)
+            np.save(LHMM._acc_file(dirs[2], 'GMM_alpha_acc'), np.asarray(self.alpha_acc))
+            np.save(LHMM._acc_file(dirs[3], 'GMM_mean_acc'), self.mean_acc)
+            np.save(LHMM._acc_file(dirs[4], 'GMM_covariance_acc'), np.stack(self.covariance_acc_log))
+
+        def init_acc(self, path):
+            import os
+
+            path = path + '/GMM_%d' % self.__gmm_id
+
+            def files(sub):
+                d = path + '/' + sub
+                return [np.load(os.path.join(d, f)) for f in sorted(os.listdir(d))] if os.path.exists(d) else []
+
+            with np.errstate(over="ignore", invalid="ignore"):
+                occ_files = np.zeros_like(self._occ)
+                for a in files('acc'):
+                    occ_files = occ_files + np.exp(np.asarray(a, dtype=np.float64).reshape(-1))
+                self._occ = self._occ + occ_files
+                for a in files('alpha-acc'):
+                    self._socc += float(np.exp(np.asarray(a, dtype=np.float64)).sum())
+                # mean_acc carries the +100 bias of every contributing frame: sum gamma x = sum_f exp(mean_acc_f) - 100 sum_f occ_f
+                m_files = files('mean-acc')
+                if m_files:
+                    self._sx = self._sx + sum(np.exp(np.asarray(m, dtype=np.float64)) for m in m_files) \
+                        - self.__bias * occ_files[:, None]
+                for c in files('covariance-acc'):
+                    self._scc = self._scc + np.exp(np.asarray(c, dtype=np.float64))
 
         # ---- parameters (Clustering.py:122-229) -------------------------------------------
         @property
@@ -315,9 +358,14 @@ class Clustering(object):
             self.__mean = mean[0, 0].cpu().numpy()
             self.__covariance = _diag_stack(var[0, 0].cpu().numpy())
             self.__alpha = alpha[0, 0].cpu().numpy()
+            if self._socc > 0.0:
+                # the reference divides by alpha_acc, the state occupancy it was GIVEN (Clustering.py:685); the kernel
+                # uses the sum of the component occupancies, which differs when b_value is not the exact
+                # log-sum-exp of the component scores
+                self.__alpha = self._occ / self._socc
             if show_q:
                 self.log.note("GMM %s re-estimated" % self.__gmm_id, cls="i")
-            self._clear_acc()
+            # (the accumulators stay, as in the reference; AcousticModel builds fresh unit objects per M-step)
 
         # ---- stand-alone EM of one GMM (mode 1, Clustering.py:583-651, 695-719) ----------
         # The data set is laid out as a corpus of one pseudo unit whose first state carries this GMM and

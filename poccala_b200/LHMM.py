@@ -87,7 +87,38 @@ class LHMM(object):
         self.log_likelihood = None   # log P(O) of the last baulm_welch
         self.iterations = None       # pi-iterations the reference's loop runs (LHMM.py:526-544)
 
-    # ---- DataInitialization surface (DataInitialization.py:92-120) --------------------------------
+    # ---- DataInitialization surface (DataInitialization.py:32-120) --------------------------------
+    def init_data(self, data=None, datapath=None, shuffle=False, continuous=True, matrix=True, hasmark=True):
+        """DataInitialization.py:32-90: take `data` as is, or read the reference's text format - a title
+        line, a line `<n> <dimension> <k> <mark 1> .. <mark k>`, then one comma-separated sample per line
+        whose last field is its mark."""
+        import random
+
+        if data is not None:
+            self.__data = data
+        elif datapath is not None:
+            self.__markdata, self.__data = {}, []
+            with open(datapath) as f:
+                f.readline()
+                s = f.readline().strip('\n').split(' ')
+                self.__dimension, self.__classes = int(s[1]), int(s[2])
+                if hasmark:
+                    for i in range(self.__classes):
+                        self.__markdata[s[i + 3]] = []
+                for line in f:
+                    fields = line.strip('\n').split(',')
+                    if len(fields) < self.__dimension:
+                        continue
+                    row = [float(x) if continuous else x for x in fields[:self.__dimension]]
+                    row = np.array(row) if matrix else row
+                    if hasmark:
+                        self.__markdata[fields[self.__dimension]].append(row)
+                    self.__data.append(row)
+        else:
+            raise Exception("init_data: neither data nor datapath given")
+        if shuffle:
+            random.shuffle(self.__data)
+
     def add_data(self, data):
         self.__data.extend(data)
 
@@ -101,6 +132,18 @@ class LHMM(object):
     @property
     def datasize(self):
         return len(self.__data)
+
+    @property
+    def markdata(self):
+        return getattr(self, "_LHMM__markdata", {})
+
+    @property
+    def dimension(self):
+        return getattr(self, "_LHMM__dimension", 0)
+
+    @property
+    def classes(self):
+        return getattr(self, "_LHMM__classes", 0)
 
     # ---- properties (LHMM.py:100-145) ----------------------------------------------------------
     @property
@@ -183,6 +226,46 @@ class LHMM(object):
         self.__pi = np.load(path + '/pi.npy')
         # HMM_config.ini is written but never parsed by the reference (Q15): fix_code keeps its value
 
+    # ---- accumulator files (LHMM.py:211-231, 256-290): the reference's layout, so partial E-steps written by
+    # either side merge in the other.  The reference names the files by int(time.time()) and loses one of two
+    # saves of the same second (Q13); here a counter is appended when the name is taken.
+    @staticmethod
+    def _acc_file(directory, stem):
+        import os
+        import time
+
+        name = "%s_%d.npy" % (stem, int(time.time()))
+        k = 0
+        while os.path.exists(os.path.join(directory, name)):
+            k += 1
+            name = "%s_%d_%d.npy" % (stem, int(time.time()), k)
+        return os.path.join(directory, name)
+
+    def save_acc(self, path):
+        import os
+
+        path = path + '/HMM'
+        for d in (path, path + '/ksai-acc', path + '/gamma-acc'):
+            if not os.path.exists(d):
+                os.mkdir(d)
+        np.save(self._acc_file(path + '/ksai-acc', 'ksai_acc'), self.__ksai_acc)
+        np.save(self._acc_file(path + '/gamma-acc', 'gamma_acc'), self.__gamma_acc)
+
+    def init_acc(self, path):
+        """Log-sum-exp of every accumulator file under <path>/HMM (util.matrix_log_sum_exp / log_sum_exp)."""
+        import os
+
+        path = path + '/HMM'
+        kdir, gdir = path + '/ksai-acc', path + '/gamma-acc'
+        if not (os.path.exists(kdir) and os.path.exists(gdir)):
+            return
+        ks = [np.load(os.path.join(kdir, f)) for f in sorted(os.listdir(kdir))]
+        gs = [np.load(os.path.join(gdir, f)) for f in sorted(os.listdir(gdir))]
+        if ks:
+            self.__ksai_acc = _lse(np.stack(ks), axis=0)
+        if gs:
+            self.__gamma_acc = _lse(np.stack(gs), axis=0)
+
     # ---- accumulators (LHMM.py:149-161) ----------------------------------------------------------
     def add_acc(self, ksai_value, gamma_value):
         """Element-wise log-add into the log-domain transition accumulators."""
@@ -233,6 +316,9 @@ class LHMM(object):
                                    "AcousticModel.embedded); the profunc-only form crashes in the reference (Q16)")
         if self.__statesnum != 5:
             raise UnsupportedModel("the kernels cover state_num = 5 (3 emitting states per unit)")
+        if self.__fix_list[2]:
+            raise UnsupportedModel("fix_code bit 1 (pi fixed): the kernel always runs the reference's pi re-estimation "
+                                   "loop (LHMM.py:447-471); AcousticModel never fixes pi")
         eng = get_engine()
         hl = self.__hmm_list
         L = len(hl)
@@ -328,10 +414,6 @@ class LHMM(object):
         if not self.__fix_list[1] and self.__profunction is not None:
             for g in self.__profunction[1:-1]:
                 g.update_param(show_q=show_q, c_covariance=c_covariance)
-        with np.errstate(divide="ignore"):
-            self.__ksai_acc = np.log(np.zeros((self.__statesnum - 2, self.__statesnum)))
-            self.__gamma_acc = np.log(np.zeros((self.__statesnum - 2,)))
-
     # ---- K4: Viterbi (LHMM.py:546-609) ---------------------------------------------------------
     @staticmethod
     def viterbi(log, states, transmat, prob, pi, convert=False, end_state_back=False, show_mark_state=False):

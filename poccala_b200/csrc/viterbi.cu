@@ -178,7 +178,8 @@ __global__ void viterbi_kernel(CorpusView v, const E *__restrict__ b,
             uint32_t wsel = w[0];
 #pragma unroll
             for (int q = 1; q < SPL; ++q) wsel = ((cur % SPL) == q) ? w[q] : wsel;
-            const uint32_t bit = (__shfl_sync(0xffffffffu, wsel, cur / SPL) >> k) & 1u;
+            // (state 0 has no predecessor: its bit is set when every score of the column is -inf, move = stay = -inf)
+            const uint32_t bit = cur > 0 ? (__shfl_sync(0xffffffffu, wsel, cur / SPL) >> k) & 1u : 0u;
             cur -= (int)bit;
             steps |= bit << k;
         };

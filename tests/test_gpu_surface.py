@@ -312,3 +312,42 @@ def test_mode1_training_segment_kmeans_gmm_em():
     assert np.isfinite(ll) and all(np.isfinite(p).all() for p in am.get_parameters())
     with pytest.raises(ModeError):
         am.process_data(mode=3)
+
+
+def test_multi_process_data_per_utterance_equals_batched_grouping():
+    """AcousticModel.multi_process_data (AcousticModel.py:723-769), utterance by utterance in the reference's call
+    order, builds the same per-state data sets as the batched process_data(mode=1): uniform cut (init) and the cut
+    along the forced alignment; multi_training then trains the same GMMs from either."""
+    from poccala_b200 import synth
+    from poccala_b200.AcousticModel import AcousticModel
+
+    M = 2
+    truth, init, labels, utts = synth.make_corpus(24, 90, 3, 3, M, 15)
+    names = [[UNITS3[i] for i in l] for l in labels]
+
+    def fresh():
+        am = AcousticModel(None, "T", state_num=5, mix_level=M)
+        am.set_units(UNITS3)
+        am.set_parameters(*init)
+        return am
+
+    for init_flag in (True, False):
+        a = fresh()
+        a.add_corpus(names, utts)
+        sd = a.process_data(mode=1, init=init_flag)
+        off, data = sd["key_off"], sd["data"].cpu().numpy()
+        b = fresh()
+        kept = [b.multi_process_data(l, x, init_flag, k + 1, len(utts), 2) for k, (l, x) in enumerate(zip(names, utts))]
+        if not init_flag:
+            assert kept == [bool(v) for v in sd["utt_kept"].cpu().numpy()]
+        for ui, u in enumerate(UNITS3):
+            rows = b._state_rows_from_segments(u)
+            for r in range(3):
+                want = data[off[ui * 3 + r]:off[ui * 3 + r + 1]]
+                got = rows[r].cpu().numpy()
+                # same frames; the reference appends a unit's runs label by label, the batched path in (utterance, time) order
+                assert got.shape == want.shape
+                assert np.array_equal(np.sort(got.sum(axis=1)), np.sort(want.sum(axis=1)))
+    random.seed(5)
+    hmm = b.multi_training(UNITS3[0], True, False, False, 1e-3)
+    assert all(np.isfinite(g.mean).all() for g in hmm.profunction[1:-1])
