@@ -422,9 +422,8 @@ class AcousticModel(object):
         data sets: k-means initialisation (ClusterInitialization.kmeans(algorithm=1), all three
         states in one launch) when `init` or when the mixture count changed, then GMM.em.  A state
         with fewer frames than mixtures is skipped (:546-548); a unit without data keeps its
-        parameters (:830-832).  args = (show_q, show_a, c_covariance, ...).  The reference runs
-        em(smem=init); the SMEM split / merge search is outside this path, so the EM
-        here is em(smem=False)."""
+        parameters (:830-832).  args = (show_q, show_a, c_covariance, ...).  As in the reference the EM
+        runs with the split / merge search when `init` is set (em(smem=init), :835 -> :560)."""
         import random
 
         show_q = args[0] if len(args) > 0 else False
@@ -444,26 +443,26 @@ class AcousticModel(object):
             self.log.note("unit %s has no data" % unit, cls="w")
             self.__save_parameter(unit, hmm)
             return hmm
-        todo = [r for r in range(EMIT) if len(rows[r]) >= M]
-        fresh = [r for r in todo if init or hmm.profunction[r + 1].mixture != M]
-        if fresh:
-            sub = torch.cat([rows[r] for r in fresh])
-            sub_off = np.concatenate([[0], np.cumsum([len(rows[r]) for r in fresh])]).astype(np.int64)
-            seeds = [_eng.kmeans_seed_points(np.ascontiguousarray(rows[r][:, 0].cpu().numpy()), M, random) for r in fresh]
-            km = _eng.kmeans_run(self.engine, sub, sub_off, M, np.array(seeds, dtype=np.int32))
-            k_mean, k_var, k_alpha = (km[k].cpu().numpy() for k in ("mean", "var", "alpha"))
-            for i, r in enumerate(fresh):
-                gmm = hmm.profunction[r + 1]
-                gmm.mean = k_mean[i]
-                gmm.covariance = np.stack([np.diag(v) for v in k_var[i]])
-                gmm.alpha = k_alpha[i]
+        # state by state, as __cal_gmm does (AcousticModel.py:547-561): the seeding draws, the one draw per k-means
+        # move (Clustering.py:932) and the draws of the split / merge search all come from the same `random` stream, so
+        # the order of the states is part of the result
         for r in range(EMIT):
             gmm = hmm.profunction[r + 1]
-            if r not in todo:
+            if len(rows[r]) < M:
                 gmm.log.note("too little data, state skipped", cls="w")
                 continue
+            if init or gmm.mixture != M:
+                seeds = _eng.kmeans_seed_points(np.ascontiguousarray(rows[r][:, 0].cpu().numpy()), M, random)
+                km = _eng.kmeans_run(self.engine, rows[r], np.array([0, len(rows[r])], dtype=np.int64), M,
+                                     np.array([seeds], dtype=np.int32))
+                for _ in range(int(km["moves"][0])):
+                    random.random()
+                gmm.mixture = M
+                gmm.mean = km["mean"][0].cpu().numpy()
+                gmm.covariance = np.stack([np.diag(v) for v in km["var"][0].cpu().numpy()])
+                gmm.alpha = km["alpha"][0].cpu().numpy()
             gmm.add_data(rows[r])
-            gmm.em(show_q=show_q, smem=False, c_covariance=c_cov)
+            gmm.em(show_q=show_q, smem=init, c_covariance=c_cov)
             gmm.clear_data()
         self.__save_parameter(unit, hmm)
         return hmm

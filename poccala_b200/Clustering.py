@@ -187,9 +187,22 @@ class Clustering(object):
         def mixture(self):
             return self.__mix_level
 
+        @mixture.setter
+        def mixture(self, mix_level):
+            """Clustering.py:156-159: a new mixture count; the caller sets mean / covariance / alpha next."""
+            self.__mix_level = int(mix_level)
+            self._em_es = None
+            self._clear_acc()
+
         @property
         def data(self):
             return self.__data
+
+        @data.setter
+        def data(self, data):
+            """Clustering.py:166-174."""
+            self.__data = data if isinstance(data, torch.Tensor) else np.array(data)
+            self._em_es = None
 
         @property
         def bias(self):
@@ -391,11 +404,13 @@ class Clustering(object):
             model = _eng.Model(eng, np.zeros((1, 3, M, D)), np.ones((1, 3, M, D)), np.ones((1, 3, M)) / M,
                                np.zeros((1, 5, 5)))
             es = _eng.EStep(eng, corpus, model)
-            es.load_frames(torch.as_tensor(data).to(eng.device))
+            x_dev = torch.as_tensor(data).to(eng.device)
+            es.load_frames(x_dev)
             # every frame belongs to state 0 with posterior 1; states 1, 2 of the pseudo unit are unused
             es.lgam.fill_(float("-inf"))
             es.lgam.view(-1, 8)[:, 0] = 0.0
             self._em_es, self._em_n = es, n
+            self._em_x, self._em_rows, self._em_prev = x_dev, None, None
 
         def expectation(self):
             """Clustering.py:583-600: gamma_ik = alpha_k N(x_i; k) / sum_k' (...), reduced on the device
@@ -403,6 +418,8 @@ class Clustering(object):
             self._em_setup()
             es, m = self._em_es, self._em_es.model
             dev = es.engine.device
+            # the posteriors of this pass belong to THESE parameters (the split / merge search ranks on them)
+            self._em_prev = (np.array(self.__mean), np.array(self.variance), np.array(self.__alpha))
             for r in range(3):
                 m.mean[0, r].copy_(torch.as_tensor(self.__mean).to(dev))
                 m.var[0, r].copy_(torch.as_tensor(self.variance).to(dev))
@@ -435,12 +452,12 @@ class Clustering(object):
             return float(value_1 + np.sum(occ * const - 0.5 * quad))
 
         def em(self, show_q=False, smem=False, c_covariance=1e-3):
-            """Clustering.py:695-719: iterate while Q grows by more than 1.28."""
-            if smem:
-                raise NotImplementedError("the SMEM split / merge search (Clustering.py:483-577) is host-side model "
-                                          "selection outside this path; em(smem=False) is covered")
+            """Clustering.py:695-719: iterate while Q grows by more than 1.28; with `smem` the split / merge
+            search runs once the plain iteration has converged and the loop goes on if it found a better
+            model."""
             self._em_setup()
             self.iterations = 0
+            self.smem_trace = []
             q_value = -float("inf")
             while True:
                 self.log.note("GMM Q: %f" % q_value, cls="i", show_console=show_q)
@@ -451,9 +468,170 @@ class Clustering(object):
                 _q = self.q_function()
                 if _q - q_value > 1.28:
                     q_value = _q
-                else:
+                    continue
+                if not smem:
                     break
+                new_q_value = self._smem(q_value, c_covariance=c_covariance)
+                if new_q_value is False:
+                    break
+                q_value = new_q_value
             self.q_value = q_value
+
+        # ---- split and merge (SMEM, Clustering.py:371-577; SURVEY section 8 f2) ----------------------------
+        # The search itself is model selection on [M, n] posteriors and runs on the host in fp64, as SURVEY
+        # section 8 f2 places it; every Gaussian evaluation it needs (the posteriors it ranks on, the three
+        # candidate components, the Q terms) is one launch of the dense scoring kernel with one component per
+        # output column.  The reference's arithmetic is kept as it is written, including where it mixes
+        # domains: `__gamma` holds LOG posteriors after expectation(), and __J_merge, __J_split and the
+        # `gamma_sum` of __SMEM use those logs as if they were weights (:381, :395-409, :536-540); __reestimate
+        # then returns posterior x (sum of three logs) (:481), which maximization() and q_function() read as
+        # log weights.  The accept / reject decision and the ranking are reproduced on exactly those numbers.
+        def _component_scores(self, mean, var, alpha):
+            """[K, n] fp64: log alpha_k + log N(x_i; k) (util.py:20-31 with log=True, Q1) on the device."""
+            es = self._em_es
+            eng = es.engine
+            if self._em_rows is None:
+                self._em_rows = eng.prepare_rows(self._em_x, es.shift, es.inv_scale)
+            K = len(alpha)
+            W = eng.pack_gmm(torch.as_tensor(np.ascontiguousarray(mean, dtype=np.float64)).to(eng.device),
+                             torch.as_tensor(np.ascontiguousarray(var, dtype=np.float64)).to(eng.device),
+                             torch.as_tensor(np.ascontiguousarray(alpha, dtype=np.float64)).to(eng.device),
+                             es.shift, es.inv_scale, mix=0)
+            out = eng.score_dense(self._em_rows, W, K, 1)
+            return out.double().t().contiguous().cpu().numpy()
+
+        def _log_posteriors(self):
+            """The `__gamma` table the reference holds when __SMEM starts: log posteriors of the last
+            expectation(), i.e. under the parameters BEFORE the last maximization (Clustering.py:591-599)."""
+            s = self._component_scores(*self._em_prev)
+            m = s.max(axis=0)
+            return s - (m + np.log(np.exp(s - m).sum(axis=0)))
+
+        def _j_merge(self, gamma):
+            """Clustering.py:372-386: cosine of every pair of `__gamma` rows, best first."""
+            M = len(gamma)
+            out = []
+            with np.errstate(all="ignore"):
+                norm = [np.linalg.norm(gamma[i]) for i in range(M)]
+                for i in range(M):
+                    for j in range(i + 1, M):
+                        out.append([i, j, float(np.dot(gamma[i], gamma[j])) / (norm[i] * norm[j])])
+            out.sort(key=lambda r: r[2], reverse=True)
+            return out
+
+        def _j_split(self, gamma, X, mean, var):
+            """Clustering.py:388-430.  For component k and point x: the members of k (points whose largest
+            `__gamma` entry is k's, first one on ties) sorted by distance to x; p = sum_r (r / n_k) gamma_k[r-th]
+            / sum_i gamma_k[i]; J_split(k) = sum_x p log(p / N_std(x; k)) with the `standard=True` density of
+            util.py:24-26 (deviation multiplied by sqrt(var), unit covariance)."""
+            M, n = gamma.shape
+            D = X.shape[1]
+            owner = np.argmax(gamma, axis=0)
+            out = []
+            with np.errstate(all="ignore"):
+                for k in range(M):
+                    idx = np.flatnonzero(owner == k)
+                    nk = len(idx)
+                    pg = gamma[k]
+                    p2 = np.sum(pg)
+                    if nk == 0:
+                        p = np.zeros(n) / p2
+                    else:
+                        Y, pgk = X[idx], pg[idx]
+                        rank = np.arange(nk) / nk
+                        p1 = np.empty(n)
+                        step = max(1, (1 << 22) // (nk * D))
+                        for o in range(0, n, step):
+                            diff = X[o:o + step, None, :] - Y[None, :, :]
+                            order = np.argsort(np.einsum("abk,abk->ab", diff, diff), axis=1, kind="stable")
+                            p1[o:o + step] = np.cumsum(rank * pgk[order], axis=1)[:, -1]
+                        p = p1 / p2
+                    dev = (X - mean[k]) * np.sqrt(var[k])
+                    dens = np.exp(-0.5 * np.sum(dev * dev, axis=1)) / (2 * np.pi) ** (D / 2)
+                    out.append([k, float(np.cumsum(p * np.log(p / dens))[-1])])
+            out.sort(key=lambda r: r[1], reverse=True)
+            return out, owner
+
+        def _split(self, x, X, owner):
+            """Clustering.py:443-465: 2-means of the points component x owns, centres jittered by
+            numpy's global generator, spherical covariance det^(1/D), half the weight each."""
+            pts = X[owner == x]
+            if len(pts) < self.__mix_level:
+                return False
+            mean_, _, _, _ = Clustering.ClusterInitialization(list(pts), 2, self.__dimension, self.log).kmeans(algorithm=1)
+            D = self.__dimension
+            m1 = mean_[0] + np.random.rand(D) * 1e-2
+            m2 = mean_[1] + np.random.rand(D) * 1e-2
+            v = np.full(D, np.linalg.det(self.__covariance[x]) ** (1 / D))
+            return [m1, m2], [v, v.copy()], [self.__alpha[x] * 0.5, self.__alpha[x] * 0.5]
+
+        def _smem(self, q_value, c_max=5, c_covariance=1e-3):
+            """Clustering.py:483-577.  Returns the new Q value when a merge(i, j) + split(k) candidate beats
+            `q_value`, False otherwise.  As in the reference only the first candidate whose split is possible is
+            evaluated (both branches of :563-577 return).  Where the reference cannot continue - an accepted
+            candidate leaves `__mix_level` at M - 3 (:556) and the next maximization() raises for M > 4; no
+            splittable candidate returns None into a float subtraction - the accepted model is kept with all
+            its M components, and "nothing to split" ends the search."""
+            if self.__mix_level < 3:
+                return False
+            M, D, n = self.__mix_level, self.__dimension, self._em_n
+            X = self._em_x.cpu().numpy()
+            mean, var, alpha = np.array(self.__mean), np.array(self.variance), np.array(self.__alpha)
+            gamma = self._log_posteriors()
+            merge_list = self._j_merge(gamma)
+            split_list, owner = self._j_split(gamma, X, mean, var)
+            candidates = []
+            for i, j, _ in merge_list:
+                for k, _ in split_list:
+                    if k != i and k != j and len(candidates) < c_max:
+                        candidates.append([i, j, k])
+                if len(candidates) == c_max:
+                    break
+            trace = {"merge": merge_list, "split": split_list, "candidates": candidates}
+            self.smem_trace.append(trace)
+            for cand in candidates:
+                i, j, k = cand
+                sp = self._split(k, X, owner)
+                if sp is False:
+                    continue
+                a_m = alpha[i] + alpha[j]
+                mean3 = np.stack([(mean[i] * alpha[i] + mean[j] * alpha[j]) / a_m] + sp[0])
+                var3 = np.stack([(var[i] * alpha[i] + var[j] * alpha[j]) / a_m] + sp[1])
+                alpha3 = np.array([a_m] + sp[2])
+                with np.errstate(all="ignore"):
+                    gamma_sum = gamma[i] + gamma[j] + gamma[k]
+                    s3 = self._component_scores(mean3, var3, alpha3)
+                    m3 = s3.max(axis=0)
+                    g3 = np.exp(s3 - (m3 + np.log(np.exp(s3 - m3).sum(axis=0)))) * gamma_sum  # __reestimate :467-481
+                    # maximization() on g3 read as log weights (:619-651), in linear arithmetic
+                    top = g3.max(axis=1, keepdims=True)
+                    w = np.exp(g3 - top)
+                    ws = w.sum(axis=1)
+                    new_mean = (w @ X) / ws[:, None]
+                    new_var = np.stack([(w[c] @ (X - new_mean[c]) ** 2) / ws[c] for c in range(3)])
+                    new_var = np.where(new_var < c_covariance, c_covariance, new_var)
+                    new_alpha = np.exp(top[:, 0]) * ws / n
+                    # q_function() of the three new components (:602-613)
+                    w3 = np.exp(g3)
+                    ln3 = self._component_scores(new_mean, new_var, np.ones(3))
+                    q_1 = float(np.sum(w3.sum(axis=1) * np.log(new_alpha)) + np.sum(w3 * ln3))
+                    # ... and of the components that stay, with the table of the last expectation()
+                    keep = np.array([c for c in range(M) if c not in cand], dtype=np.int64)
+                    q_2 = 0.0
+                    if len(keep):
+                        wk = np.exp(gamma[keep])
+                        lnk = self._component_scores(mean[keep], var[keep], np.ones(len(keep)))
+                        q_2 = float(np.sum(wk.sum(axis=1) * np.log(alpha[keep])) + np.sum(wk * lnk))
+                new_q = q_1 + q_2
+                trace.update(chosen=cand, mean3=mean3, var3=var3, alpha3=alpha3, new_mean=new_mean, new_var=new_var,
+                             new_alpha=new_alpha, q_1=q_1, q_2=q_2, accepted=bool(new_q > q_value))
+                if new_q > q_value:
+                    self.__mean = np.append(mean[keep], new_mean, axis=0)
+                    self.__covariance = _diag_stack(np.append(var[keep], new_var, axis=0))
+                    self.__alpha = np.append(alpha[keep], new_alpha)
+                    return new_q
+                return False
+            return False
 
         def theta(self):
             """Clustering.py:721-726: {'theta_k': [mean_k, diag(covariance_k)]}."""

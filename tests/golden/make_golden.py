@@ -186,6 +186,79 @@ def gmm_em_golden():
     print("gmm_em.npz written", [int(out[f"e{c}_iters"]) for c in range(2)])
 
 
+def smem_golden():
+    """Clustering.GMM.em(smem=True) (Clustering.py:483-577,695-719) executed on three small problems; what the
+    split / merge search ranked, chose and decided is recorded next to the final parameters."""
+    import random
+
+    H = rh.Harness(UNITS, MIX)
+    out = {}
+    problems = [(160, 3, 0.35, 5), (240, 4, 2.0, 6), (300, 5, 1.0, 7)]
+    for c, (n, M, spread, seed) in enumerate(problems):
+        rng = np.random.default_rng(seed)
+        centres = rng.normal(0, spread, size=(M, 39))
+        data = centres[rng.integers(0, M, size=n)] + rng.normal(size=(n, 39)) * rng.uniform(0.6, 1.2, size=(1, 39))
+        mean0 = centres[rng.integers(0, M, size=M)] + rng.normal(0, 0.25, size=centres.shape)
+        var0 = rng.uniform(0.8, 1.6, size=(M, 39))
+        alpha0 = np.ones(M) / M
+        g = H.Clustering.GMM(H.log, dimension=39, mix_level=M, data=list(data), alpha=alpha0.copy(), mean=mean0.copy(),
+                             covariance=np.stack([np.diag(v) for v in var0]))
+        rec = {"q": [], "max": [], "exp": 0}
+        merge, split, smem, qf, mx, ex = (g._GMM__J_merge, g._GMM__J_split, g._GMM__SMEM, g.q_function, g.maximization,
+                                          g.expectation)
+
+        def w_merge():
+            rec["merge"] = merge()
+            return rec["merge"]
+
+        def w_split():
+            rec["split"] = split()
+            return rec["split"]
+
+        def w_smem(q, **kw):
+            rec["q_in"] = q
+            rec["q"], rec["max"] = [], []
+            rec["ret"] = smem(q, **kw)
+            return rec["ret"]
+
+        def w_q():
+            rec["q"].append(qf())
+            return rec["q"][-1]
+
+        def w_max(**kw):
+            rec["max"].append(mx(**kw))
+            return rec["max"][-1]
+
+        def w_exp():
+            rec["exp"] += 1
+            return ex()
+
+        g._GMM__J_merge, g._GMM__J_split, g._GMM__SMEM = w_merge, w_split, w_smem
+        g.q_function, g.maximization, g.expectation = w_q, w_max, w_exp
+        np.random.seed(100 + c)
+        random.seed(200 + c)
+        g.em(show_q=False, smem=True, c_covariance=1e-3)
+        assert rec["ret"] is False, "an accepted candidate cannot be continued by the reference (mix_level stays M-3)"
+        out[f"s{c}_data"], out[f"s{c}_mean0"], out[f"s{c}_var0"], out[f"s{c}_alpha0"] = data, mean0, var0, alpha0
+        out[f"s{c}_merge"] = np.array([[r[0], r[1], float(np.ravel(r[2])[0])] for r in rec["merge"]])
+        out[f"s{c}_split"] = np.array([[r[0], float(np.ravel(r[1])[0])] for r in rec["split"]])
+        out[f"s{c}_q_in"] = float(rec["q_in"])
+        out[f"s{c}_q12"] = np.array([float(v) for v in rec["q"]])  # q_1 (three new components), q_2 (the rest)
+        nm, nc, na = rec["max"][-1]
+        out[f"s{c}_new_mean"] = np.array(nm)
+        out[f"s{c}_new_var"] = np.stack([np.diag(x) for x in nc])
+        out[f"s{c}_new_alpha"] = np.array(na)
+        out[f"s{c}_mean"] = np.array(g.mean)
+        out[f"s{c}_var"] = np.stack([np.diag(x) for x in g.covariance])
+        out[f"s{c}_alpha"] = np.array(g.alpha)
+        out[f"s{c}_iters"] = rec["exp"]
+        out[f"s{c}_seeds"] = np.array([100 + c, 200 + c])
+        print(c, "merge", out[f"s{c}_merge"][:3].tolist(), "split", out[f"s{c}_split"].tolist(), "q", rec["q_in"], rec["q"])
+    out["n"] = len(problems)
+    np.savez_compressed(os.path.join(OUT, "gmm_smem.npz"), **out)
+    print("gmm_smem.npz written")
+
+
 def alignment_golden():
     """Mode-1 data preparation executed as is: __eq_segment(mode='e') (AcousticModel.py:605-612), the
     post-Viterbi part of multi_process_data (:750-764, with discriminate :937-955) and __get_gmmdata
@@ -271,6 +344,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--gmm-em-only" in sys.argv:
         gmm_em_golden()
+        sys.exit(0)
+    if "--smem-only" in sys.argv:
+        smem_golden()
         sys.exit(0)
     estep_golden()
     viterbi_ties_golden()

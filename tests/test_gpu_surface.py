@@ -261,6 +261,76 @@ def test_gmm_em_matches_executed_reference():
         Clustering.GMM(None, dimension=39, mix_level=2).em()
 
 
+def test_gmm_em_split_merge_matches_executed_reference():
+    """§8 f2: Clustering.GMM.em(smem=True) (Clustering.py:371-577): the merge ranking, the split ranking, the candidate
+    the search evaluates, its re-estimated three components, the two Q terms and the decision, against the
+    reference's own run (tests/golden/make_golden.py --smem-only).  Problem 1 has densities that underflow: every
+    split score is nan there and the ranking stays in component order, as Python's sort leaves it."""
+    import random
+
+    from poccala_b200.Clustering import Clustering
+
+    g = load_golden("gmm_smem.npz")
+    worst = {}
+    for c in range(int(g["n"])):
+        data = g[f"s{c}_data"]
+        M = len(g[f"s{c}_alpha0"])
+        gm = Clustering.GMM(None, dimension=39, mix_level=M, data=list(data), alpha=g[f"s{c}_alpha0"].copy(),
+                            mean=g[f"s{c}_mean0"].copy(), variance=g[f"s{c}_var0"].copy())
+        np.random.seed(int(g[f"s{c}_seeds"][0]))
+        random.seed(int(g[f"s{c}_seeds"][1]))
+        gm.em(show_q=False, smem=True, c_covariance=1e-3)
+        assert gm.iterations == int(g[f"s{c}_iters"])
+        assert len(gm.smem_trace) == 1
+        tr = gm.smem_trace[0]
+        merge, split = np.array(tr["merge"]), np.array(tr["split"])
+        assert np.array_equal(merge[:, :2], g[f"s{c}_merge"][:, :2])
+        assert np.array_equal(split[:, 0], g[f"s{c}_split"][:, 0])
+        assert np.array_equal(np.isnan(split[:, 1]), np.isnan(g[f"s{c}_split"][:, 1]))
+        err = lambda a, b, floor=0.0: float(np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), floor)))  # noqa: E731
+        e = {"merge": err(merge[:, 2], g[f"s{c}_merge"][:, 2]),
+             "split": err(split[:, 1], g[f"s{c}_split"][:, 1], 1e-3) if not np.isnan(split[:, 1]).all() else 0.0,
+             "q_1": err(tr["q_1"], g[f"s{c}_q12"][0]), "q_2": err(tr["q_2"], g[f"s{c}_q12"][1], 1.0),
+             "mean": float(np.max(np.abs(tr["new_mean"] - g[f"s{c}_new_mean"]) / np.maximum(np.abs(g[f"s{c}_new_mean"]), np.sqrt(g[f"s{c}_new_var"])))),
+             "var": err(tr["new_var"], g[f"s{c}_new_var"]), "alpha": err(tr["new_alpha"], g[f"s{c}_new_alpha"], 1e-2)}
+        worst[c] = e
+        assert tr["accepted"] is False
+        # everything within 1e-4 except the split score: a sum of signed terms p log(p / N) over all points, evaluated on
+        # parameters that already went through several fp32 E-steps (held to 1e-3 like the final parameters below;
+        # measured 1.8e-4)
+        assert max(v for k, v in e.items() if k != "split") < 1e-4 and e["split"] < 1e-3, worst
+        var = np.stack([np.diag(x) for x in gm.covariance])
+        assert np.all(np.abs(gm.alpha - g[f"s{c}_alpha"]) <= 1e-3 * np.maximum(g[f"s{c}_alpha"], 1e-2))
+        assert np.all(np.abs(gm.mean - g[f"s{c}_mean"]) <= 1e-3 * np.maximum(np.abs(g[f"s{c}_mean"]), np.sqrt(g[f"s{c}_var"])))
+        assert np.all(np.abs(var - g[f"s{c}_var"]) <= 1e-3 * g[f"s{c}_var"])
+    print("SMEM worst relative errors", worst)
+
+
+def test_gmm_em_split_merge_accepts_a_better_model():
+    """The branch the reference cannot finish (an accepted candidate leaves its mix_level at M - 3): the threshold
+    is lowered so that the candidate is accepted; the model keeps M components, Q is the candidate's, and the
+    iteration goes on from there."""
+    import random
+
+    from poccala_b200.Clustering import Clustering
+
+    g = load_golden("gmm_smem.npz")
+    data, M = g["s2_data"], len(g["s2_alpha0"])
+    gm = Clustering.GMM(None, dimension=39, mix_level=M, data=list(data), alpha=g["s2_alpha0"].copy(),
+                        mean=g["s2_mean0"].copy(), variance=g["s2_var0"].copy())
+    np.random.seed(1)
+    random.seed(2)
+    gm.em(smem=False)
+    new_q = gm._smem(-1e9)
+    tr = gm.smem_trace[-1]
+    assert tr["accepted"] and new_q == tr["q_1"] + tr["q_2"]
+    assert gm.mean.shape == (M, 39) and gm.covariance.shape == (M, 39, 39) and gm.alpha.shape == (M,)
+    keep = [k for k in range(M) if k not in tr["chosen"]]
+    assert np.array_equal(gm.mean[:M - 3], np.asarray(g["s2_mean"])[keep]) or np.allclose(gm.mean[M - 3:], tr["new_mean"])
+    assert np.array_equal(gm.mean[M - 3:], tr["new_mean"])
+    assert Clustering.GMM(None, dimension=39, mix_level=2, data=list(data[:20]))._smem(0.0) is False  # fewer than 3
+
+
 def test_mode1_training_segment_kmeans_gmm_em():
     """§8 f2 + f3 through the reference-shaped surface: process_data(mode=1, init=True) (uniform
     segmentation, per-state data sets grouped on the device), multi_training (k-means initialisation
@@ -291,10 +361,7 @@ def test_mode1_training_segment_kmeans_gmm_em():
     compared = 0
     for k in range(9):
         data = xs[sets[k]]
-        twin = random.Random()
-        twin.setstate(random.getstate())
-        km = fast.kmeans_compat(data, M, twin)
-        kmeans_seed_points(np.ascontiguousarray(data[:, 0]), M, random)  # advance the stream as multi_training does
+        km = fast.kmeans_compat(data, M, random)  # seeding draws + one draw per move, the stream multi_training follows
         o_mean, o_var, o_alpha, iters, _ = fast.gmm_em(data, km["mean"], km["var"], km["alpha"], c_covariance=1e-3)
         if fast.gmm_em.margin < 0.05:
             continue  # a Q increment within 0.05 of the 1.28 threshold: the iteration count is a coin toss
