@@ -50,7 +50,7 @@ extern "C" {
 #define PC_EMIT 3     /* emitting states per unit HMM (state_num 5, AcousticModel.py:39) */
 #define PC_STATES 5
 #define PC_TRANS_SLOTS 9 /* per unit: 3 x (self, next, gamma) log-domain transition accumulators */
-#define PC_W_BYTES_PER_GAUSS 760 /* upper bound: 320 (fp32 row) + 8 (scale, flags) + <= 427 (fp16 image) */
+#define PC_W_BYTES_PER_GAUSS 1190 /* upper bound: 320 (fp32 row) + 8 (scale, flags) + 2 x <= 427 (fp16 images) */
 
 typedef struct pc_handle_s *pc_handle;
 typedef struct pc_corpus_s *pc_corpus;

@@ -15,6 +15,11 @@
 
 // byte offsets of the fp16 operand images inside the W / X buffers (pack.cu)
 __host__ __device__ inline size_t pc_w16_offset(int64_t n_gauss) { return ((size_t)n_gauss * 328 + 127) & ~(size_t)127; }
+// second image set behind the first: the same units with the hi and the lo halves as two contiguous pieces
+// (row groups of 1 280 B each), for kernels that move them separately (score_tc_big.cu)
+__host__ __device__ inline size_t pc_w16s_offset(int64_t n_gauss, int n_unit) {
+    return pc_w16_offset(n_gauss) + (size_t)(n_gauss / n_unit) * 2 * (PC_KA / 8) * ((n_unit + 15) & ~15) * 16;
+}
 __host__ __device__ inline size_t pc_x16_offset(int64_t n_frames) { return ((size_t)n_frames * PC_XS * 4 + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t pc_x32_offset(int64_t n_frames, int64_t n_xtiles) {
     return pc_x16_offset(n_frames) + (size_t)n_xtiles * PC_XTILE_BYTES;
@@ -198,6 +203,9 @@ bool score_tc_supported(int mix);
 int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                     float *b, int item_lo, int item_hi, cudaStream_t st);
 bool score_tc_wide_supported(int mix);
+bool score_tc_big_supported(int mix);
+int launch_score_tc_big(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix, float *b,
+                        int item_lo, int item_hi, cudaStream_t st);
 int launch_score_tc_wide(pc_handle h, const CorpusView &v, const float *X, const float *W, int mix,
                          float *b, int item_lo, int item_hi, cudaStream_t st);
 bool accumulate_tc_supported(int mix);

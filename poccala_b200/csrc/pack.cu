@@ -15,6 +15,8 @@
 //                             rows are zero).  Every [8 rows][16 B] block is one UMMA core matrix
 //                             (LBO = 128 B between K chunks, SBO = 2560 B between row groups), units
 //                             and slices of units concatenate along N, and a unit is ONE cp.async.bulk.
+//     [pc_w16s_offset(G, 3*mix), ..)  the same images with hi and lo as two contiguous pieces per unit
+//                             ([NPAD/8 row groups][10 chunks][8 rows][8 halves] each, SBO = 1280 B)
 // A row is scaled by 2^-e so that it fits fp16 (scale = 2^e undoes it in the epilogue); a row whose
 // constant is not finite (alpha = 0 -> log 0) is stored as zero weights with the constant -60000,
 // which underflows to probability 0 against any live component (the fp32 row keeps -inf).
@@ -49,10 +51,17 @@ __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *_
     const int unit = slot / npad, row = slot - unit * npad;
     uint8_t *img = reinterpret_cast<uint8_t *>(W) + pc_w16_offset(n_gauss) + (size_t)unit * 2 * (PC_KA / 8) * npad * 16;
     uint8_t *grp = img + (size_t)(row >> 3) * PC_WGROUP_BYTES + (row & 7) * 16;
-    if (row >= n_unit) {  // padding row of the operand image
-        if (lane < 2 * (PC_KA / 8))
+    // the split image set: hi piece, then lo piece, each [npad / 8 row groups][10 chunks][8 rows][8 halves]
+    const size_t piece = (size_t)(PC_KA / 8) * npad * 16;
+    uint8_t *grp_s = reinterpret_cast<uint8_t *>(W) + pc_w16s_offset(n_gauss, n_unit) + (size_t)unit * 2 * piece +
+                     (size_t)(row >> 3) * (PC_WGROUP_BYTES / 2) + (row & 7) * 16;
+    if (row >= n_unit) {  // padding row of the operand images
+        if (lane < 2 * (PC_KA / 8)) {
             *reinterpret_cast<uint4 *>(grp + (lane / (PC_KA / 8)) * (PC_WGROUP_BYTES / 2) + (lane % (PC_KA / 8)) * 128) =
                 make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(grp_s + (lane / (PC_KA / 8)) * piece + (lane % (PC_KA / 8)) * 128) =
+                make_uint4(0u, 0u, 0u, 0u);
+        }
         return;
     }
     const int g = unit * n_unit + row;
@@ -135,6 +144,8 @@ __global__ void pack_gmm_kernel(const double *__restrict__ mean, const double *_
             const int c = i >> 3, j = i & 7;
             reinterpret_cast<__half *>(grp + c * 128)[j] = hi;
             reinterpret_cast<__half *>(grp + PC_WGROUP_BYTES / 2 + c * 128)[j] = lo;
+            reinterpret_cast<__half *>(grp_s + c * 128)[j] = hi;
+            reinterpret_cast<__half *>(grp_s + piece + c * 128)[j] = lo;
         }
     }
 }

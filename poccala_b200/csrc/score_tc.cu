@@ -40,10 +40,10 @@ struct Cfg {
     static constexpr int NPAD = (N_REAL + 15) & ~15;
     static constexpr int B_PIECE = T_KCH * NPAD * 16;
     static constexpr int B_STAGE = 2 * B_PIECE;  // hi, lo
-    static constexpr int G = MIX <= 16 ? 3 : 2;                                // tiles per group
+    static constexpr int G = MIX <= 32 ? 3 : 2;                                // tiles per group
     // frame-tile slots: the group's tiles stay in shared memory for all label positions; one more
     // slot lets the producer start on the next group
-    static constexpr int NA = MIX <= 16 ? 4 : (MIX <= 32 ? 3 : 2);
+    static constexpr int NA = MIX <= 32 ? 4 : 2;
     // PG label positions share one accumulator (one MMA of N = PG * NPAD columns, one hand-off to the
     // epilogue): with the frame tile in tensor memory an N = 48 MMA still costs ~32 clk of a 24 clk
     // floor and every accumulator costs a commit / wait round trip, so narrow units go in pairs
@@ -444,6 +444,8 @@ int launch_score_tc(pc_handle h, const CorpusView &v, const float *X, const floa
     if (item_hi <= item_lo) return PC_OK;
     if (h->k1_kernel && score_tc_wide_supported(mix))  // narrow units: wide accumulators (score_tc_wide.cu)
         return launch_score_tc_wide(h, v, X, W, mix, b, item_lo, item_hi, st);
+    if (h->k1_kernel && score_tc_big_supported(mix))  // 64 mixtures: resident tiles, unit images in pieces (score_tc_big.cu)
+        return launch_score_tc_big(h, v, X, W, mix, b, item_lo, item_hi, st);
     switch (mix) {
         case 4: return launch_mix<4>(h, v, X, W, b, item_lo, item_hi, st);
         case 8: return launch_mix<8>(h, v, X, W, b, item_lo, item_hi, st);

@@ -100,7 +100,8 @@ def test_scores_tensor_core_vs_cuda_core_and_oracle(eng, mix):
     eng.set_option("tensor_core", 1)
     eng.set_option("k1_kernel", 1)
     for u in range(len(utts)):  # both tensor-core kernels run the same contraction
-        assert np.abs(corpus.emission_view(out[1], u).cpu().numpy() - corpus.emission_view(out[2], u).cpu().numpy()).max() < 1e-4
+        a1, a2 = corpus.emission_view(out[1], u).cpu().numpy(), corpus.emission_view(out[2], u).cpu().numpy()
+        assert np.all(np.abs(a1 - a2) <= 1e-4 + 2e-7 * np.abs(a2))  # a few fp32 ulps: the FMA-pipe exponential
     worst = 0.0
     for u, (lab, X) in enumerate(zip(labels, utts)):
         c = fast.score_components_direct(om, lab[None], X[None])
