@@ -837,6 +837,16 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     // prepares and scores run k as soon as it has landed, under the copy of run k+1 (pinned host
     // memory makes the copies asynchronous; pageable memory still works, without the overlap).
     if ((rc = ensure_streams(h))) return rc;
+    // the model first: host-to-device copies are served in the order they were issued, and the packing of the model
+    // must not queue behind 47 MB of frames
+    PC_CUDA_TRY(cudaMemcpyAsync(mean, host_mean, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(var, host_var, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(alpha, host_alpha, (size_t)G * 8, cudaMemcpyHostToDevice, st));
+    PC_CUDA_TRY(cudaMemcpyAsync(tm, host_transmat, (size_t)n_units * 25 * 8, cudaMemcpyHostToDevice, st));
+    if (host_shift) {
+        PC_CUDA_TRY(cudaMemcpyAsync(shift, host_shift, (size_t)dim * 8, cudaMemcpyHostToDevice, st));
+        PC_CUDA_TRY(cudaMemcpyAsync(inv_scale, host_inv_scale, (size_t)dim * 8, cudaMemcpyHostToDevice, st));
+    }
     PC_CUDA_TRY(cudaEventRecord(h->start_ev, st));  // whatever the caller queued before us
     PC_CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->start_ev, 0));
     // option "host_chunks" merges neighbouring runs (1 = one copy, no overlap)
@@ -849,10 +859,6 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
                                     (size_t)(f_hi - f_lo) * dim * 4, cudaMemcpyHostToDevice, h->copy_stream));
         PC_CUDA_TRY(cudaEventRecord(h->chunk_ev[k], h->copy_stream));
     }
-    PC_CUDA_TRY(cudaMemcpyAsync(mean, host_mean, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
-    PC_CUDA_TRY(cudaMemcpyAsync(var, host_var, (size_t)G * dim * 8, cudaMemcpyHostToDevice, st));
-    PC_CUDA_TRY(cudaMemcpyAsync(alpha, host_alpha, (size_t)G * 8, cudaMemcpyHostToDevice, st));
-    PC_CUDA_TRY(cudaMemcpyAsync(tm, host_transmat, (size_t)n_units * 25 * 8, cudaMemcpyHostToDevice, st));
     PC_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)G * PC_KA * 8, st));
     {
         log_bands_kernel<<<(n_units * PC_STATES + 127) / 128, 128, 0, st>>>(tm, n_units, ls, ln);
@@ -861,10 +867,7 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     }
     // Standardisation: the caller's corpus constants, or - without them - the
     // moments of this call's frames, which every chunk has to land for
-    if (host_shift) {
-        PC_CUDA_TRY(cudaMemcpyAsync(shift, host_shift, (size_t)dim * 8, cudaMemcpyHostToDevice, st));
-        PC_CUDA_TRY(cudaMemcpyAsync(inv_scale, host_inv_scale, (size_t)dim * 8, cudaMemcpyHostToDevice, st));
-    } else {
+    if (!host_shift) {
         PC_CUDA_TRY(cudaMemsetAsync(mom, 0, 2 * PC_XS * 8, st));
         for (int k = 0; k < c->n_chunks; k += kstep) {
             const int k1 = k + kstep < c->n_chunks ? k + kstep : c->n_chunks;
