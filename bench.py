@@ -258,12 +258,14 @@ def run_check(args):
     truth, init0, labels, x = synth.torch_corpus(n_all, T, L, N_UNITS, MIX, 2, dev, N_INITIALS)  # identical on every rank
     tm0 = synth.default_transmat(N_UNITS)
 
-    def train(sel, grp):
+    def train(sel, grp, peer=None):
         xs = x.view(n_all, T, DIM)[sel].reshape(-1, DIM).contiguous()
         corpus = Corpus(eng, labels[sel], np.full(len(sel), T, dtype=np.int32), N_UNITS)
         model = Model(eng, init0[0], init0[1], init0[2], tm0)
         es = EStep(eng, corpus, model)
         es.load_frames(xs, group=grp)
+        if peer is not None:
+            es.use_peer(peer)
         ll, snaps = [], []
         for _ in range(iters):
             es.em_iteration(c_covariance=1e-6, group=grp)
@@ -278,6 +280,13 @@ def run_check(args):
     single_all, ll1, _, _ = train(np.arange(n_all), None)
     mine = np.arange(rank, n_all, world)
     sharded_all, llN, corpus_s, xs = train(mine, group)
+    # the same shards with the reduction over peer memory (no collective call inside the iterations)
+    peer = peer_all = None
+    if group is not None:
+        from poccala_b200.distributed import PeerExchange
+
+        peer = PeerExchange(eng, N_UNITS, N_UNITS * 3 * MIX, group)
+        peer_all, llP, _, _ = train(mine, group, peer)
 
     def diff(got, ref):
         """Worst deviation of a model from a reference model: means in units of max(|mean|, standard deviation),
@@ -294,6 +303,12 @@ def run_check(args):
     diffs1, diffs = diff(sharded_all[0], single_all[0]), diff(sharded_all[-1], single_all[-1])
     sharded = sharded_all[-1]
     identical = True
+    peer_diffs = peer_host_diffs = None
+    if peer is not None:
+        # peer-memory reduction against the NCCL reduction of the same shards: the same sums up to the order of the
+        # N terms (and the same at N = 2)
+        peer_diffs = diff(peer_all[-1], sharded_all[-1])
+        sharded = list(sharded) + list(peer_all[-1])
     if group is not None:
         for t in sharded:
             hi, lo = t.clone(), t.clone()
@@ -314,6 +329,15 @@ def run_check(args):
     host_diffs = diff([torch.as_tensor(a).to(dev) for a in hp], single_all[0])
     ok = identical and max(diffs1.values()) <= 2e-5 and max(host_diffs.values()) <= 2e-5 and \
         max(diffs.values()) <= 1e-3 and abs(llN[-1] - ll1[-1]) <= 1e-8 * abs(ll1[-1])
+    peer_timeouts = None
+    if peer is not None:
+        # the host entry point without a hook: the connected exchange block makes it reduce over peer memory
+        hp2 = [np.ascontiguousarray(a, dtype=np.float64).copy() for a in init0] + [tm0.copy()]
+        em_iteration_host(eng, corpus_s, host_x, *hp2, c_covariance=1e-6, shift=shift, inv_scale=isc)
+        peer_host_diffs = diff([torch.as_tensor(a).to(dev) for a in hp2], single_all[0])
+        peer_timeouts = peer.timeouts()
+        ok = ok and max(peer_diffs.values()) <= 1e-9 and max(peer_host_diffs.values()) <= 2e-5 and peer_timeouts == 0
+        peer.close()
     flag = torch.tensor([0 if ok else 1], device=dev)
     if group is not None:
         dist.all_reduce(flag, group=group)
@@ -323,6 +347,9 @@ def run_check(args):
                           "replicas_bit_identical": identical, "diff_vs_single_rank_iteration_1": diffs1,
                           "diff_vs_single_rank_iteration_2": diffs,
                           "host_entry_diff_vs_single_rank_iteration_1": host_diffs,
+                          "peer_memory_vs_nccl_iteration_2": peer_diffs,
+                          "peer_memory_host_entry_diff_vs_single_rank_iteration_1": peer_host_diffs,
+                          "peer_timeouts": peer_timeouts,
                           "sum_logp_single": ll1, "sum_logp_sharded": llN}), flush=True)
     if group is not None:
         dist.destroy_process_group()

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PC_ABI_VERSION 2
+#define PC_ABI_VERSION 3
 
 #define PC_OK 0
 #define PC_ERR_INVALID (-1)     /* bad argument (shape, NULL pointer, dimension mismatch) */
@@ -289,6 +289,34 @@ int pc_frame_moments_host(pc_handle h, const float *host_frames, int64_t n_frame
 typedef int (*pc_reduce_hook)(void *user, int32_t op, void *stream);
 int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_tmax, double *dev_flat,
                        int64_t flat_len);
+
+/* Cross-rank reduction over PEER MEMORY (one process per GPU on one NVLink / NVSwitch node), the
+ * device-side replacement of the accumulator-file merge (LHMM.py:256-290, Clustering.py:314-367;
+ * AcousticModel.py:842-882): every rank keeps its statistics in an exchange block the other ranks map
+ * through CUDA IPC, and the M-step kernels add the N copies in rank order while they read them - no
+ * collective library call, replicas bit-identical.
+ *   pc_peer_create   allocates this rank's block (two alternating statistic sets + the reduced set + arrival
+ *                    flags) and returns its 64-byte IPC handle;
+ *   pc_peer_connect  takes the handles of ALL ranks in rank order ([n_ranks][64], own entry ignored); call a
+ *                    host barrier between pc_peer_connect and the first iteration;
+ *   pc_peer_buffers  device pointers of a statistic set: which = 0 / 1 the set of an even / odd iteration
+ *                    (option "peer_epoch" & 1 names the current one), 2 = the reduced sums of the last M-step:
+ *                    acc double [n_gauss][PC_KA], tsum / tmax double [n_units][9] (tsum relative to the SAME
+ *                    rank's tmax - pc_transitions_max / _sum on the local pairs, no collective in between);
+ *   pc_update_params_peer  pc_update_params on the sum over the ranks of the current set; every rank must call
+ *                    it once per iteration.  Read-only option "peer_timeouts": arrival waits that gave up (a rank
+ *                    that never called) - 0 in a healthy run.
+ * With a connected block and no reduce hook pc_em_iteration_host uses this path by itself. */
+#define PC_MAX_PEERS 16
+#define PC_IPC_HANDLE_BYTES 64
+int pc_peer_create(pc_handle h, int32_t rank, int32_t n_ranks, int64_t n_gauss, int32_t n_units,
+                   uint8_t *handle_out);
+int pc_peer_connect(pc_handle h, const uint8_t *handles);
+int pc_peer_buffers(pc_handle h, int32_t which, double **acc, double **tsum, double **tmax);
+int pc_update_params_peer(pc_handle h, int32_t mix, int32_t dim, const double *dev_shift,
+                          const double *dev_inv_scale, double c_covariance, int32_t fix_code, double *dev_mean,
+                          double *dev_var, double *dev_alpha, double *dev_transmat, void *stream);
+int pc_peer_destroy(pc_handle h);
 
 /* One full EM iteration the way AcousticModel.embedded_training runs it (AcousticModel.py:842-882)
  * with HOST inputs and outputs: frames [total_frames][dim] float (pinned or pageable), parameters

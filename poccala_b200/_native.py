@@ -88,6 +88,12 @@ _SIGS = {
     "pc_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
     "pc_frame_moments_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
     "pc_set_reduce_hook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "pc_peer_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "pc_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pc_peer_buffers": (C.c_int, [C.c_void_p, C.c_int32] + [C.POINTER(C.c_void_p)] * 3),
+    "pc_update_params_peer": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
+                              + [C.c_void_p] * 5),
+    "pc_peer_destroy": (C.c_int, [C.c_void_p]),
     "pc_em_iteration_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
                              + [C.c_void_p] * 6 + [C.c_double, C.c_int32, C.c_void_p, C.c_void_p]),
 }
@@ -111,10 +117,18 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.pc_abi_version() != 2:
+        if l.pc_abi_version() != 3:
             raise RuntimeError("poccala_b200: ABI version mismatch")
         _lib = l
     return _lib
+
+
+_CONSTS = {"PC_MAX_PEERS": 16}
+
+
+def lib_const(name):
+    """Constants of include/poccala_b200.h the host side needs."""
+    return _CONSTS[name]
 
 
 def check(code):

@@ -65,6 +65,7 @@ int pc_create(int device, pc_handle *out) {
 int pc_destroy(pc_handle h) {
     if (!h) return PC_OK;
     cudaSetDevice(h->device);
+    pc_peer_destroy(h);
     if (h->ws) cudaFree(h->ws);
     if (h->dev_counters) cudaFree(h->dev_counters);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -102,13 +103,14 @@ int64_t pc_get_option(pc_handle h, const char *key) {
     if (!strcmp(key, "k2_kernel")) return h->k2_kernel;
     if (!strcmp(key, "k1_kernel")) return h->k1_kernel;
     if (!strcmp(key, "k3_kernel")) return h->k3_kernel;
-    if (!strcmp(key, "clamped")) {
-        const int idx = PC_CNT_CLAMPED;
+    if (!strcmp(key, "peer_epoch")) return h->peer_epoch;
+    if (!strcmp(key, "clamped") || !strcmp(key, "peer_timeouts")) {
+        const int idx = !strcmp(key, "clamped") ? PC_CNT_CLAMPED : PC_CNT_PEER_TIMEOUT;
         int n = 0;
         if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
             cudaMemcpy(&n, h->dev_counters + idx, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
             return -1;
-        if (idx == PC_CNT_CLAMPED && n != 0) cudaMemset(h->dev_counters + idx, 0, sizeof(int));
+        if (n != 0) cudaMemset(h->dev_counters + idx, 0, sizeof(int));
         return n;
     }
     return -1;
@@ -783,6 +785,88 @@ int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_t
     return PC_OK;
 }
 
+// --------------------------------------------------------------------------------- peer-memory reduction
+static size_t peer_set_doubles(pc_handle h) { return (size_t)h->peer_n_acc + 2 * (size_t)h->peer_n_units * PC_TRANS_SLOTS; }
+static size_t peer_block_bytes(pc_handle h) { return 3 * peer_set_doubles(h) * sizeof(double) + 256; }
+
+int pc_peer_destroy(pc_handle h) {
+    if (!h || h->peer_n == 0) return PC_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < h->peer_n; ++r) {
+        if (!h->peer_block[r]) continue;
+        if (r == h->peer_rank) cudaFree(h->peer_block[r]);
+        else cudaIpcCloseMemHandle(h->peer_block[r]);
+        h->peer_block[r] = nullptr;
+    }
+    h->peer_n = 0;
+    h->peer_epoch = 0;
+    return PC_OK;
+}
+
+int pc_peer_create(pc_handle h, int32_t rank, int32_t n_ranks, int64_t n_gauss, int32_t n_units,
+                   uint8_t *handle_out) {
+    PC_ENTER(h);
+    PC_REQUIRE(handle_out && n_ranks >= 1 && n_ranks <= PC_MAX_PEERS && rank >= 0 && rank < n_ranks && n_gauss > 0 &&
+                   n_units > 0, "pc_peer_create: rank %d of %d (at most %d), %lld Gaussians, %d units", rank, n_ranks,
+               PC_MAX_PEERS, (long long)n_gauss, n_units);
+    static_assert(sizeof(cudaIpcMemHandle_t) == PC_IPC_HANDLE_BYTES, "IPC handle size");
+    pc_peer_destroy(h);
+    h->peer_n = n_ranks;
+    h->peer_rank = rank;
+    h->peer_n_acc = n_gauss * PC_KA;
+    h->peer_n_units = n_units;
+    h->peer_epoch = 0;
+    for (int r = 0; r < PC_MAX_PEERS; ++r) h->peer_block[r] = nullptr;
+    const size_t bytes = peer_block_bytes(h);
+    if (cudaMalloc(&h->peer_block[rank], bytes) != cudaSuccess) {
+        h->peer_n = 0;
+        pc_set_error("pc_peer_create: cudaMalloc of %zu bytes failed", bytes);
+        return PC_ERR_CUDA;
+    }
+    PC_CUDA_TRY(cudaMemset(h->peer_block[rank], 0, bytes));
+    cudaIpcMemHandle_t ipc;
+    PC_CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->peer_block[rank]));
+    memcpy(handle_out, &ipc, sizeof(ipc));
+    return PC_OK;
+}
+
+int pc_peer_connect(pc_handle h, const uint8_t *handles) {
+    PC_ENTER(h);
+    PC_REQUIRE(handles && h->peer_n > 0, "pc_peer_connect: pc_peer_create first");
+    for (int r = 0; r < h->peer_n; ++r) {
+        if (r == h->peer_rank) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + (size_t)r * PC_IPC_HANDLE_BYTES, sizeof(ipc));
+        PC_CUDA_TRY(cudaIpcOpenMemHandle(&h->peer_block[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    return PC_OK;
+}
+
+int pc_peer_buffers(pc_handle h, int32_t which, double **acc, double **tsum, double **tmax) {
+    PC_REQUIRE(h && h->peer_n > 0 && which >= 0 && which <= 2, "pc_peer_buffers: no exchange block / which=%d", which);
+    double *set = (double *)h->peer_block[h->peer_rank] + (size_t)which * peer_set_doubles(h);
+    if (acc) *acc = set;
+    if (tsum) *tsum = set + h->peer_n_acc;
+    if (tmax) *tmax = set + h->peer_n_acc + (size_t)h->peer_n_units * PC_TRANS_SLOTS;
+    return PC_OK;
+}
+
+int pc_update_params_peer(pc_handle h, int32_t mix, int32_t dim, const double *shift, const double *inv_scale,
+                          double c_cov, int32_t fix_code, double *mean, double *var, double *alpha, double *transmat,
+                          void *stream) {
+    PC_ENTER(h);
+    PC_REQUIRE(h->peer_n > 0, "pc_update_params_peer: no exchange block (pc_peer_create / pc_peer_connect)");
+    PC_REQUIRE(mean && var && alpha && transmat, "pc_update_params_peer: NULL parameter pointer");
+    int rc = check_dim_mix("pc_update_params_peer", dim, mix);
+    if (rc) return rc;
+    PC_REQUIRE((int64_t)h->peer_n_units * PC_EMIT * mix * PC_KA == h->peer_n_acc,
+               "pc_update_params_peer: the block was created for %lld statistics, mix=%d needs %lld",
+               (long long)h->peer_n_acc, mix, (long long)h->peer_n_units * PC_EMIT * mix * PC_KA);
+    return launch_update_params_peer(h, mix, dim, shift, inv_scale, c_cov, fix_code, mean, var, alpha, transmat,
+                                     (cudaStream_t)stream);
+}
+
 int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int32_t dim,
                          int32_t n_units, int32_t mix, double *host_mean, double *host_var,
                          double *host_alpha, double *host_transmat, const double *host_shift,
@@ -822,9 +906,14 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
     char *ws = (char *)h->ws;
     float *raw = (float *)(ws + o_raw), *X = (float *)(ws + o_X), *b = (float *)(ws + o_b);
     float *lg = (float *)(ws + o_lg), *W = (float *)(ws + o_W), *pt = (float *)(ws + o_pt);
+    // statistics: the hook's exchange buffers, the current set of the peer-memory block, or the workspace
+    const bool peer = !h->hook && h->peer_n > 1;
+    PC_REQUIRE(!peer || (h->peer_n_acc == G * PC_KA && h->peer_n_units == n_units),
+               "pc_em_iteration_host: the peer exchange block was created for another model");
     double *flat = h->hook ? h->hook_flat : (double *)(ws + o_flat);
-    double *acc = flat, *tsum = flat + G * PC_KA;
     double *tmax = h->hook ? h->hook_tmax : (double *)(ws + o_tmax);
+    if (peer) pc_peer_buffers(h, (int32_t)(h->peer_epoch & 1), &flat, nullptr, &tmax);
+    double *acc = flat, *tsum = flat + G * PC_KA;
     double *mean = (double *)(ws + o_mean);
     double *var = (double *)(ws + o_var), *alpha = (double *)(ws + o_alpha);
     double *tm = (double *)(ws + o_tm), *ls = (double *)(ws + o_ls), *ln = (double *)(ws + o_ln);
@@ -922,8 +1011,13 @@ int pc_em_iteration_host(pc_handle h, pc_corpus c, const float *host_frames, int
         pc_set_error("pc_em_iteration_host: the reduce hook failed (SUM)");
         return PC_ERR_CUDA;
     }
-    if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, shift, inv_scale, c_cov,
-                                   fix_code, mean, var, alpha, tm, st))) return rc;
+    if (peer) {
+        if ((rc = launch_update_params_peer(h, mix, dim, shift, inv_scale, c_cov, fix_code, mean, var, alpha, tm, st)))
+            return rc;
+    } else if ((rc = launch_update_params(h, n_units, mix, dim, acc, tmax, tsum, shift, inv_scale, c_cov,
+                                          fix_code, mean, var, alpha, tm, st))) {
+        return rc;
+    }
     sum_double_kernel<<<1, 32, 0, st>>>(logp, c->v.n_utt, sum);
     PC_LAUNCH_CHECK();
     h->launches++;

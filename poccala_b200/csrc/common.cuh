@@ -164,8 +164,15 @@ struct pc_handle_s {
     void *hook_user;
     double *hook_tmax, *hook_flat;
     int64_t hook_flat_len;
+    // exchange blocks of the peer-memory reduction (peer.cu): [rank] = this rank's own allocation
+    int peer_n, peer_rank;
+    void *peer_block[PC_MAX_PEERS];
+    int64_t peer_n_acc;
+    int peer_n_units;
+    int64_t peer_epoch;  // M-steps run so far; buffer parity of the current iteration = peer_epoch & 1
 };
 #define PC_CNT_CLAMPED 0
+#define PC_CNT_PEER_TIMEOUT 1
 #define PC_CNT_N 8
 
 struct pc_corpus_s {
@@ -233,6 +240,8 @@ int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_l
 int launch_transitions_sum(pc_handle h, const CorpusView &v, const double *utt_logp,
                            const float *pair_trans, const double *tmax, double *tsum,
                            cudaStream_t st);
+int launch_update_params_peer(pc_handle h, int mix, int dim, const double *shift, const double *inv_scale, double c_cov,
+                              int fix_code, double *mean, double *var, double *alpha, double *transmat, cudaStream_t st);
 int launch_update_params(pc_handle h, int n_units, int mix, int dim, const double *acc,
                          const double *tmax, const double *tsum, const double *shift,
                          const double *inv_scale, double c_cov, int fix_code, double *mean,

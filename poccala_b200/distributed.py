@@ -10,9 +10,16 @@ Clustering.py:314-367); here that is two collectives per iteration:
 
 Every rank then runs the M-step on identical numbers: replicas stay bit-identical, no broadcast.
 The functions take tensors on any device - NCCL over NVLink on the GPUs, gloo in the CPU tests.
+
+On one NVLink / NVSwitch node the two collectives disappear altogether (PeerExchange): every rank's
+statistics live in a block the other ranks map through CUDA IPC, and the M-step kernels read and add the
+N copies themselves (csrc/peer.cu).  The process group is then only used to hand the IPC handles round.
 """
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -49,3 +56,65 @@ def allreduce_em_statistics(flat, tmax, compute_tsum, group=None):
 def log_accumulators(tmax, tsum):
     """(max, sum) pair -> the reference's log-domain accumulator values."""
     return tmax + torch.log(tsum)
+
+
+class _DeviceDoubles:
+    """A range of device memory owned by the library, for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerExchange:
+    """This rank's exchange block of the peer-memory reduction (pc_peer_*), connected to the blocks of all
+    ranks of `group` (which must live on one node).  `views(which)` wraps a statistic set as torch tensors
+    (acc [G,80], tsum [U,9], tmax [U,9]): which = 0 / 1 the sets of even / odd iterations, 2 the reduced sums
+    of the last M-step."""
+
+    def __init__(self, engine, n_units, n_gauss, group):
+        from . import _native as nat
+
+        self.engine, self.group = engine, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > nat.lib_const("PC_MAX_PEERS"):
+            raise ValueError("at most %d ranks share an exchange" % nat.lib_const("PC_MAX_PEERS"))
+        mine = np.zeros(64, dtype=np.uint8)
+        nat.call("pc_peer_create", engine.h, self.rank, self.world, int(n_gauss), int(n_units), nat._p(mine))
+        # the handles travel through the process group (a uint8 tensor: NCCL and gloo both carry it)
+        t = torch.as_tensor(mine).to(engine.device if dist.get_backend(group) == "nccl" else "cpu")
+        every = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(every, t, group=group)
+        handles = np.ascontiguousarray(torch.stack(every).cpu().numpy())
+        nat.call("pc_peer_connect", engine.h, nat._p(handles))
+        dist.barrier(group=group)  # nobody signals into a block that is not mapped yet
+        self.n_units, self.n_gauss = int(n_units), int(n_gauss)
+        self._views = [self._wrap(w) for w in range(3)]
+
+    def _wrap(self, which):
+        from . import _native as nat
+
+        ptrs = [C.c_void_p() for _ in range(3)]
+        nat.call("pc_peer_buffers", self.engine.h, which, *[C.byref(p) for p in ptrs])
+        sizes = (self.n_gauss * nat.KA, self.n_units * nat.TRANS_SLOTS, self.n_units * nat.TRANS_SLOTS)
+        acc, tsum, tmax = (torch.as_tensor(_DeviceDoubles(p.value, n), device=self.engine.device)
+                           for p, n in zip(ptrs, sizes))
+        return acc.view(self.n_gauss, nat.KA), tsum.view(self.n_units, nat.TRANS_SLOTS), tmax.view(self.n_units, nat.TRANS_SLOTS)
+
+    def views(self, which):
+        return self._views[which]
+
+    def current(self):
+        """(acc, tsum, tmax) the next M-step will reduce."""
+        return self._views[self.engine.get_option("peer_epoch") & 1]
+
+    def timeouts(self):
+        """Arrival waits that gave up since the last call (synchronises the device); 0 in a healthy run."""
+        return self.engine.get_option("peer_timeouts")
+
+    def close(self):
+        from . import _native as nat
+
+        self._views = None
+        dist.barrier(group=self.group)  # every rank is past its last read
+        nat.call("pc_peer_destroy", self.engine.h)

@@ -257,6 +257,19 @@ class EStep:
         self.inv_scale = None
         self.standardise = standardise
 
+    # peer-memory reduction ----------------------------------------------------------------
+    def use_peer(self, peer):
+        """Keep the statistics in `peer`'s exchange block (distributed.PeerExchange): estep() then runs no
+        collective at all, mstep() reduces over the ranks while it reads (pc_update_params_peer) and leaves
+        the summed statistics in acc / tsum / tmax."""
+        self.peer = peer
+        self._peer_bind()
+
+    def _peer_bind(self):
+        self.acc, self.tsum, self.tmax = self.peer.current()
+        self.flat = None
+        self._acc_clean = False
+
     # frames -------------------------------------------------------------------------------
     def load_frames(self, x, group=None, shift=None, inv_scale=None):
         """x: [F,D] float tensor on the device (utterances concatenated in corpus order).
@@ -342,7 +355,8 @@ class EStep:
         with torch.cuda.stream(side):
             nat.call("pc_transitions_max", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
                      _p(self.tmax), _stream())  # writes every (unit, slot): -inf where the unit has no pair
-            _dist.allreduce_transition_maxima(self.tmax, group)
+            if getattr(self, "peer", None) is None:  # (the peer M-step combines the ranks' (max, sum) pairs itself)
+                _dist.allreduce_transition_maxima(self.tmax, group)
             nat.call("pc_transitions_sum", self.engine.h, self.corpus.c, _p(self.utt_logp), _p(self.pair_trans),
                      _p(self.tmax), _p(self.tsum), _stream())
             self._side_done = torch.cuda.Event()
@@ -356,12 +370,15 @@ class EStep:
             self.reduce_transitions_async(group)
         torch.cuda.current_stream().wait_event(self._side_done)
         self._side_done = None
-        _dist.allreduce_flat_statistics(self.flat, group)
+        if getattr(self, "peer", None) is None:
+            _dist.allreduce_flat_statistics(self.flat, group)
 
     reduce_transitions = reduce_statistics
 
     def estep(self, fix_code=0, group=None):
         """(K1 || log bands) -> K2 -> (K3 || transition reductions) -> accumulator reduction."""
+        if getattr(self, "peer", None) is not None:
+            self._peer_bind()  # this iteration's statistic set
         self.log_bands_async()
         self.score()
         self.forward_backward()
@@ -374,6 +391,11 @@ class EStep:
 
     def mstep(self, c_covariance=1e-3, fix_code=0):
         m = self.model
+        if getattr(self, "peer", None) is not None:
+            nat.call("pc_update_params_peer", self.engine.h, m.mix, m.dim, _p(self.shift), _p(self.inv_scale),
+                     float(c_covariance), int(fix_code), _p(m.mean), _p(m.var), _p(m.alpha), _p(m.transmat), _stream())
+            self.acc, self.tsum, self.tmax = self.peer.views(2)  # the sums over the ranks
+            return
         nat.call("pc_update_params", self.engine.h, m.n_units, m.mix, m.dim, _p(self.acc), _p(self.tmax),
                  _p(self.tsum), _p(self.shift), _p(self.inv_scale), float(c_covariance), int(fix_code),
                  _p(m.mean), _p(m.var), _p(m.alpha), _p(m.transmat), _stream())

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_function():
     assert set(_native.EXPORTS) <= set(names)
     missing = set(names) - set(_native.EXPORTS) - {"pc_debug_read", "pc_debug_read_fb"}
     assert not missing, missing
-    assert lib.pc_abi_version() == 2
+    assert lib.pc_abi_version() == 3
 
 
 def test_product_path_has_no_cpu_fallback():
