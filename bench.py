@@ -254,7 +254,7 @@ def run_check(args):
     group = _init_group(world, local)
     eng = Engine(local)
     dev = eng.device
-    n_all, iters = 2000, 2
+    n_all, iters = 2000, 4  # four iterations: both statistic sets of the peer exchange are reused once
     truth, init0, labels, x = synth.torch_corpus(n_all, T, L, N_UNITS, MIX, 2, dev, N_INITIALS)  # identical on every rank
     tm0 = synth.default_transmat(N_UNITS)
 
@@ -300,7 +300,7 @@ def run_check(args):
     # One iteration from the same model: the shards change only the order of the fp32 partial sums inside the
     # accumulation kernel (a work item covers other tiles) - 2e-5.  The second iteration starts from models that
     # differ by that much, and components with little occupancy amplify it - 1e-3.
-    diffs1, diffs = diff(sharded_all[0], single_all[0]), diff(sharded_all[-1], single_all[-1])
+    diffs1, diffs = diff(sharded_all[0], single_all[0]), diff(sharded_all[1], single_all[1])
     sharded = sharded_all[-1]
     identical = True
     peer_diffs = peer_host_diffs = None
@@ -328,7 +328,7 @@ def run_check(args):
     # against the single-rank model after ONE iteration
     host_diffs = diff([torch.as_tensor(a).to(dev) for a in hp], single_all[0])
     ok = identical and max(diffs1.values()) <= 2e-5 and max(host_diffs.values()) <= 2e-5 and \
-        max(diffs.values()) <= 1e-3 and abs(llN[-1] - ll1[-1]) <= 1e-8 * abs(ll1[-1])
+        max(diffs.values()) <= 1e-3 and abs(llN[1] - ll1[1]) <= 1e-8 * abs(ll1[1])
     peer_timeouts = None
     if peer is not None:
         # the host entry point without a hook: the connected exchange block makes it reduce over peer memory
@@ -347,7 +347,7 @@ def run_check(args):
                           "replicas_bit_identical": identical, "diff_vs_single_rank_iteration_1": diffs1,
                           "diff_vs_single_rank_iteration_2": diffs,
                           "host_entry_diff_vs_single_rank_iteration_1": host_diffs,
-                          "peer_memory_vs_nccl_iteration_2": peer_diffs,
+                          "peer_memory_vs_nccl_iteration_4": peer_diffs,
                           "peer_memory_host_entry_diff_vs_single_rank_iteration_1": peer_host_diffs,
                           "peer_timeouts": peer_timeouts,
                           "sum_logp_single": ll1, "sum_logp_sharded": llN}), flush=True)
@@ -380,6 +380,12 @@ def run_gpu(args):
     model = Model(eng, init0[0], init0[1], init0[2], tm0)
     es = EStep(eng, corpus, model)
     es.load_frames(x, group=group)  # corpus-wide standardisation: identical on every rank
+    peer = None
+    if group is not None and args.collective == "peer":
+        from poccala_b200.distributed import PeerExchange
+
+        peer = PeerExchange(eng, N_UNITS, N_UNITS * 3 * MIX, group)
+        es.use_peer(peer)
     frames = corpus.total_frames
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -400,6 +406,8 @@ def run_gpu(args):
             es.em_iteration(c_covariance=1e-6, group=group)
             return
         ev[0].record()
+        if peer is not None:
+            es._peer_bind()  # this iteration's statistic set of the exchange block
         if not os.environ.get("PC_NO_BANDS_ASYNC"):
             es.log_bands_async()  # log(transmat) bands on the side stream, beside K1
         es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
@@ -450,7 +458,9 @@ def run_gpu(args):
     hp_t = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).clone().pin_memory() for a in list(init0) + [tm0]]
     hp = [t.numpy() for t in hp_t]
     shift_h, isc_h = frame_moments_host(eng, host_x.numpy(), group=group)
-    hook = HostReduceHook(eng, N_UNITS, N_UNITS * 3 * MIX, group) if group is not None else None
+    # N > 1: the connected exchange block makes the call reduce over peer memory; with --collective nccl the reduce
+    # hook queues the two all-reduces instead
+    hook = HostReduceHook(eng, N_UNITS, N_UNITS * 3 * MIX, group) if group is not None and peer is None else None
     e2e_steps = max(3, min(args.steps, 10))
     host_frames = host_x.numpy()
     for _ in range(2):
@@ -486,13 +496,21 @@ def run_gpu(args):
     pk, pk_src = peaks()
     kern_ms = {"K1_score": statistics.mean(k1), "K2_forward_backward": statistics.mean(k2),
                "K3_accumulate": statistics.mean(k3)}
-    del es, model, corpus, x
+    peer_used = peer is not None
+    peer_timeouts = None
+    if peer is not None:
+        peer_timeouts = peer.timeouts()
+        del es
+        peer.close()
+        peer = None
+    del model, corpus, x
+    es = None
     torch.cuda.empty_cache()
 
     # ---- BASELINE.json configs[4]: every rank takes part (the job is split over the ranks)
     cfg5 = None
     if args.cfg5_utt > 0:
-        cfg5 = cfg5_leg(eng, pk, group, world, rank, args.cfg5_utt, sync_all)
+        cfg5 = cfg5_leg(eng, pk, group, world, rank, args.cfg5_utt, sync_all, use_peer=peer_used)
 
     if rank != 0:
         if group is not None:
@@ -547,6 +565,9 @@ def run_gpu(args):
         "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "api": "pc_em_iteration_host", "pinned_h2d_gbs": h2d_gbs,
                 "collectives_inside": world > 1},
+        "collective": (None if world == 1 else ("peer-memory reduction inside the M-step kernels (CUDA IPC, NVLink loads)"
+                                                if peer_used else "NCCL all-reduce (MAX + SUM)")),
+        "peer_timeouts": peer_timeouts,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cfg5": cfg5,
@@ -617,7 +638,8 @@ def scoring_sweep_leg(eng, pk, F=10_000_000, G=4096, mix=64, slab=2_500_000):
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak}}
 
 
-def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=64, em_iters=5, kmeans_points=4096):
+def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=64, em_iters=5, kmeans_points=4096,
+             use_peer=False):
     """BASELINE.json configs[4]: data-parallel EM on `n_total` synthetic utterances (100k) split over the
     ranks, 64-mix IF HMMs: uniform segmentation -> per-state k-means (K = 64, the 171 states sharded over the
     ranks, parameters all-gathered) -> 5 Baum-Welch iterations with the NCCL accumulator all-reduce.  The
@@ -677,6 +699,12 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
     es = EStep(eng, corpus, model)
     es.load_frames(x, group=group)
     del x
+    peer = None
+    if use_peer and group is not None:
+        from poccala_b200.distributed import PeerExchange
+
+        peer = PeerExchange(eng, N_UNITS, N_UNITS * EMIT * mix, group)
+        es.use_peer(peer)
     es.em_iteration(c_covariance=1e-3, group=group)  # warm-up (first launches, NCCL buffers); its update is kept
     ms, ll = [], []
     for it in range(em_iters):
@@ -694,12 +722,17 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
     # stage split of one more iteration (events on the launch stream)
     sync_all()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    ev[0].record(); es.log_bands_async(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
+    ev[0].record()
+    if peer is not None:
+        es._peer_bind()
+    es.log_bands_async(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
     es.reduce_transitions_async(group); es.accumulate(); ev[3].record()
     es.reduce_statistics(group); es.mstep(c_covariance=1e-3); ev[4].record()
     torch.cuda.synchronize()
     stage = {"K1_score": ev[0].elapsed_time(ev[1]), "K2_forward_backward": ev[1].elapsed_time(ev[2]),
              "K3_accumulate": ev[2].elapsed_time(ev[3]), "reduce_mstep": ev[3].elapsed_time(ev[4])}
+    if os.environ.get("PC_BENCH_RANK_STAGES"):
+        print("rank %d cfg5 stages %s" % (rank, {k: round(v, 4) for k, v in stage.items()}), file=sys.stderr, flush=True)
     stage = {k: max_over_ranks(v) for k, v in stage.items()}
     active = nat.lib().pc_corpus_active_tiles(corpus.c) / max(nat.lib().pc_corpus_total_tiles(corpus.c), 1)
     frames_rank = n_utt * T5
@@ -709,7 +742,7 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
     out = {
         "workload": "cfg5: %d utterances x %d frames x %d IF units over %d GPU(s) (%d per rank), %d-mix, uniform "
                     "segmentation + per-state k-means (K = %d, <= %d pooled frames per state, states sharded over the "
-                    "ranks) + %d EM iterations with NCCL all-reduce" % (n_utt * world, T5, L5, world, n_utt, mix, mix,
+                    "ranks) + %d EM iterations with the cross-rank reduction" % (n_utt * world, T5, L5, world, n_utt, mix, mix,
                                                                         kmeans_points, em_iters),
         "n_gpus": world, "value": world * frames_rank / (it_ms * 1e-3), "unit": "frames/s",
         "ms_per_iteration": it_ms, "em_ms": ms, "stage_ms": stage,
@@ -723,6 +756,8 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
         "segmentation_s": t_seg, "sum_logp": ll, "k3_active_pair_frac": active,
     }
     del es, model, corpus
+    if peer is not None:
+        peer.close()
     torch.cuda.empty_cache()
     return out
 
@@ -791,6 +826,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--check", action="store_true", help="N-rank vs 1-rank model agreement instead of timing")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: reduction over peer memory inside the M-step kernels (default) or two NCCL all-reduces")
     ap.add_argument("--cfg5-utt", type=int, default=int(os.environ.get("PC_BENCH_CFG5_UTT", "100000")),
                     help="utterances of the configs[4] leg over all ranks (0 = skip the leg)")
     args = ap.parse_args()

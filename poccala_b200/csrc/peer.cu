@@ -26,11 +26,9 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ double ld_peer(const double *p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
+// statistics of a peer: read past the (incoherent) L1; no ordering of its own - every read sits behind the block's
+// arrival wait (acquire load + barrier) - so the compiler is free to keep many of them in flight
+__device__ __forceinline__ double ld_peer(const double *p) { return __ldcg(p); }
 
 struct PeerView {
     char *block[PC_MAX_PEERS];
@@ -67,7 +65,7 @@ __device__ __forceinline__ void peer_wait(const PeerView &pv, int epoch, int *ti
 
 // One block per state: sum the state's mix x 80 statistics over the ranks (rank order), keep the sum in the
 // `reduced` set, re-estimate the state (same arithmetic as update_gmm_kernel, reduce.cu).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 update_gmm_peer_kernel(PeerView pv, int parity, int epoch, int mix, int dim, const double *__restrict__ shift,
                        const double *__restrict__ inv_scale, double c_cov, double *mean, double *var, double *alpha,
                        int *timeouts) {
@@ -76,12 +74,35 @@ update_gmm_peer_kernel(PeerView pv, int parity, int epoch, int mix, int dim, con
     const int64_t state = blockIdx.x;
     const size_t base = (size_t)state * mix * PC_KA;
     double *reduced = reinterpret_cast<double *>(pv.block[pv.rank]) + 2 * pv.set_doubles + base;
-    for (int i = threadIdx.x; i < mix * PC_KA; i += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < pv.n; ++r)
-            s += ld_peer(reinterpret_cast<const double *>(pv.block[r]) + (size_t)parity * pv.set_doubles + base + i);
-        sm[i] = s;
-        reduced[i] = s;
+    // NVLink loads are latency-bound: each thread keeps 4 elements x up to 4 ranks in flight, ranks added in order
+    const size_t off = (size_t)parity * pv.set_doubles + base;
+    const int n_el = mix * PC_KA;
+    for (int i0 = threadIdx.x; i0 < n_el; i0 += 4 * blockDim.x) {
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r0 = 0; r0 < pv.n; r0 += 4) {
+            double v[4][4];
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const double *src = reinterpret_cast<const double *>(pv.block[min(r0 + rr, pv.n - 1)]) + off;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = i0 + e * blockDim.x;
+                    v[rr][e] = (r0 + rr < pv.n && i < n_el) ? ld_peer(src + i) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) s[e] += v[rr][e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e * blockDim.x;
+            if (i < n_el) {
+                sm[i] = s[e];
+                reduced[i] = s[e];
+            }
+        }
     }
     __syncthreads();
     double socc = 0.0;
@@ -177,7 +198,7 @@ int launch_update_params_peer(pc_handle h, int mix, int dim, const double *shift
     if (!(fix_code & 2)) {
         const size_t smem = (size_t)mix * PC_KA * sizeof(double);
         PC_CUDA_TRY(cudaFuncSetAttribute(update_gmm_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        update_gmm_peer_kernel<<<n_states, 256, smem, st>>>(pv, parity, epoch, mix, dim, shift, inv_scale, c_cov, mean,
+        update_gmm_peer_kernel<<<n_states, 512, smem, st>>>(pv, parity, epoch, mix, dim, shift, inv_scale, c_cov, mean,
                                                              var, alpha, timeouts);
         PC_LAUNCH_CHECK();
         h->launches++;
