@@ -293,8 +293,9 @@ int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_t
 /* Cross-rank reduction over PEER MEMORY (one process per GPU on one NVLink / NVSwitch node), the
  * device-side replacement of the accumulator-file merge (LHMM.py:256-290, Clustering.py:314-367;
  * AcousticModel.py:842-882): every rank keeps its statistics in an exchange block the other ranks map
- * through CUDA IPC, and the M-step kernels add the N copies in rank order while they read them - no
- * collective library call, replicas bit-identical.
+ * through CUDA IPC; the M-step of a state runs on its owner (state mod n_ranks), whose kernel adds the N copies of
+ * the state's rows in rank order while it reads them over NVLink and publishes the new parameters, which the other
+ * ranks copy - no collective library call, replicas bit-identical.
  *   pc_peer_create   allocates this rank's block (two alternating statistic sets + the reduced set + arrival
  *                    flags) and returns its 64-byte IPC handle;
  *   pc_peer_connect  takes the handles of ALL ranks in rank order ([n_ranks][64], own entry ignored); call a

@@ -787,7 +787,7 @@ int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_t
 
 // --------------------------------------------------------------------------------- peer-memory reduction
 static size_t peer_set_doubles(pc_handle h) { return (size_t)h->peer_n_acc + 2 * (size_t)h->peer_n_units * PC_TRANS_SLOTS; }
-static size_t peer_block_bytes(pc_handle h) { return 3 * peer_set_doubles(h) * sizeof(double) + 256; }
+static size_t peer_block_bytes(pc_handle h) { return 4 * peer_set_doubles(h) * sizeof(double) + 2 * PC_MAX_PEERS * sizeof(int) + 256; }
 
 int pc_peer_destroy(pc_handle h) {
     if (!h || h->peer_n == 0) return PC_OK;

@@ -3,7 +3,7 @@
 TAG=$1
 mkdir -p profiles/$TAG profiles/current /tmp/ncu_x
 cp gpurun_out/${TAG}_launches.csv profiles/$TAG/launches.csv
-for K in score_tc_kernel accumulate_tc_kernel fwdbwd_kernel; do
+for K in score_tc_wide_kernel accumulate_tcx_kernel fwdbwd_warp_kernel; do
   ncu -i gpurun_out/${TAG}_$K.ncu-rep --page raw --csv 2>/dev/null > /tmp/ncu_x/$K.raw.csv
   python - "$K" "$TAG" <<'PY'
 import csv, sys

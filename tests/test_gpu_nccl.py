@@ -43,8 +43,12 @@ def test_sharded_training_matches_single_rank_nccl(n):
     out = _run_check(n)
     assert out["check"] == "ok", out
     assert out["replicas_bit_identical"], out
-    # the shards regroup the fp32 partial sums of the accumulation kernel: 2e-5 after one iteration from the same model
-    # (measured 1.6e-5 on a variance, 5e-7 on the means), for the device-resident path and the host entry point alike
-    assert max(out["diff_vs_single_rank_iteration_1"].values()) <= 2e-5, out
-    assert max(out["host_entry_diff_vs_single_rank_iteration_1"].values()) <= 2e-5, out
+    # the shards regroup the fp32 partial sums of the accumulation kernel: 5e-5 after one iteration from the same model
+    # (measured on a variance 1.6e-5 at 2 ranks, 3.0e-5 at 8; 7e-7 on the means), for the device-resident path, the host
+    # entry point with the NCCL hook and the host entry point over peer memory alike
+    assert max(out["diff_vs_single_rank_iteration_1"].values()) <= 5e-5, out
+    assert max(out["host_entry_diff_vs_single_rank_iteration_1"].values()) <= 5e-5, out
+    assert max(out["peer_memory_host_entry_diff_vs_single_rank_iteration_1"].values()) <= 5e-5, out
     assert max(out["diff_vs_single_rank_iteration_2"].values()) <= 1e-3, out
+    # the peer-memory reduction gives the NCCL reduction's model (sums of N terms in another order), no waits gave up
+    assert max(out["peer_memory_vs_nccl_iteration_4"].values()) <= 1e-9 and out["peer_timeouts"] == 0, out
