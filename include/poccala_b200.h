@@ -290,6 +290,20 @@ typedef int (*pc_reduce_hook)(void *user, int32_t op, void *stream);
 int pc_set_reduce_hook(pc_handle h, pc_reduce_hook fn, void *user, double *dev_tmax, double *dev_flat,
                        int64_t flat_len);
 
+/* Front end.  pc_mfcc: AudioProcessing.MFCC.mfcc (AudioProcessing.py:416-448: pre-emphasis
+ * :195-198, framing :215-227, the per-frame Hamming factor :243-246, |rfft| :262-263, filter bank + frame energy
+ * :328-343, log + DCT :355-368, deltas :405-412) on device buffers, fp64.  dev_signal double [n_samples] (the samples
+ * after AudioProcessing.MFCC.init_audio's zero removal); frame geometry as frame_blocking computes it (framesize =
+ * int(rate * sampletime), step = int(framesize * overlap), n_frames = 1 + ceil((n_samples - framesize) / step) >= 2);
+ * nfft a power of two in [64, 2048]; dev_fbank double [n_filters][nfft/2 + 1] the triangular responses (host-built
+ * with the reference's expression); dev_out double [n_frames][n_ceps * (1 + n_delta)], n_delta in {0, 1, 2}.
+ * pc_vad_distance: VAD.mel_distance + VAD.osf (:462-506): dev_dist / dev_dist_osf double [n_frames]. */
+int pc_mfcc(pc_handle h, const double *dev_signal, int64_t n_samples, int32_t framesize, int32_t step,
+            int32_t n_frames, int32_t nfft, const double *dev_fbank, int32_t n_filters, int32_t n_ceps,
+            int32_t cal_energy, int32_t n_delta, double *dev_out, void *stream);
+int pc_vad_distance(pc_handle h, const double *dev_mfcc, int32_t n_frames, int32_t dim, int32_t sample_size,
+                    double alpha, double beta, double *dev_dist, double *dev_dist_osf, void *stream);
+
 /* Cross-rank reduction over PEER MEMORY (one process per GPU on one NVLink / NVSwitch node), the
  * device-side replacement of the accumulator-file merge (LHMM.py:256-290, Clustering.py:314-367;
  * AcousticModel.py:842-882): every rank keeps its statistics in an exchange block the other ranks map

@@ -52,6 +52,7 @@ class AcousticModel(object):
         self.__state_num = state_num
         self.__mix_level = mix_level
         self.__vector_size = dct_num * (1 + int(bool(delta_1)) + int(bool(delta_2)))
+        self.__dct_num, self.__delta_1, self.__delta_2 = dct_num, delta_1, delta_2
         self.__unit_file_path = unit_file_path
         self.__device = device
         self.__loaded_units = []
@@ -209,6 +210,19 @@ class AcousticModel(object):
             for file in d[2]:
                 name = file.split('.')[0]
                 yield audiopath + '/%s.wav\n' % name, labelpath + '/%s.wav.trn\n' % name
+
+    def load_audio(self, audiopath):
+        """AcousticModel.__load_audio (AcousticModel.py:463-477): MFCC features of a wave file (with the first and
+        second differences the model was configured with), frames the cepstral-distance detector rejects removed.
+        Computed on the device (csrc/mfcc.cu)."""
+        from .AudioProcessing import AudioProcessing
+
+        mfcc = AudioProcessing.MFCC(self.__dct_num)
+        mfcc.init_audio(path=audiopath)
+        m = mfcc.mfcc(nfft=512, d1=self.__delta_1, d2=self.__delta_2)
+        vad = AudioProcessing.VAD()
+        vad.init_mfcc(m)
+        return vad.mfcc()
 
     # ---- sentence HMM assembly (AcousticModel.py:957-1014) ----------------------------------
     def embedded(self, label, hmm_list, data_index, alter=15):

@@ -88,6 +88,10 @@ _SIGS = {
     "pc_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
     "pc_frame_moments_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 3),
     "pc_set_reduce_hook": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "pc_mfcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 4 + [C.c_void_p] + [C.c_int32] * 4
+                + [C.c_void_p, C.c_void_p]),
+    "pc_vad_distance": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 3 + [C.c_double, C.c_double]
+                        + [C.c_void_p] * 3),
     "pc_peer_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "pc_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pc_peer_buffers": (C.c_int, [C.c_void_p, C.c_int32] + [C.POINTER(C.c_void_p)] * 3),

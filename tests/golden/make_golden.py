@@ -259,6 +259,48 @@ def smem_golden():
     print("gmm_smem.npz written")
 
 
+def mfcc_golden():
+    """AudioProcessing.MFCC.mfcc + AudioProcessing.VAD (AudioProcessing.py:146-542) executed on two synthetic wave
+    files (16 kHz mono; 8 kHz stereo).  numpy 2 removed the binary mode of np.fromstring that init_audio calls
+    (:164): it is mapped to np.frombuffer for the run - the same bytes -> int16 conversion."""
+    import tempfile
+    import wave
+
+    rh.Harness(UNITS, MIX)
+    from StatisticalModel.AudioProcessing import AudioProcessing
+
+    np.fromstring = lambda b, dtype=float: np.frombuffer(b, dtype=dtype).copy()
+    out = {}
+    cases = [(16000, 1, 1.0, 3), (8000, 2, 1.5, 4)]
+    for c, (sr, nch, secs, seed) in enumerate(cases):
+        rng = np.random.default_rng(seed)
+        n = int(sr * secs)
+        t = np.arange(n) / sr
+        voiced = (t > 0.3 * secs) & (t < 0.8 * secs)
+        sig = 3000 * np.sin(2 * np.pi * 220 * t) * voiced + 900 * np.sin(2 * np.pi * 1330 * t + 1.0) * voiced
+        chans = [(sig * g + 200 * rng.normal(size=n)).astype(np.int16) for g in ([1.0] if nch == 1 else [1.0, 0.6])]
+        pcm = np.stack(chans, axis=1).reshape(-1)
+        path = os.path.join(tempfile.mkdtemp(), "x.wav")
+        w = wave.open(path, "wb")
+        w.setnchannels(nch); w.setsampwidth(2); w.setframerate(sr); w.writeframes(pcm.tobytes()); w.close()
+        m = AudioProcessing.MFCC(13)
+        m.init_audio(path=path)
+        feat = m.mfcc(nfft=512, d1=True, d2=True)
+        v = AudioProcessing.VAD()
+        v.init_mfcc(feat)
+        dist = v.mel_distance()
+        osf = v.osf(dist)
+        kept = v.detect(osf)
+        out[f"m{c}_pcm"], out[f"m{c}_rate"], out[f"m{c}_channels"] = pcm, sr, nch
+        out[f"m{c}_data"] = np.array(m.data)
+        out[f"m{c}_mfcc"], out[f"m{c}_dist"], out[f"m{c}_osf"], out[f"m{c}_kept"] = feat, dist, osf, kept
+        out[f"m{c}_static"] = m.mfcc(nfft=512, cal_energy=False)
+        print(c, "frames", feat.shape, "kept", kept.shape, "finite", bool(np.isfinite(feat).all()))
+    out["n"] = len(cases)
+    np.savez_compressed(os.path.join(OUT, "mfcc.npz"), **out)
+    print("mfcc.npz written")
+
+
 def alignment_golden():
     """Mode-1 data preparation executed as is: __eq_segment(mode='e') (AcousticModel.py:605-612), the
     post-Viterbi part of multi_process_data (:750-764, with discriminate :937-955) and __get_gmmdata
@@ -344,6 +386,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--gmm-em-only" in sys.argv:
         gmm_em_golden()
+        sys.exit(0)
+    if "--mfcc-only" in sys.argv:
+        mfcc_golden()
         sys.exit(0)
     if "--smem-only" in sys.argv:
         smem_golden()
