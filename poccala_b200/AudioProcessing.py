@@ -75,18 +75,18 @@ class AudioProcessing(object):
             """The response matrix of mel_filter_bank (AudioProcessing.py:302-343), [filterbanks][nfft // 2 + 1], with
             the reference's own expressions (natural-log mel scale, floor((nfft + 1) / rate * hz) bins, both flanks of a
             triangle rising)."""
-            high_hz = high_hz or samplerate / 2
-            mel = np.linspace(2595 * math.log(1 + low_hz / 700, math.e), 2595 * math.log(1 + high_hz / 700, math.e),
-                              filterbanks + 2)
-            hz = 700 * (np.exp(mel / 2595) - 1)
-            bin_ = np.floor((nfft + 1) / samplerate * hz)
-            response = np.zeros((filterbanks, nfft // 2 + 1))
-            for i in range(filterbanks):
-                for j in range(int(bin_[i]), int(bin_[i + 1])):
-                    response[i][j] = (j - int(bin_[i])) / (bin_[i + 1] - bin_[i])
-                for j in range(int(bin_[i + 1]), int(bin_[i + 2])):
-                    response[i][j] = (j - int(bin_[i + 1])) / (bin_[i + 2] - bin_[i + 1])
-            return response
+            top = high_hz or samplerate / 2
+            to_mel = lambda f: 2595 * math.log(1 + f / 700, math.e)  # noqa: E731  (natural log, as the reference has it)
+            edges_hz = 700 * (np.exp(np.linspace(to_mel(low_hz), to_mel(top), filterbanks + 2) / 2595) - 1)
+            edge = np.floor((nfft + 1) / samplerate * edges_hz)  # float bin positions, filterbanks + 2 of them
+            lo = edge.astype(np.int64)
+            out = np.zeros((filterbanks, nfft // 2 + 1))
+            for m in range(filterbanks):
+                # two ramps, each starting at 0 on its left edge: [lo_m, lo_m+1) and [lo_m+1, lo_m+2)
+                for a, b in ((m, m + 1), (m + 1, m + 2)):
+                    cols = np.arange(lo[a], lo[b])
+                    out[m, cols] = (cols - lo[a]) / (edge[b] - edge[a])
+            return out
 
         def mfcc(self, sampletime=0.025, overlap=0.5, nfft=512, cal_energy=True, d1=False, d2=False):
             """AudioProcessing.py:416-448 -> [frames, vec_num * (1 + d1 + d2)] fp64 numpy (d2 only with d1, as there)."""
