@@ -1,5 +1,6 @@
 """BASELINE.json's full sizes through size-independent properties (the oracle needs core-hours there):
-configs[1] (1 000 utterances x 300 frames x 10 units of 57, 16 mixtures) - posterior mass is conserved
+configs[1] (1 000 utterances x 300 frames x 10 units of 57, 16 mixtures) and a shard of configs[4] (the same shape
+with 64 mixtures) - posterior mass is conserved
 from K2 into K3's statistics, first moments match a direct fp64 reduction, utterance shards add up and
 per-utterance results do not depend on the batch they ran in; configs[3] (10 000 x 1 000 frames x 20
 units) - every Viterbi path is a legal monotone walk whose recomputed score equals the returned one,
@@ -37,8 +38,11 @@ def _estep(eng, init, labels, n_frames, x, n_units, shift=None, inv_scale=None):
     return corpus, model, es
 
 
-def test_cfg2_full_size_mass_conservation_and_shard_additivity(eng):
-    U, T, L, NU, M = 1000, 300, 10, 57, 16
+@pytest.mark.parametrize("U,M", [(1000, 16), (1500, 64)])
+def test_full_size_mass_conservation_and_shard_additivity(eng, U, M):
+    """(1000, 16): configs[1] as it is; (1500, 64): the configs[4] model (64 mixtures: the kernels for wide units) on
+    a 1 500-utterance shard of its corpus."""
+    T, L, NU = 300, 10, 57
     truth, init, labels, utts = synth.make_corpus(U, T, L, NU, M, 2)
     x = torch.as_tensor(np.concatenate(utts, axis=0)).to(eng.device)
     corpus, model, es = _estep(eng, init, labels, [T] * U, x, NU)
