@@ -114,6 +114,42 @@ def test_scores_tensor_core_vs_cuda_core_and_oracle(eng, mix):
     assert worst < 2e-3, worst
 
 
+@pytest.mark.parametrize("mix", [16, 32, 64])
+def test_scores_tile_and_label_shapes(eng, mix):
+    """The utterance-major scoring kernels hold their frame tiles in groups of three and hand unit images through
+    rings whose turn-around depends on the number of tiles and label positions: utterances of 1 .. 6 tiles (one
+    frame, one tile, the tile boundaries +-1, two groups) with 1, 2 and 7 label positions, both kernel
+    generations against each other and against the fp64 oracle."""
+    n_units = 5
+    rng = np.random.default_rng(100 + mix)
+    truth = synth.make_truth(n_units, mix, 300 + mix)
+    init = synth.perturb(*truth, seed=400 + mix)
+    lengths = [1, 2, 127, 128, 129, 256, 257, 300, 384, 385, 513, 700]
+    labels, utts = [], []
+    for i, T in enumerate(lengths):
+        L = (1, 2, 7)[i % 3]
+        lab = rng.integers(0, n_units, size=L).astype(np.int32)
+        labels.append(lab)
+        utts.append(synth.make_utterance(lab, T, truth, 500 + i))
+    corpus, model, es, om = _setup(eng, init, labels, utts, n_units)
+    out = {}
+    for k1 in (1, 0):
+        eng.set_option("k1_kernel", k1)
+        es.b.fill_(float("nan"))
+        es.score()
+        torch.cuda.synchronize()
+        out[k1] = es.b.clone()
+    eng.set_option("k1_kernel", 1)
+    for u, (lab, X) in enumerate(zip(labels, utts)):
+        c = fast.score_components_direct(om, lab[None], X[None])
+        b_ref = fast.lse(c, axis=-1)[0].T
+        b1 = corpus.emission_view(out[1], u).cpu().numpy()
+        b0 = corpus.emission_view(out[0], u).cpu().numpy()
+        assert np.isfinite(b1).all() and b1.shape == b_ref.shape
+        assert np.all(np.abs(b1 - b0) <= 1e-4 + 2e-7 * np.abs(b0)), (u, len(X), len(lab))
+        assert _relerr(b1, b_ref) < REL, (u, len(X), len(lab))
+
+
 def test_scores_tensor_core_dead_and_scaled_rows(eng):
     """alpha = 0 (log 0 constant) and a collapsed component whose weights exceed the fp16 range."""
     truth, init, labels, utts = synth.make_corpus(6, 200, 3, 3, 16, 77)
