@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libpoccala_b200.so")
+LIB_PATH = os.environ.get("POCCALA_B200_LIB") or os.path.join(_HERE, "_lib", "libpoccala_b200.so")  # (override: A/B runs)
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = -1, -2, -3, -4

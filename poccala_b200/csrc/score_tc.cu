@@ -89,22 +89,7 @@ __device__ __forceinline__ float state_lse(const float (&v_in)[MIX], const float
     float v[MIX];
 #pragma unroll
     for (int e = 0; e < MIX; ++e) v[e] = SCALED ? v_in[e] * __ldg(scale + e) : v_in[e];
-    float m0 = v[0], m1 = v[1 % MIX], m2 = v[2 % MIX], m3 = v[3 % MIX];
-#pragma unroll
-    for (int e = 4; e + 3 < MIX; e += 4) {
-        m0 = fmaxf(m0, v[e]); m1 = fmaxf(m1, v[e + 1]); m2 = fmaxf(m2, v[e + 2]); m3 = fmaxf(m3, v[e + 3]);
-    }
-    const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-    const float ms = mx * LOG2E;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-    for (int e = 0; e + 3 < MIX; e += 4) {
-        s0 += tc::ex2(fmaf(v[e], LOG2E, -ms));
-        s1 += tc::ex2(fmaf(v[e + 1], LOG2E, -ms));
-        s2 += tc::ex2(fmaf(v[e + 2], LOG2E, -ms));
-        s3 += tc::ex2(fmaf(v[e + 3], LOG2E, -ms));
-    }
-    return mx + LN2 * tc::lg2((s0 + s1) + (s2 + s3));
+    return tc::lse_packed<MIX, false>(v);
 }
 
 template <int MIX, bool SCALED>

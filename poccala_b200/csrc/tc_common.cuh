@@ -186,6 +186,66 @@ __device__ __forceinline__ float ex2_fma(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs and 3-input max (sm_100)
+// FFMA2 / FADD2 work on two floats per lane and instruction, FMNMX3 takes three inputs: the log-sum-exp epilogues are
+// bound by instruction issue, and these halve their multiply-add / add / max counts.  Same rounding as the scalar forms.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// log-sum-exp of MIX component scores (MIX in {4, 8, .., 64}); POLY: every fourth exponential on the FMA pipe
+// (ex2_fma) instead of the MUFU unit.  Sums run in four interleaved chains, as the scalar version did.
+template <int MIX, bool POLY>
+__device__ __forceinline__ float lse_packed(const float (&v)[MIX]) {
+    constexpr float LOG2E_ = 1.4426950408889634f, LN2_ = 0.6931471805599453f;
+    constexpr int H = MIX / 2;
+    float ma = v[0], mb = v[H];
+#pragma unroll
+    for (int e = 1; e + 1 < H; e += 2) {
+        ma = max3(ma, v[e], v[e + 1]);
+        mb = max3(mb, v[H + e], v[H + e + 1]);
+    }
+    ma = fmaxf(ma, v[H - 1]);
+    mb = fmaxf(mb, v[MIX - 1]);
+    const float mx = fmaxf(ma, mb);
+    const float nms = -mx * LOG2E_;
+    const uint64_t l2 = pack2(LOG2E_, LOG2E_), n2 = pack2(nms, nms);
+    uint64_t sa = pack2(0.f, 0.f), sb = sa;
+#pragma unroll
+    for (int e = 0; e + 3 < MIX; e += 4) {
+        float t0, t1, t2, t3;
+        unpack2(fma2(pack2(v[e], v[e + 1]), l2, n2), t0, t1);
+        unpack2(fma2(pack2(v[e + 2], v[e + 3]), l2, n2), t2, t3);
+        const float p3 = POLY ? ex2_fma(t3) : ex2(t3);
+        sa = add2(sa, pack2(ex2(t0), ex2(t1)));
+        sb = add2(sb, pack2(ex2(t2), p3));
+    }
+    float s0, s1, s2, s3;
+    unpack2(sa, s0, s1);
+    unpack2(sb, s2, s3);
+    return mx + LN2_ * lg2((s0 + s1) + (s2 + s3));
+}
+
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor, no swizzle ("interleave"): the operand is stored as 8x16-byte
 // core matrices (8 rows of the non-contracted dimension x 16 contiguous bytes of the other);
