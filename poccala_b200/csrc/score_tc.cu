@@ -89,7 +89,7 @@ __device__ __forceinline__ float state_lse(const float (&v_in)[MIX], const float
     float v[MIX];
 #pragma unroll
     for (int e = 0; e < MIX; ++e) v[e] = SCALED ? v_in[e] * __ldg(scale + e) : v_in[e];
-    return tc::lse_packed<MIX, false>(v);
+    return tc::lse_packed<MIX, 0>(v);
 }
 
 template <int MIX, bool SCALED>

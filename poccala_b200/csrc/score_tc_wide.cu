@@ -29,6 +29,10 @@
 //                                convert the next tile, then take the accumulator.
 #include "tc_common.cuh"
 
+#ifndef PC_K1W_POLY
+#define PC_K1W_POLY 1  // exponentials on the FMA pipe: 0 none, 1 every fourth, 2 every second (measured at cfg 2: 125 / 119 / 125 us)
+#endif
+
 __device__ long long g_k1w_dbg[8192];
 
 namespace {
@@ -77,7 +81,7 @@ __device__ __forceinline__ float state_lse_w(const float (&v_in)[MIX], const flo
     float v[MIX];
 #pragma unroll
     for (int e = 0; e < MIX; ++e) v[e] = SCALED ? v_in[e] * __ldg(scale + e) : v_in[e];
-    return tc::lse_packed<MIX, true>(v);  // every fourth exponential on the FMA pipe
+    return tc::lse_packed<MIX, PC_K1W_POLY>(v);  // every fourth exponential on the FMA pipe
 }
 
 template <int MIX>
@@ -292,7 +296,7 @@ score_tc_wide_kernel(CorpusView v, const float *__restrict__ X, const float *__r
                     // of a lane quarter come from the EPQ warps of that quarter: one named barrier per quarter
                     asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(C::EPQ * 32) : "memory");
                     if (rece) g_k1w_dbg[6656 + n_acc * 5 + 4] = clock64();
-                    if (!(dbg & 16)) {
+                    if (!(dbg & (16 | 64))) {
                         // CPR threads per frame (a power of two >= NCOL: no division), EW*32 / CPR frames per pass
                         constexpr int CPR = C::NCOL <= 16 ? 16 : (C::NCOL <= 32 ? 32 : 64);
                         constexpr int RPP = C::EPQ * 32 / CPR;  // frames per pass of the quarter's threads

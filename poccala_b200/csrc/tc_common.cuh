@@ -213,9 +213,28 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return d;
 }
 
-// log-sum-exp of MIX component scores (MIX in {4, 8, .., 64}); POLY: every fourth exponential on the FMA pipe
-// (ex2_fma) instead of the MUFU unit.  Sums run in four interleaved chains, as the scalar version did.
-template <int MIX, bool POLY>
+// two 2^x (x <= 0) at once on the FMA pipe: ex2_fma with the additions and the polynomial as packed instructions
+__device__ __forceinline__ uint64_t ex2_fma2(float x0, float x1) {
+    const uint64_t x = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+    const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+    const uint64_t one = pack2(1.f, 1.f), none = pack2(-1.f, -1.f);
+    const uint64_t t = add2(x, magic);
+    const uint64_t f = fma2(add2(t, nmagic), none, x);  // x - (t - magic)
+    uint64_t p = fma2(pack2(1.326472731307149e-3f, 1.326472731307149e-3f), f, pack2(9.671512991189957e-3f, 9.671512991189957e-3f));
+    p = fma2(p, f, pack2(5.550733581185341e-2f, 5.550733581185341e-2f));
+    p = fma2(p, f, pack2(0.24022242426872253f, 0.24022242426872253f));
+    p = fma2(p, f, pack2(0.6931470036506653f, 0.6931470036506653f));
+    p = fma2(p, f, one);
+    float p0, p1, t0, t1;
+    unpack2(p, p0, p1);
+    unpack2(t, t0, t1);
+    return pack2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
+                 __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+
+// log-sum-exp of MIX component scores (MIX in {4, 8, .., 64}); POLY: 0 = every exponential on the MUFU unit, 1 = every
+// fourth on the FMA pipe (ex2_fma), 2 = every second (packed, ex2_fma2).  Sums run in four interleaved chains.
+template <int MIX, int POLY>
 __device__ __forceinline__ float lse_packed(const float (&v)[MIX]) {
     constexpr float LOG2E_ = 1.4426950408889634f, LN2_ = 0.6931471805599453f;
     constexpr int H = MIX / 2;
@@ -236,9 +255,13 @@ __device__ __forceinline__ float lse_packed(const float (&v)[MIX]) {
         float t0, t1, t2, t3;
         unpack2(fma2(pack2(v[e], v[e + 1]), l2, n2), t0, t1);
         unpack2(fma2(pack2(v[e + 2], v[e + 3]), l2, n2), t2, t3);
-        const float p3 = POLY ? ex2_fma(t3) : ex2(t3);
         sa = add2(sa, pack2(ex2(t0), ex2(t1)));
-        sb = add2(sb, pack2(ex2(t2), p3));
+        if constexpr (POLY == 2) {
+            sb = add2(sb, ex2_fma2(t2, t3));
+        } else {
+            const float p3 = POLY == 1 ? ex2_fma(t3) : ex2(t3);
+            sb = add2(sb, pack2(ex2(t2), p3));
+        }
     }
     float s0, s1, s2, s3;
     unpack2(sa, s0, s1);

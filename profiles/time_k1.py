@@ -13,8 +13,10 @@ model = Model(eng, *init0, synth.default_transmat(57))
 es = EStep(eng, corpus, model)
 es.load_frames(x)
 ref = None
+import os
 for k in (1, 0):
     eng.set_option("k1_kernel", k)
+    eng.set_option("debug_flags", int(os.environ.get("K1_DBG", "0")))
     for _ in range(2):
         es.score()
     torch.cuda.synchronize()
