@@ -67,11 +67,13 @@ int pc_destroy(pc_handle h);
  * covered; the tests cross-check both on the same inputs); "host_chunks" caps the transfer pipeline
  * depth of pc_em_iteration_host (0 = 8); "debug_flags" is a tuning aid for the tcgen05 kernels (skip
  * stages, record block 0's phase clocks); "k1_kernel" 1 (default) = scoring kernel with wide accumulators
- * (several label positions per tcgen05 accumulator) for units of <= 16 mixtures, 0 = the per-position-pair
- * kernel for every mixture count; "k3_kernel" 1 (default) = accumulation kernel with the Gaussians on the
+ * (several label positions per tcgen05 accumulator) for units of <= 16 mixtures and resident frame tiles with the
+ * unit images in pieces for 64 mixtures, 0 = the per-position-pair kernel for every mixture count; "k3_kernel" 1 (default) = accumulation kernel with the Gaussians on the
  * accumulator lanes and gathered 32-frame blocks, 0 = one (128-frame tile, unit) pair at a time; "k2_kernel" 1 (default) = one warp per utterance, posteriors
  * normalised by the utterance likelihood; 0 = three warps per utterance with a per-frame normaliser (the
- * tests cross-check both); read-only: "launches" (kernels launched), "sm_count", "clamped" (standardised
+ * tests cross-check both); "kmeans_cluster" 1 (default) = k-means problems run on a thread-block cluster each when
+ * they are few and large, 0 = always one CTA per problem, 2 = always a cluster (same results, bit for bit);
+ * read-only: "launches" (kernels launched), "sm_count", "clamped" (standardised
  * feature values the frame preparation had to clamp to +-240 since the counter was last read: synchronises
  * the device and clears the counter; anything but 0 means the frames were not standardised - see
  * pc_frame_moments_host). */

@@ -52,6 +52,7 @@ int pc_create(int device, pc_handle *out) {
     h->k2_kernel = 1;
     h->k1_kernel = 1;
     h->k3_kernel = 1;
+    h->kmeans_cluster = 1;
     if (cudaMalloc((void **)&h->dev_counters, PC_CNT_N * sizeof(int)) != cudaSuccess ||
         cudaMemset(h->dev_counters, 0, PC_CNT_N * sizeof(int)) != cudaSuccess) {
         pc_set_error("pc_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -89,6 +90,7 @@ int pc_set_option(pc_handle h, const char *key, int64_t value) {
     if (!strcmp(key, "k2_kernel")) { h->k2_kernel = (int)value; return PC_OK; }
     if (!strcmp(key, "k1_kernel")) { h->k1_kernel = (int)value; return PC_OK; }
     if (!strcmp(key, "k3_kernel")) { h->k3_kernel = (int)value; return PC_OK; }
+    if (!strcmp(key, "kmeans_cluster")) { h->kmeans_cluster = (int)value; return PC_OK; }
     pc_set_error("pc_set_option: unknown key '%s'", key);
     return PC_ERR_INVALID;
 }
@@ -103,6 +105,7 @@ int64_t pc_get_option(pc_handle h, const char *key) {
     if (!strcmp(key, "k2_kernel")) return h->k2_kernel;
     if (!strcmp(key, "k1_kernel")) return h->k1_kernel;
     if (!strcmp(key, "k3_kernel")) return h->k3_kernel;
+    if (!strcmp(key, "kmeans_cluster")) return h->kmeans_cluster;
     if (!strcmp(key, "peer_epoch")) return h->peer_epoch;
     if (!strcmp(key, "clamped") || !strcmp(key, "peer_timeouts")) {
         const int idx = !strcmp(key, "clamped") ? PC_CNT_CLAMPED : PC_CNT_PEER_TIMEOUT;

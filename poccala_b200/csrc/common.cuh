@@ -158,6 +158,7 @@ struct pc_handle_s {
     int *dev_counters;
     int k1_kernel;       // option "k1_kernel": 1 = wide accumulators for <= 16 mixtures (score_tc_wide.cu), 0 = score_tc.cu only
     int k3_kernel;       // option "k3_kernel": 1 = Gaussians on the accumulator lanes, gathered frame blocks (accumulate_tcx.cu), 0 = accumulate_tc.cu
+    int kmeans_cluster;  // option "kmeans_cluster": 1 = problems beyond 20 480 points run on a thread-block cluster (kmeans.cu)
     int k2_kernel;       // option "k2_kernel": 1 = one warp per utterance (fwdbwd_warp.cu), 0 = three warps (fwdbwd.cu)
     // cross-rank reduction hook of the host-buffer entry point (pc_set_reduce_hook)
     pc_reduce_hook hook;

@@ -3,7 +3,8 @@ golden vectors of the executed reference (ClusterInitialization.kmeans(algorithm
 Clustering.py:838-1044) and against the oracle restatement on many seeded problems.
 Bar: memberships AND their insertion order bit-exact (integer work); means, variances and
 weights equal to the last ulp or two (sequential fp64 sums in the same order; the reference's
-`v ** 0.5` goes through libm pow, ours through sqrt)."""
+`v ** 0.5` goes through libm pow, ours through sqrt).  Both kernels (one CTA per problem / one thread-block cluster per
+problem) are held to the same vectors, and to each other at a size only the device reaches."""
 import random
 
 import numpy as np
@@ -17,11 +18,14 @@ from tests.helpers import load_golden  # noqa: E402
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["one-cta", "auto", "cluster"])
+def eng(request):
+    """Every test runs with one CTA per problem (large problems scan global memory), with the library's own choice, and
+    with a 16-CTA thread-block cluster per problem (slices in distributed shared memory): the same bits each time."""
     from poccala_b200.engine import Engine
 
     e = Engine(0)
+    e.set_option("kmeans_cluster", request.param)
     yield e
     e.close()
 
@@ -128,3 +132,30 @@ def test_kmeans_k1_flat_start_statistics(eng):
     assert (g["members"][0] == np.array(r["members"][0])).all()
     assert len(g["members"][0]) == 500
     assert np.abs(g["mean"] - r["mean"]).max() == 0
+
+
+def test_kmeans_cluster_equals_single_cta_at_scale(eng):
+    """60 000 points with duplicated metric coordinates, K = 32: the cluster kernel and the single-CTA kernel give
+    the same owners, member lists (insertion order), pass and move counts and statistics."""
+    from poccala_b200.engine import kmeans_run, kmeans_seed_points
+
+    if eng.get_option("kmeans_cluster") != 1:
+        pytest.skip("runs once")
+    rng = np.random.default_rng(11)
+    n, K = 60000, 32
+    centres = rng.normal(0, 1.0, size=(K, 39))
+    data = centres[rng.integers(0, K, size=n)] + rng.normal(size=(n, 39)) * 0.7
+    data[::5, 0] = np.round(data[::5, 0], 1)
+    seeds = kmeans_seed_points(np.ascontiguousarray(data[:, 0]), K, random.Random(5))
+    x = torch.as_tensor(data).to(eng.device)
+    res = {}
+    for mode in (2, 0):
+        eng.set_option("kmeans_cluster", mode)
+        res[mode] = kmeans_run(eng, x, np.array([0, n], dtype=np.int64), K, np.array([seeds], dtype=np.int32))
+        torch.cuda.synchronize()
+    eng.set_option("kmeans_cluster", 1)
+    for key in ("owner", "member_count", "passes", "moves", "mean", "var", "alpha"):
+        assert torch.equal(res[0][key], res[2][key]), key
+    used = int(res[0]["member_count"].sum())  # (the list has room for the doubly counted seed points, Q11)
+    assert torch.equal(res[0]["member_list"][:used], res[2]["member_list"][:used])
+    assert int(res[2]["passes"][0]) > 1000
