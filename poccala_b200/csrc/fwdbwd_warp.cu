@@ -77,6 +77,8 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
@@ -92,8 +94,12 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
                    float *__restrict__ pair_trans) {
     constexpr int CH = FW_CH;
     // two-stage ring of prefetched rows: every lane copies (and later reads) its own columns
-    __shared__ float sm_b[2][CH][32 * SPL], sm_n[2][CH][32 * SPL];
-    __shared__ __align__(16) float4 sm_f[2][CH];
+    // ring of NST chunks of rows: the rows of chunk i + NST - 1 are requested while chunk i is worked on, so a row has
+    // (NST - 1) chunks of chain time (~800 clk each) to arrive - with two stages every chunk waited ~1 000 clk for
+    // HBM / L2 (measured 244 clk per frame against ~100 of dependent latency)
+    constexpr int NST = SPL <= 2 ? 4 : (SPL <= 4 ? 3 : 2);
+    __shared__ float sm_b[NST][CH][32 * SPL], sm_n[NST][CH][32 * SPL];
+    __shared__ __align__(16) float4 sm_f[NST][CH];
     const int lane = threadIdx.x;
     const int idx = blockIdx.x;
     const int u = v.fb_order[idx];
@@ -189,12 +195,13 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
             }
             cp_async_commit();
         };
-        prefetch_b(0, tau_hi);
+#pragma unroll
+        for (int d = 0; d < NST - 1; ++d) prefetch_b(d, tau_hi - d * CH);
         int stage = 0;
         auto chunk = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             float es[CH][SPL], g2[CH];
-            cp_async_wait_all();
+            cp_async_wait<NST - 2>();
 #pragma unroll
             for (int k = 0; k < CH; ++k) {  // off the dependency chain
                 float e[SPL];
@@ -203,8 +210,8 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
                 g2[k] = ceilf(frame_max(e) * kLog2e);
                 shift_row(e, g2[k], es[k]);
             }
-            prefetch_b(stage ^ 1, tau_hi - CH);
-            stage ^= 1;
+            prefetch_b((stage + NST - 1) % NST, tau_hi - (NST - 1) * CH);
+            stage = (stage + 1) % NST;
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int tau = tau_hi - k;
@@ -243,6 +250,7 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
         };
         while (tau_hi >= CH) chunk(std::true_type{});
         if (tau_hi >= 1) chunk(std::false_type{});
+        cp_async_wait_all();  // the look-ahead requests past row 0 still target the ring the forward pass reuses
     }
     if (trace) g_fw_dbg[1] = clock64();
     float e0[SPL];
@@ -381,12 +389,13 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
             }
             cp_async_commit();
         };
-        prefetch_f(0, tau_lo);
+#pragma unroll
+        for (int d = 0; d < NST - 1; ++d) prefetch_f(d, tau_lo + d * CH);
         int stage = 0;
         auto chunk = [&](auto full_tag) {
             constexpr bool FULL = decltype(full_tag)::value;
             float es[CH][SPL], nbc[CH][SPL], g2[CH], db[CH];
-            cp_async_wait_all();
+            cp_async_wait<NST - 2>();
             __syncwarp();  // the per-frame records were fetched by lanes 0 .. CH-1
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
@@ -402,8 +411,8 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
                 shift_row(e, g2[k], es[k]);
             }
             __syncwarp();  // every lane has read the records before the other stage's refill can land on a reused slot
-            prefetch_f(stage ^ 1, tau_lo + CH);
-            stage ^= 1;
+            prefetch_f((stage + NST - 1) % NST, tau_lo + (NST - 1) * CH);
+            stage = (stage + 1) % NST;
             float xs[CH][SPL], xn[CH][SPL], lg2_last[SPL];
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
@@ -474,6 +483,7 @@ fwdbwd_warp_kernel(CorpusView v, const float *__restrict__ b, const double *__re
         };
         while (tau_lo + CH - 1 <= T - 1) chunk(std::true_type{});
         if (tau_lo <= T - 1) chunk(std::false_type{});
+        cp_async_wait_all();
         if (T > 1 && ((T - 1) & (PC_BLOCK_ROWS - 1)) != PC_BLOCK_ROWS - 1) flag_block(T - 1);  // the last, partial block
     }
     // the move counts were collected at the destination state: state s's "next" count sits with state s + 1
