@@ -382,7 +382,7 @@ def run_gpu(args):
     es = EStep(eng, corpus, model)
     es.load_frames(x, group=group)  # corpus-wide standardisation: identical on every rank
     peer = None
-    if group is not None and args.collective == "peer":
+    if group is not None and args.collective in ("peer", "auto"):
         from poccala_b200.distributed import PeerExchange
 
         peer = PeerExchange(eng, N_UNITS, N_UNITS * 3 * MIX, group)
@@ -407,7 +407,7 @@ def run_gpu(args):
             es.em_iteration(c_covariance=1e-6, group=group)
             return
         ev[0].record()
-        if peer is not None:
+        if getattr(es, "peer", None) is not None:
             es._peer_bind()  # this iteration's statistic set of the exchange block
         if not os.environ.get("PC_NO_BANDS_ASYNC"):
             es.log_bands_async()  # log(transmat) bands on the side stream, beside K1
@@ -418,6 +418,31 @@ def run_gpu(args):
         es.mstep(c_covariance=1e-6)
         ev[4].record()
 
+    trial_ms = None
+    if peer is not None and args.collective == "auto":
+        # both reductions for a few steps each (device time, max over ranks: every rank takes the same decision)
+        trial_ms = {}
+        for mode in ("nccl", "peer", "nccl", "peer"):
+            es.use_peer(peer) if mode == "peer" else es.use_nccl()
+            for _ in range(2):
+                flush.zero_()
+                step()
+            sync_all()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(6):
+                step()
+            t1.record()
+            torch.cuda.synchronize()
+            tm = torch.tensor([t0.elapsed_time(t1) / 6], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX, group=group)
+            trial_ms[mode] = min(trial_ms.get(mode, 1e9), float(tm.item()))
+        if trial_ms["peer"] <= trial_ms["nccl"]:
+            es.use_peer(peer)
+        else:
+            es.use_nccl()
+            peer.close()
+            peer = None
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
@@ -511,7 +536,8 @@ def run_gpu(args):
     # ---- BASELINE.json configs[4]: every rank takes part (the job is split over the ranks)
     cfg5 = None
     if args.cfg5_utt > 0:
-        cfg5 = cfg5_leg(eng, pk, group, world, rank, args.cfg5_utt, sync_all, use_peer=peer_used)
+        cfg5 = cfg5_leg(eng, pk, group, world, rank, args.cfg5_utt, sync_all,
+                        use_peer="auto" if args.collective == "auto" else peer_used)
 
     if rank != 0:
         if group is not None:
@@ -568,7 +594,7 @@ def run_gpu(args):
                 "collectives_inside": world > 1},
         "collective": (None if world == 1 else ("peer-memory reduction inside the M-step kernels (CUDA IPC, NVLink loads)"
                                                 if peer_used else "NCCL all-reduce (MAX + SUM)")),
-        "peer_timeouts": peer_timeouts,
+        "peer_timeouts": peer_timeouts, "collective_trial_ms_per_step": trial_ms,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cfg5": cfg5,
@@ -701,12 +727,31 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
     es.load_frames(x, group=group)
     del x
     peer = None
+    trial = None
     if use_peer and group is not None:
         from poccala_b200.distributed import PeerExchange
 
         peer = PeerExchange(eng, N_UNITS, N_UNITS * EMIT * mix, group)
         es.use_peer(peer)
     es.em_iteration(c_covariance=1e-3, group=group)  # warm-up (first launches, NCCL buffers); its update is kept
+    if peer is not None and use_peer == "auto":
+        trial = {}
+        for mode in ("nccl", "peer"):  # one iteration each after a warm-up of its own; the updates are kept
+            es.use_peer(peer) if mode == "peer" else es.use_nccl()
+            es.em_iteration(c_covariance=1e-3, group=group)
+            sync_all()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            es.em_iteration(c_covariance=1e-3, group=group)
+            t1.record()
+            torch.cuda.synchronize()
+            trial[mode] = max_over_ranks(t0.elapsed_time(t1))
+        if trial["peer"] <= trial["nccl"]:
+            es.use_peer(peer)
+        else:
+            es.use_nccl()
+            peer.close()
+            peer = None
     ms, ll = [], []
     for it in range(em_iters):
         sync_all()
@@ -724,7 +769,7 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
     sync_all()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
-    if peer is not None:
+    if getattr(es, "peer", None) is not None:
         es._peer_bind()
     es.log_bands_async(); es.score(); ev[1].record(); es.forward_backward(); ev[2].record()
     es.reduce_transitions_async(group); es.accumulate(); ev[3].record()
@@ -755,6 +800,8 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
                    "scan_gbs": scan_bytes / max(km_dev_ms * 1e-3, 1e-9) / 1e9,
                    "bound": "latency: K dependent masked arg-mins per pass over shared-memory resident points"},
         "segmentation_s": t_seg, "sum_logp": ll, "k3_active_pair_frac": active,
+        "collective": None if group is None else ("peer memory" if peer is not None else "nccl"),
+        "collective_trial_ms_per_iteration": trial,
     }
     del es, model, corpus
     if peer is not None:
@@ -827,9 +874,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--check", action="store_true", help="N-rank vs 1-rank model agreement instead of timing")
-    ap.add_argument("--collective", default="nccl", choices=["peer", "nccl"],
-                    help="N > 1: two NCCL all-reduces (default; the MAX one hidden under K3) or the reduction over peer "
-                         "memory inside the M-step kernels (measured slower on this pool, profiles/README.md)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: two NCCL all-reduces (the MAX one hidden under K3), the reduction over peer memory inside "
+                         "the M-step kernels, or (default) whichever is faster in a trial during the warm-up - NCCL's "
+                         "all-reduce of the 1.75 MB of statistics varies from box to box (profiles/README.md)")
     ap.add_argument("--cfg5-utt", type=int, default=int(os.environ.get("PC_BENCH_CFG5_UTT", "100000")),
                     help="utterances of the configs[4] leg over all ranks (0 = skip the leg)")
     args = ap.parse_args()

@@ -253,6 +253,7 @@ class EStep:
         self.acc = self.flat[:n_acc].view(model.n_gauss, KA)
         self.tsum = self.flat[n_acc:].view(model.n_units, SLOTS)
         self.tmax = e.empty((model.n_units, SLOTS), torch.float64)
+        self._own = (self.flat, self.acc, self.tsum, self.tmax)
         self.shift = None
         self.inv_scale = None
         self.standardise = standardise
@@ -264,6 +265,12 @@ class EStep:
         the summed statistics in acc / tsum / tmax."""
         self.peer = peer
         self._peer_bind()
+
+    def use_nccl(self):
+        """Back to the statistics buffers of this object and the NCCL reduction (undoes use_peer)."""
+        self.peer = None
+        self.flat, self.acc, self.tsum, self.tmax = self._own
+        self._acc_clean = False
 
     def _peer_bind(self):
         self.acc, self.tsum, self.tmax = self.peer.current()
