@@ -254,7 +254,7 @@ def run_check(args):
     group = _init_group(world, local)
     eng = Engine(local)
     dev = eng.device
-    n_all, iters = 2000, 4  # four iterations: both statistic sets of the peer exchange are reused once
+    n_all, iters = 2000, 4  # four full iterations (both statistic sets of the peer exchange are reused once) + two partial ones
     truth, init0, labels, x = synth.torch_corpus(n_all, T, L, N_UNITS, MIX, 2, dev, N_INITIALS)  # identical on every rank
     tm0 = synth.default_transmat(N_UNITS)
 
@@ -267,8 +267,11 @@ def run_check(args):
         if peer is not None:
             es.use_peer(peer)
         ll, snaps = [], []
-        for _ in range(iters):
-            es.em_iteration(c_covariance=1e-6, group=grp)
+        # the fifth and sixth iteration keep the GMMs / the transitions fixed (fix_code 2 / 4, LHMM.py:66-75): the
+        # branches of the reductions that skip one of the two statistic sets
+        for it in range(iters + 2):
+            fix = 0 if it < iters else (2 if it == iters else 4)
+            es.em_iteration(c_covariance=1e-6, fix_code=fix, group=grp)
             s_ll = es.utt_logp.sum().reshape(1)
             if grp is not None:
                 dist.all_reduce(s_ll, group=grp)
@@ -348,7 +351,7 @@ def run_check(args):
                           "replicas_bit_identical": identical, "diff_vs_single_rank_iteration_1": diffs1,
                           "diff_vs_single_rank_iteration_2": diffs,
                           "host_entry_diff_vs_single_rank_iteration_1": host_diffs,
-                          "peer_memory_vs_nccl_iteration_4": peer_diffs,
+                          "peer_memory_vs_nccl_iteration_6": peer_diffs,
                           "peer_memory_host_entry_diff_vs_single_rank_iteration_1": peer_host_diffs,
                           "peer_timeouts": peer_timeouts,
                           "sum_logp_single": ll1, "sum_logp_sharded": llN}), flush=True)
