@@ -218,6 +218,10 @@ def smem_golden():
         def w_smem(q, **kw):
             rec["q_in"] = q
             rec["q"], rec["max"] = [], []
+            # the tables the search starts from: log posteriors of the last expectation(), current parameters
+            rec["gamma_in"] = np.array(g._GMM__gamma)
+            rec["mean_in"], rec["alpha_in"] = np.array(g.mean), np.array(g.alpha)
+            rec["var_in"] = np.stack([np.diag(x) for x in g.covariance])
             rec["ret"] = smem(q, **kw)
             return rec["ret"]
 
@@ -243,6 +247,8 @@ def smem_golden():
         out[f"s{c}_merge"] = np.array([[r[0], r[1], float(np.ravel(r[2])[0])] for r in rec["merge"]])
         out[f"s{c}_split"] = np.array([[r[0], float(np.ravel(r[1])[0])] for r in rec["split"]])
         out[f"s{c}_q_in"] = float(rec["q_in"])
+        out[f"s{c}_gamma_in"], out[f"s{c}_mean_in"] = rec["gamma_in"], rec["mean_in"]
+        out[f"s{c}_var_in"], out[f"s{c}_alpha_in"] = rec["var_in"], rec["alpha_in"]
         out[f"s{c}_q12"] = np.array([float(v) for v in rec["q"]])  # q_1 (three new components), q_2 (the rest)
         nm, nc, na = rec["max"][-1]
         out[f"s{c}_new_mean"] = np.array(nm)
