@@ -11,6 +11,8 @@ restated is cited per function (paths relative to /root/reference).
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 np.seterr(all="ignore")
@@ -561,3 +563,66 @@ def gmm_em(data, mean, var, alpha, c_covariance=1e-3, max_iter=10 ** 6):
         else:
             break
     return mean, var, alpha, iters, q_value
+
+
+# ---------------------------------------------------------------------------------- front end (section 8 f4)
+def mfcc_features(samples, rate, vec_num=13, sampletime=0.025, overlap=0.5, nfft=512, cal_energy=True, d1=False,
+                  d2=False, filterbanks=26):
+    """AudioProcessing.MFCC.mfcc (AudioProcessing.py:416-448) on an int16 / float sample array, stage by stage with
+    the reference's arithmetic: pre-emphasis shifted by one sample with a zero appended (:195-198), frames of
+    int(rate * sampletime) samples every int(framesize * overlap) (:215-227), ONE Hamming factor per frame computed
+    from the frame index (:243-246), |rfft(frame, nfft)| (:262-263), energy = sum of the magnitudes (:338), filter
+    responses with two rising flanks (:318-326), log, DCT with the (2k - 1) argument and 2 / sqrt(n) on every
+    coefficient (:355-368), coefficient 0 replaced by log energy, deltas over +-2 frames with edge padding (:405-412)."""
+    x = np.asarray(samples, dtype=np.float64)
+    y = np.append(x[1:] - 0.98 * x[:-1], 0.0)
+    framesize = int(rate * sampletime)
+    step = int(framesize * overlap)
+    framenum = 1 + math.ceil((len(y) - framesize) / step)
+    pad = (framenum - 1) * step + framesize
+    y = np.concatenate([y, np.zeros(int(pad - len(y)))])
+    frames = np.stack([y[f * step:f * step + framesize] for f in range(framenum)])
+    win = np.array([0.54 - 0.46 * math.cos(2 * math.pi * f / (framenum - 1)) for f in range(framenum)])
+    spec = np.absolute(np.fft.rfft(frames * win[:, None], nfft))
+    mel = np.linspace(0.0, 2595 * math.log(1 + (rate / 2) / 700), filterbanks + 2)
+    edge = np.floor((nfft + 1) / rate * (700 * (np.exp(mel / 2595) - 1)))
+    resp = np.zeros((filterbanks, nfft // 2 + 1))
+    for m in range(filterbanks):
+        a, b, c = int(edge[m]), int(edge[m + 1]), int(edge[m + 2])
+        resp[m, a:b] = (np.arange(a, b) - a) / (edge[m + 1] - edge[m])
+        resp[m, b:c] = (np.arange(b, c) - b) / (edge[m + 2] - edge[m + 1])
+    with np.errstate(divide="ignore"):
+        logfb = np.log(spec @ resp.T)
+        energy = np.log(spec.sum(axis=1))
+    k = np.arange(filterbanks)
+    basis = np.cos(np.pi * (2 * k[None, :] - 1) * np.arange(vec_num)[:, None] / (2 * filterbanks))
+    feat = (2 / filterbanks ** 0.5) * logfb @ basis.T
+    if cal_energy:
+        feat[:, 0] = energy
+
+    def delta(f):
+        p = np.pad(f, ((2, 2), (0, 0)), mode="edge")
+        return sum(i * p[2 + i:2 + i + len(f)] for i in range(-2, 3)) / 10.0
+
+    out = [feat]
+    if d1:
+        out.append(delta(feat))
+        if d2:
+            out.append(delta(out[-1]))
+    return np.concatenate(out, axis=1)
+
+
+def vad_filter(feat, sample=16, alpha=0.5, beta=0.93):
+    """AudioProcessing.VAD.mfcc (AudioProcessing.py:462-541): (distances, filtered distances, kept frames)."""
+    feat = np.asarray(feat, dtype=np.float64)
+    noise = 1.0 / sample * feat[:sample].sum(axis=0)
+    for i in range(sample):
+        noise = alpha * noise + (1 - alpha) * feat[i]
+    dist = np.sqrt(((noise[None] - feat) ** 2).sum(axis=1))
+    osf = dist.copy()
+    h = int(beta * (2 * sample + 1))
+    for i in range(sample, len(feat) - sample):
+        w = np.sort(dist[i - sample:i + sample])
+        osf[i] = (1 - beta) * w[h] + beta * w[h + 1]
+    thr = osf[int(sample / 2)] * (osf.max() - osf.min()) / osf.max()
+    return dist, osf, feat[osf - thr > 0.0]

@@ -53,3 +53,33 @@ def test_mfcc_and_vad_match_executed_reference(tmp_path):
         one = AudioProcessing.MFCC(13)
         one.set_signal(np.arange(1, 300, dtype=np.int16), 16000)
         one.mfcc()
+
+
+@pytest.mark.parametrize("rate,nfft,vec,d1,d2,n", [(44100, 512, 13, True, True, 30000), (16000, 1024, 12, True, False, 9000),
+                                                   (8000, 256, 13, False, False, 2600), (22050, 2048, 20, True, True, 12000)])
+def test_mfcc_other_geometries_match_the_oracle(rate, nfft, vec, d1, d2, n):
+    """Frames longer than the FFT (44.1 kHz: 1 102 samples cut to 512, AudioProcessing.py:262), other FFT lengths and
+    coefficient counts, with and without deltas, against the oracle restatement (itself pinned to the executed reference
+    by tests/test_oracle_golden.py)."""
+    from oracle import fast
+    from poccala_b200.AudioProcessing import AudioProcessing
+
+    rng = np.random.default_rng(rate + nfft)
+    t = np.arange(n) / rate
+    sig = (2500 * np.sin(2 * np.pi * 310 * t) * (t > 0.2 * t[-1]) + 150 * rng.normal(size=n)).astype(np.int16)
+    sig = sig[sig != 0]
+    m = AudioProcessing.MFCC(vec)
+    m.set_signal(sig, rate)
+    got = m.mfcc(nfft=nfft, d1=d1, d2=d2)
+    want = fast.mfcc_features(sig, rate, vec_num=vec, nfft=nfft, d1=d1, d2=d2)
+    assert got.shape == want.shape
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert _close(got[fin], want[fin]), np.abs(got[fin] - want[fin]).max()
+    if got.shape[0] >= 40:
+        v = AudioProcessing.VAD()
+        v.init_mfcc(np.where(fin, got, 0.0))
+        d, o, k = fast.vad_filter(np.where(fin, want, 0.0))
+        assert _close(v.mel_distance(), d) and _close(v.osf(None), o)
+        kept = v.mfcc()
+        assert kept.shape == k.shape and _close(kept, k)
