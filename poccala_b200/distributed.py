@@ -18,6 +18,7 @@ N copies themselves (csrc/peer.cu).  The process group is then only used to hand
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -90,6 +91,7 @@ class PeerExchange:
         dist.barrier(group=group)  # nobody signals into a block that is not mapped yet
         self.n_units, self.n_gauss = int(n_units), int(n_gauss)
         self._views = [self._wrap(w) for w in range(3)]
+        self._bound = weakref.WeakSet()  # EStep objects whose statistics live in this block (EStep.use_peer)
 
     def _wrap(self, which):
         from . import _native as nat
@@ -115,6 +117,8 @@ class PeerExchange:
     def close(self):
         from . import _native as nat
 
+        for es in list(self._bound):  # nobody keeps a view of memory that is about to be unmapped
+            es.use_nccl()
         self._views = None
         dist.barrier(group=self.group)  # every rank is past its last read
         nat.call("pc_peer_destroy", self.engine.h)

@@ -264,6 +264,7 @@ class EStep:
         collective at all, mstep() reduces over the ranks while it reads (pc_update_params_peer) and leaves
         the summed statistics in acc / tsum / tmax."""
         self.peer = peer
+        peer._bound.add(self)
         self._peer_bind()
 
     def use_nccl(self):
