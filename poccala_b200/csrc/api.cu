@@ -320,6 +320,8 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     size_t o_iact = add(nullptr, (size_t)(n_items + 1) * 4);           // directly behind: item counts + a ticket counter
     size_t o_titem = add(tile_item.data(), (size_t)n_tiles * 4);
     size_t o_iord = add(nullptr, (size_t)n_items * 4);
+    size_t o_ttmp = add(nullptr, (size_t)n_units * PC_TR_CHUNKS * PC_TRANS_SLOTS * 8);
+    size_t o_tcnt = add(nullptr, (size_t)n_units * 4);
     size_t o_sutt = add(sitem_utt.data(), (size_t)n_sitems * 4);
     size_t o_st0 = add(sitem_t0.data(), (size_t)n_sitems * 4);
     size_t o_snt = add(sitem_nt.data(), (size_t)n_sitems * 4);
@@ -391,6 +393,8 @@ int pc_corpus_create(pc_handle h, int32_t n_utt, const int32_t *n_frames, const 
     v.tile_active = (int32_t *)(dev + o_tact);
     v.tile_item = (const int32_t *)(dev + o_titem);
     v.item_act = (int32_t *)(dev + o_iact);
+    v.trans_tmp = (double *)(dev + o_ttmp);
+    v.trans_cnt = (int32_t *)(dev + o_tcnt);
     v.item_order = (int32_t *)(dev + o_iord);
     v.total_frames = frame_off[n_utt];
     v.n_sitems = (int32_t)n_sitems;

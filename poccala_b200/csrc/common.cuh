@@ -30,6 +30,7 @@ __host__ __device__ inline size_t pc_x32_offset(int64_t n_frames, int64_t n_xtil
 // accumulate_tc.cu); K2 sets the activity flags while it writes the rows, K3's own pre-pass does it
 // for log gamma that came from elsewhere.
 #define PC_ACTIVE_MIN_LGAM (-41.f * 0.6931471805599453f)
+#define PC_TR_CHUNKS 16  // blocks per unit in the transition reductions (fixed: the summation order depends on the corpus only)
 #define PC_MAX_CHUNKS 8  // host-buffer entry point: transfer / prepare / score pipeline depth
 
 // Device-side view of a corpus (all pointers device memory owned by pc_corpus_s).
@@ -66,6 +67,8 @@ struct CorpusView {
     const int32_t *tile_item;     // [n_tiles] work item of each unit-major tile
     int32_t *item_act;            // [n_items + 1] K3 scratch, directly behind tile_active: active tiles of the item; [n_items] = block ticket counter
     int32_t *item_order;          // [n_items] K3 scratch: items sorted by active tiles, heaviest first
+    double *trans_tmp;            // [n_units][PC_TR_CHUNKS][9] partial maxima / sums of the transition reductions
+    int32_t *trans_cnt;           // [n_units] blocks of a unit that have delivered their partial (self-resetting)
     // utterance-major work decomposition for K1: groups of <= 3 consecutive tiles of one utterance
     int64_t total_frames;
     int32_t n_sitems;

@@ -10,10 +10,12 @@
 // from the linear statistics.
 #include "common.cuh"
 
-// One block per unit: the unit's (utterance, position) pairs are contiguous in the unit-major pair
-// list, so the per-slot maximum and the per-slot sum of exp(value - max) are plain block
-// reductions - no atomics, and a fixed summation order (replicas of a rank's partial sums are
-// reproducible run to run).
+// PC_TR_CHUNKS blocks per unit: the unit's (utterance, position) pairs are contiguous in the unit-major pair list and are
+// cut into PC_TR_CHUNKS equal runs; every block reduces its run (block reduction: a fixed order), leaves the partial in
+// the corpus scratch, and the block of a unit that finishes last combines the partials IN CHUNK ORDER - no floating-point
+// atomics, and a summation order that depends on the corpus only (the partial sums of a rank are reproducible run to
+// run).  One block per unit (round 1) left 57 blocks with 17 500 pairs each at configs[4]: 1.5 ms, and the kernels do not
+// overlap the accumulation kernel, whose persistent CTAs leave no shared memory on any SM.
 #define TR_THREADS 128
 
 __device__ __forceinline__ double block_reduce(double v, bool is_max, double *sh) {
@@ -31,12 +33,41 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double *sh
     return r;
 }
 
+// the partial of (unit, chunk) is in place: the last block of the unit combines all of them in chunk order
+__device__ __forceinline__ void combine_chunks(const CorpusView &v, int unit, bool is_max, double *out) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(v.trans_cnt + unit, 1) == PC_TR_CHUNKS - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < PC_TRANS_SLOTS) {
+        const double *p = v.trans_tmp + (size_t)unit * PC_TR_CHUNKS * PC_TRANS_SLOTS + threadIdx.x;
+        double r = is_max ? -INFINITY : 0.0;
+        for (int c = 0; c < PC_TR_CHUNKS; ++c) {
+            const double x = __ldcg(p + (size_t)c * PC_TRANS_SLOTS);
+            r = is_max ? fmax(r, x) : r + x;
+        }
+        out[(size_t)unit * PC_TRANS_SLOTS + threadIdx.x] = r;
+    }
+    if (threadIdx.x == 0) v.trans_cnt[unit] = 0;  // clean for the next launch
+}
+
+__device__ __forceinline__ void chunk_range(const CorpusView &v, int unit, int chunk, int64_t &lo, int64_t &hi) {
+    const int64_t a = v.unit_pair_off[unit], b = v.unit_pair_off[unit + 1];
+    const int64_t len = (b - a + PC_TR_CHUNKS - 1) / PC_TR_CHUNKS;
+    lo = min(b, a + (int64_t)chunk * len);
+    hi = min(b, lo + len);
+}
+
 __global__ void __launch_bounds__(TR_THREADS)
 transitions_max_kernel(CorpusView v, const double *__restrict__ utt_logp,
                        const float *__restrict__ pair_trans, double *tmax) {
     __shared__ double sh[TR_THREADS / 32];
-    const int unit = blockIdx.x;
-    const int64_t lo = v.unit_pair_off[unit], hi = v.unit_pair_off[unit + 1];
+    const int unit = blockIdx.x, chunk = blockIdx.y;
+    int64_t lo, hi;
+    chunk_range(v, unit, chunk, lo, hi);
     double m[PC_TRANS_SLOTS];
 #pragma unroll
     for (int s = 0; s < PC_TRANS_SLOTS; ++s) m[s] = -INFINITY;
@@ -49,11 +80,13 @@ transitions_max_kernel(CorpusView v, const double *__restrict__ utt_logp,
             if (val > m[s]) m[s] = val;  // NaN and -inf never win
         }
     }
+    double *part = v.trans_tmp + ((size_t)unit * PC_TR_CHUNKS + chunk) * PC_TRANS_SLOTS;
 #pragma unroll
     for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
         const double r = block_reduce(m[s], true, sh);
-        if (threadIdx.x == 0) tmax[(size_t)unit * PC_TRANS_SLOTS + s] = r;
+        if (threadIdx.x == 0) part[s] = r;
     }
+    combine_chunks(v, unit, true, tmax);
 }
 
 __global__ void __launch_bounds__(TR_THREADS)
@@ -61,8 +94,9 @@ transitions_sum_kernel(CorpusView v, const double *__restrict__ utt_logp,
                        const float *__restrict__ pair_trans, const double *__restrict__ tmax,
                        double *tsum) {
     __shared__ double sh[TR_THREADS / 32];
-    const int unit = blockIdx.x;
-    const int64_t lo = v.unit_pair_off[unit], hi = v.unit_pair_off[unit + 1];
+    const int unit = blockIdx.x, chunk = blockIdx.y;
+    int64_t lo, hi;
+    chunk_range(v, unit, chunk, lo, hi);
     double acc[PC_TRANS_SLOTS], mx[PC_TRANS_SLOTS];
 #pragma unroll
     for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
@@ -80,44 +114,50 @@ transitions_sum_kernel(CorpusView v, const double *__restrict__ utt_logp,
             if (e > 0.0) acc[s] += e;
         }
     }
+    double *part = v.trans_tmp + ((size_t)unit * PC_TR_CHUNKS + chunk) * PC_TRANS_SLOTS;
 #pragma unroll
     for (int s = 0; s < PC_TRANS_SLOTS; ++s) {
         const double r = block_reduce(acc[s], false, sh);
-        if (threadIdx.x == 0) tsum[(size_t)unit * PC_TRANS_SLOTS + s] = r;
+        if (threadIdx.x == 0) part[s] = r;
     }
+    combine_chunks(v, unit, false, tsum);
 }
 
-// One thread per (gaussian, dimension); GMM part of the M-step.
-__global__ void update_gmm_kernel(int n_units, int mix, int dim, const double *__restrict__ acc,
-                                  const double *__restrict__ shift,
-                                  const double *__restrict__ inv_scale, double c_cov,
-                                  double *mean, double *var, double *alpha) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t n_g = (int64_t)n_units * PC_EMIT * mix;
-    if (i >= n_g * dim) return;
-    int64_t g = i / dim;
-    int d = (int)(i - g * dim);
-    int64_t state = g / mix;
+// GMM part of the M-step.  One block per state: the occupancies of the state's components are read once into shared
+// memory (a thread per (Gaussian, dimension) that summed them itself cost 64 loads per thread at 64 mixtures: 1.4 ms per
+// iteration at configs[4]), then one thread per (component, dimension).
+__global__ void __launch_bounds__(256)
+update_gmm_kernel(int n_units, int mix, int dim, const double *__restrict__ acc, const double *__restrict__ shift,
+                  const double *__restrict__ inv_scale, double c_cov, double *mean, double *var, double *alpha) {
+    __shared__ double occ_s[64];
+    const int64_t state = blockIdx.x;
+    const double *a0 = acc + (size_t)state * mix * PC_KA;
+    if ((int)threadIdx.x < mix) occ_s[threadIdx.x] = a0[(size_t)threadIdx.x * PC_KA + PC_XS - 1];
+    __syncthreads();
     double socc = 0.0;
-    for (int m = 0; m < mix; ++m) socc += acc[(size_t)(state * mix + m) * PC_KA + PC_XS - 1];
+    for (int m = 0; m < mix; ++m) socc += occ_s[m];  // component order: the same sum in every thread
     if (!(socc > 0.0)) return;  // unseen state: parameters stay (deviation D1)
-    const double *a = acc + (size_t)g * PC_KA;
-    double occ = a[PC_XS - 1];
-    if (!(occ > 0.0)) {  // component without any posterior mass: weight 0, mean / variance stay (D1)
-        if (d == 0) alpha[g] = 0.0;
-        return;
+    for (int i = threadIdx.x; i < mix * dim; i += blockDim.x) {
+        const int m = i / dim, d = i - m * dim;
+        const int64_t g = state * mix + m;
+        const double *a = a0 + (size_t)m * PC_KA;
+        const double occ = occ_s[m];
+        if (!(occ > 0.0)) {  // component without any posterior mass: weight 0, mean / variance stay (D1)
+            if (d == 0) alpha[g] = 0.0;
+            continue;
+        }
+        const double sx = a[d], sxx = a[PC_XS + d];
+        const double sh = shift ? shift[d] : 0.0;
+        const double is = inv_scale ? inv_scale[d] : 1.0;
+        const double mu_old_s = (mean[g * dim + d] - sh) * is;  // old mean in the standardised space of X
+        const double mu_s = sx / occ;
+        const double var_s = (sxx - 2.0 * mu_old_s * sx + mu_old_s * mu_old_s * occ) / occ;  // Q8: old mean
+        double v_new = var_s / (is * is);
+        if (v_new < c_cov) v_new = c_cov;  // Clustering.py:690-691
+        mean[g * dim + d] = sh + mu_s / is;
+        var[g * dim + d] = v_new;
+        if (d == 0) alpha[g] = occ / socc;
     }
-    double sx = a[d], sxx = a[PC_XS + d];
-    double sh = shift ? shift[d] : 0.0;
-    double is = inv_scale ? inv_scale[d] : 1.0;
-    double mu_old_s = (mean[i] - sh) * is;  // old mean in the standardised space of X
-    double mu_s = sx / occ;
-    double var_s = (sxx - 2.0 * mu_old_s * sx + mu_old_s * mu_old_s * occ) / occ;  // Q8: old mean
-    double v_new = var_s / (is * is);
-    if (v_new < c_cov) v_new = c_cov;  // Clustering.py:690-691
-    mean[i] = sh + mu_s / is;
-    var[i] = v_new;
-    if (d == 0) alpha[g] = occ / socc;
 }
 
 __global__ void update_transmat_kernel(int n_units, const double *__restrict__ tmax,
@@ -140,7 +180,7 @@ __global__ void update_transmat_kernel(int n_units, const double *__restrict__ t
 int launch_transitions_max(pc_handle h, const CorpusView &v, const double *utt_logp,
                            const float *pair_trans, double *tmax, cudaStream_t st) {
     if (v.n_units == 0) return PC_OK;
-    transitions_max_kernel<<<v.n_units, TR_THREADS, 0, st>>>(v, utt_logp, pair_trans, tmax);
+    transitions_max_kernel<<<dim3(v.n_units, PC_TR_CHUNKS), TR_THREADS, 0, st>>>(v, utt_logp, pair_trans, tmax);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -150,7 +190,7 @@ int launch_transitions_sum(pc_handle h, const CorpusView &v, const double *utt_l
                            const float *pair_trans, const double *tmax, double *tsum,
                            cudaStream_t st) {
     if (v.n_units == 0) return PC_OK;
-    transitions_sum_kernel<<<v.n_units, TR_THREADS, 0, st>>>(v, utt_logp, pair_trans, tmax, tsum);
+    transitions_sum_kernel<<<dim3(v.n_units, PC_TR_CHUNKS), TR_THREADS, 0, st>>>(v, utt_logp, pair_trans, tmax, tsum);
     PC_LAUNCH_CHECK();
     h->launches++;
     return PC_OK;
@@ -162,10 +202,8 @@ int launch_update_params(pc_handle h, int n_units, int mix, int dim, const doubl
                          double *var, double *alpha, double *transmat, cudaStream_t st) {
     if (n_units == 0) return PC_OK;
     if (!(fix_code & 2)) {
-        int64_t n = (int64_t)n_units * PC_EMIT * mix * dim;
-        update_gmm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_units, mix, dim, acc, shift,
-                                                                      inv_scale, c_cov, mean, var,
-                                                                      alpha);
+        update_gmm_kernel<<<(unsigned)(n_units * PC_EMIT), 256, 0, st>>>(n_units, mix, dim, acc, shift, inv_scale, c_cov,
+                                                                         mean, var, alpha);
         PC_LAUNCH_CHECK();
         h->launches++;
     }
