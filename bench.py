@@ -370,7 +370,7 @@ def run_check(args):
         em_iteration_host(eng, corpus_s, host_x, *hp2, c_covariance=1e-6, shift=shift, inv_scale=isc)
         peer_host_diffs = diff([torch.as_tensor(a).to(dev) for a in hp2], single_all[0])
         peer_timeouts = peer.timeouts()
-        ok = ok and max(peer_diffs.values()) <= 1e-9 and max(peer_host_diffs.values()) <= 5e-5 and peer_timeouts == 0
+        ok = ok and max(peer_diffs.values()) <= 1e-7 and max(peer_host_diffs.values()) <= 5e-5 and peer_timeouts == 0
         peer.close()
     flag = torch.tensor([0 if ok else 1], device=dev)
     if group is not None:
