@@ -319,7 +319,7 @@ class LHMM(object):
         if self.__fix_list[2]:
             raise UnsupportedModel("fix_code bit 1 (pi fixed): the kernel always runs the reference's pi re-estimation "
                                    "loop (LHMM.py:447-471); AcousticModel never fixes pi")
-        if len(self.__data) > 1:
+        if self.__data is not None and len(self.__data) > 1:
             raise UnsupportedModel("several data items in one sentence HMM: the reference re-estimates ONE pi from all of "
                                    "them jointly inside the iteration (LHMM.py:455-466); AcousticModel passes one utterance "
                                    "per sentence HMM (AcousticModel.py:907-912) - use one LHMM per utterance or the batched "
