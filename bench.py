@@ -416,11 +416,17 @@ def run_gpu(args):
     es = EStep(eng, corpus, model)
     es.load_frames(x, group=group)  # corpus-wide standardisation: identical on every rank
     peer = None
+    peer_error = None
     if group is not None and args.collective in ("peer", "auto"):
         from poccala_b200.distributed import PeerExchange
 
-        peer = PeerExchange(eng, N_UNITS, N_UNITS * 3 * MIX, group)
-        es.use_peer(peer)
+        try:
+            peer = PeerExchange(eng, N_UNITS, N_UNITS * 3 * MIX, group)  # (raises on every rank or on none)
+            es.use_peer(peer)
+        except RuntimeError as e:
+            if args.collective == "peer":
+                raise
+            peer_error = str(e)  # auto: NCCL it is
     frames = corpus.total_frames
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -571,7 +577,7 @@ def run_gpu(args):
     cfg5 = None
     if args.cfg5_utt > 0:
         cfg5 = cfg5_leg(eng, pk, group, world, rank, args.cfg5_utt, sync_all,
-                        use_peer="auto" if args.collective == "auto" else peer_used)
+                        use_peer=("auto" if args.collective == "auto" and peer_error is None else peer_used))
 
     if rank != 0:
         if group is not None:
@@ -628,7 +634,7 @@ def run_gpu(args):
                 "collectives_inside": world > 1},
         "collective": (None if world == 1 else ("peer-memory reduction inside the M-step kernels (CUDA IPC, NVLink loads)"
                                                 if peer_used else "NCCL all-reduce (MAX + SUM)")),
-        "peer_timeouts": peer_timeouts, "collective_trial_ms_per_step": trial_ms,
+        "peer_timeouts": peer_timeouts, "collective_trial_ms_per_step": trial_ms, "peer_unavailable": peer_error,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cfg5": cfg5,
@@ -765,8 +771,13 @@ def cfg5_leg(eng, pk, group, world, rank, n_total, sync_all, T5=300, L5=10, mix=
     if use_peer and group is not None:
         from poccala_b200.distributed import PeerExchange
 
-        peer = PeerExchange(eng, N_UNITS, N_UNITS * EMIT * mix, group)
-        es.use_peer(peer)
+        try:
+            peer = PeerExchange(eng, N_UNITS, N_UNITS * EMIT * mix, group)  # (raises on every rank or on none)
+            es.use_peer(peer)
+        except RuntimeError:
+            if use_peer != "auto":
+                raise
+            peer = None
     es.em_iteration(c_covariance=1e-3, group=group)  # warm-up (first launches, NCCL buffers); its update is kept
     if peer is not None and use_peer == "auto":
         trial = {}

@@ -80,15 +80,35 @@ class PeerExchange:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > nat.lib_const("PC_MAX_PEERS"):
             raise ValueError("at most %d ranks share an exchange" % nat.lib_const("PC_MAX_PEERS"))
+        # Every step below is followed by the collective that comes next on ALL ranks, whatever happened locally: a rank
+        # that cannot allocate, export or map a block must not leave the others waiting in a barrier.  The outcome is
+        # agreed on at the end (MIN over the ranks) and a failure is raised everywhere.
         mine = np.zeros(64, dtype=np.uint8)
-        nat.call("pc_peer_create", engine.h, self.rank, self.world, int(n_gauss), int(n_units), nat._p(mine))
+        err = None
+        try:
+            nat.call("pc_peer_create", engine.h, self.rank, self.world, int(n_gauss), int(n_units), nat._p(mine))
+        except Exception as e:  # noqa: BLE001
+            err = e
         # the handles travel through the process group (a uint8 tensor: NCCL and gloo both carry it)
-        t = torch.as_tensor(mine).to(engine.device if dist.get_backend(group) == "nccl" else "cpu")
+        on_dev = dist.get_backend(group) == "nccl"
+        t = torch.as_tensor(mine).to(engine.device if on_dev else "cpu")
         every = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(every, t, group=group)
         handles = np.ascontiguousarray(torch.stack(every).cpu().numpy())
-        nat.call("pc_peer_connect", engine.h, nat._p(handles))
-        dist.barrier(group=group)  # nobody signals into a block that is not mapped yet
+        if err is None:
+            try:
+                nat.call("pc_peer_connect", engine.h, nat._p(handles))
+            except Exception as e:  # noqa: BLE001
+                err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=engine.device if on_dev else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also the barrier: nobody signals into an unmapped block
+        if int(ok.item()) == 0:
+            try:
+                nat.call("pc_peer_destroy", engine.h)
+            except Exception:  # noqa: BLE001
+                pass
+            raise RuntimeError("peer-memory exchange unavailable (CUDA IPC between the ranks of this node): %s"
+                               % (err if err is not None else "another rank failed"))
         self.n_units, self.n_gauss = int(n_units), int(n_gauss)
         self._views = [self._wrap(w) for w in range(3)]
         self._bound = weakref.WeakSet()  # EStep objects whose statistics live in this block (EStep.use_peer)
